@@ -1,0 +1,559 @@
+// hb_capi.cu -- the C ABI of libhb_b200.so (include/hb_b200.h): context, device buffers,
+// host<->device staging and kernel launches.  No model arithmetic lives here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hb_b200.h"
+#include "hb_device.cuh"
+#include "hb_kernels.h"
+
+using namespace hb;
+
+static std::string g_error;
+static std::mutex g_error_mu;
+
+struct hb_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t global_mem = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    long launches = 0;
+
+    // observed light curve (device)
+    double *d_t = nullptr, *d_flux = nullptr, *d_w = nullptr;
+    long N = 0;
+    bool has_data = false;
+    MagSetup ms;
+
+    // per-batch work buffers, grown on demand
+    double* d_params = nullptr;
+    ChainConst* d_cc = nullptr;
+    double* d_logL = nullptr;
+    long cap_chains = 0;
+    uint64_t* d_scratch = nullptr;
+    size_t scratch_stride = 0;
+    int grid = 0;
+    int* d_counter = nullptr;
+    double* d_lc = nullptr;
+    size_t cap_lc = 0;
+    double* d_times2 = nullptr;  // hb_calc_light_curve / hb_traj time grid
+    long cap_times2 = 0;
+    double* d_small = nullptr;   // 64 doubles of scalar args / results
+    double* d_aux = nullptr;     // generic output buffer
+    size_t cap_aux = 0;
+
+    // pinned host staging
+    double* h_pin = nullptr;
+    size_t cap_pin = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int fail_cuda(hb_ctx* c, cudaError_t e, const char* what)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    c->err = buf;
+    return HB_ERR_CUDA;
+}
+int fail_arg(hb_ctx* c, const char* what)
+{
+    c->err = what;
+    return HB_ERR_ARG;
+}
+
+#define CK(call)                                                      \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);    \
+    } while (0)
+
+template <typename T>
+cudaError_t grow(T*& p, size_t& cap, size_t need)
+{
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t n = std::max(need, (size_t)64);
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+}
+
+cudaError_t grow_pin(hb_ctx* c, size_t doubles)
+{
+    if (doubles <= c->cap_pin) return cudaSuccess;
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    c->h_pin = nullptr;
+    c->cap_pin = 0;
+    cudaError_t e = cudaMallocHost((void**)&c->h_pin, doubles * sizeof(double));
+    if (e == cudaSuccess) c->cap_pin = doubles;
+    return e;
+}
+
+int ensure_chains(hb_ctx* ctx, long n)
+{
+    if (n <= ctx->cap_chains) return HB_OK;
+    long cap = std::max(n, 2 * ctx->cap_chains);
+    if (ctx->d_params) cudaFree(ctx->d_params);
+    if (ctx->d_cc) cudaFree(ctx->d_cc);
+    if (ctx->d_logL) cudaFree(ctx->d_logL);
+    ctx->d_params = nullptr; ctx->d_cc = nullptr; ctx->d_logL = nullptr; ctx->cap_chains = 0;
+    CK(cudaMalloc((void**)&ctx->d_params, (size_t)cap * NPARS * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->d_cc, (size_t)cap * sizeof(ChainConst)));
+    CK(cudaMalloc((void**)&ctx->d_logL, (size_t)cap * sizeof(double)));
+    ctx->cap_chains = cap;
+    return HB_OK;
+}
+
+// scratch: per resident CTA three key arrays of `stride` entries (template + two select buffers)
+int ensure_scratch(hb_ctx* ctx, long n_points)
+{
+    size_t stride = ((size_t)std::max(n_points, 1L) + 31) / 32 * 32;
+    if (ctx->d_scratch && stride <= ctx->scratch_stride) return HB_OK;
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_stride = 0;
+    CK(cudaMalloc((void**)&ctx->d_scratch, (size_t)ctx->grid * 3 * stride * sizeof(uint64_t)));
+    ctx->scratch_stride = stride;
+    return HB_OK;
+}
+
+// host -> device through the pinned staging buffer, on the context stream
+int upload(hb_ctx* ctx, double* dst, const double* src, size_t n)
+{
+    if (n == 0) return HB_OK;
+    CK(grow_pin(ctx, n));
+    std::memcpy(ctx->h_pin, src, n * sizeof(double));
+    CK(cudaMemcpyAsync(dst, ctx->h_pin, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // h_pin is reused
+    return HB_OK;
+}
+int download(hb_ctx* ctx, double* dst, const double* src, size_t n)
+{
+    if (n == 0) return HB_OK;
+    CK(grow_pin(ctx, n));
+    CK(cudaMemcpyAsync(ctx->h_pin, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(dst, ctx->h_pin, n * sizeof(double));
+    return HB_OK;
+}
+
+int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, const double* d_flux, const double* d_w,
+             long N, double* d_logL, double* d_lc)
+{
+    CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->stream));
+    CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_flux, d_w, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
+                         d_logL, d_lc, ctx->d_counter, ctx->stream));
+    ctx->launches += 2;
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hb_global_error(void) { return g_error.c_str(); }
+
+int hb_create(hb_ctx** out, int device)
+{
+    if (!out) return HB_ERR_ARG;
+    *out = nullptr;
+    auto set_global = [](const std::string& s) {
+        std::lock_guard<std::mutex> g(g_error_mu);
+        g_error = s;
+    };
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_global(std::string("hb_create: no CUDA device: ") + cudaGetErrorString(e));
+        return HB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_global("hb_create: device index out of range");
+        return HB_ERR_ARG;
+    }
+    hb_ctx* ctx = new hb_ctx();
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        set_global(std::string("hb_create: ") + cudaGetErrorString(e));
+        delete ctx;
+        return HB_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->global_mem = prop.totalGlobalMem;
+    if (prop.major != 10) {
+        // the library carries sm_100a code only: fail loudly instead of hitting "no kernel image"
+        char buf[256];
+        snprintf(buf, sizeof(buf), "hb_create: device %d is sm_%d%d; libhb_b200 is built for sm_100a (B200) only", device,
+                 prop.major, prop.minor);
+        set_global(buf);
+        delete ctx;
+        return HB_ERR_CUDA;
+    }
+    ctx->grid = ctx->sm_count * kEvalCtasPerSm;
+    ctx->ms.mag_data[0] = 1000.;  // mcmc_wrapper2.c:322-327
+    for (int i = 0; i < 4; i++) {
+        ctx->ms.mag_data[i + 1] = 1.;
+        ctx->ms.magerr[i] = kBig;
+    }
+    ctx->ms.use_gmag = 1;  // likelihood3.h:11-12
+    ctx->ms.use_color = 0;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_counter, sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_small, 64 * sizeof(double)) == cudaSuccess &&
+              configure_eval() == cudaSuccess;
+    if (!ok) {
+        set_global(std::string("hb_create: ") + cudaGetErrorString(cudaGetLastError()));
+        hb_destroy(ctx);
+        return HB_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return HB_OK;
+}
+
+void hb_destroy(hb_ctx* ctx)
+{
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx->device);
+        cudaDeviceSynchronize();
+        cudaFree(ctx->d_t); cudaFree(ctx->d_flux); cudaFree(ctx->d_w);
+        cudaFree(ctx->d_params); cudaFree(ctx->d_cc); cudaFree(ctx->d_logL);
+        cudaFree(ctx->d_scratch); cudaFree(ctx->d_counter); cudaFree(ctx->d_lc);
+        cudaFree(ctx->d_times2); cudaFree(ctx->d_small); cudaFree(ctx->d_aux);
+        if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    }
+    delete ctx;
+}
+
+const char* hb_last_error(const hb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+long hb_launch_count(const hb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hb_device_info(hb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, long* global_mem_mb)
+{
+    if (!ctx) return HB_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (global_mem_mb) *global_mem_mb = (long)(ctx->global_mem >> 20);
+    return HB_OK;
+}
+
+int hb_set_stream(hb_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return HB_OK;
+}
+
+int hb_sync(hb_ctx* ctx)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* err, long n)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!t || !flux || !err))) return fail_arg(ctx, "hb_set_data: null array or negative n");
+    if (n > 0x7fffff00L) return fail_arg(ctx, "hb_set_data: n too large");
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_t); cudaFree(ctx->d_flux); cudaFree(ctx->d_w);
+    ctx->d_t = ctx->d_flux = ctx->d_w = nullptr;
+    ctx->has_data = false;
+    size_t alloc = (size_t)std::max(n, 1L) * sizeof(double);
+    CK(cudaMalloc((void**)&ctx->d_t, alloc));
+    CK(cudaMalloc((void**)&ctx->d_flux, alloc));
+    CK(cudaMalloc((void**)&ctx->d_w, alloc));
+    // weights 1/max(sigma, 1e-5): the clamp of likelihood3.c:824-827 applied once at upload
+    std::vector<double> w((size_t)n);
+    for (long i = 0; i < n; i++) w[i] = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
+    int rc;
+    if ((rc = upload(ctx, ctx->d_t, t, (size_t)n)) != HB_OK) return rc;
+    if ((rc = upload(ctx, ctx->d_flux, flux, (size_t)n)) != HB_OK) return rc;
+    if ((rc = upload(ctx, ctx->d_w, w.data(), (size_t)n)) != HB_OK) return rc;
+    ctx->N = n;
+    if ((rc = ensure_scratch(ctx, n)) != HB_OK) return rc;
+    ctx->has_data = true;
+    return HB_OK;
+}
+
+int hb_set_mags(hb_ctx* ctx, const double* mag_data, const double* magerr, int use_gmag, int use_color)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!mag_data || !magerr) return fail_arg(ctx, "hb_set_mags: null array");
+    for (int i = 0; i < 5; i++) ctx->ms.mag_data[i] = mag_data[i];
+    for (int i = 0; i < 4; i++) ctx->ms.magerr[i] = magerr[i];
+    ctx->ms.use_gmag = use_gmag ? 1 : 0;
+    ctx->ms.use_color = use_color ? 1 : 0;
+    return HB_OK;
+}
+
+int hb_loglikelihood_batch_dev(hb_ctx* ctx, const double* d_params, long n_chains, double* d_logL)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_data) {
+        ctx->err = "hb_loglikelihood_batch_dev: hb_set_data has not been called";
+        return HB_ERR_STATE;
+    }
+    if (n_chains < 0 || (n_chains > 0 && (!d_params || !d_logL))) return fail_arg(ctx, "hb_loglikelihood_batch_dev: bad argument");
+    if (n_chains == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
+    return run_eval(ctx, d_params, n_chains, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, d_logL, nullptr);
+}
+
+int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, double* logL)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_data) {
+        ctx->err = "hb_loglikelihood_batch: hb_set_data has not been called";
+        return HB_ERR_STATE;
+    }
+    if (n_chains < 0 || (n_chains > 0 && (!params || !logL))) return fail_arg(ctx, "hb_loglikelihood_batch: bad argument");
+    if (n_chains == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
+    const size_t np = (size_t)n_chains * NPARS;
+    CK(grow_pin(ctx, np));
+    std::memcpy(ctx->h_pin, params, np * sizeof(double));
+    CK(cudaMemcpyAsync(ctx->d_params, ctx->h_pin, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, ctx->d_logL, nullptr)) != HB_OK)
+        return rc;
+    // the D2H lands in the head of the pinned buffer; stream order keeps it after the H2D read
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_logL, (size_t)n_chains * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(logL, ctx->h_pin, (size_t)n_chains * sizeof(double));
+    return HB_OK;
+}
+
+int hb_light_curve_batch(hb_ctx* ctx, const double* params, long n_chains, double* templates)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_data) {
+        ctx->err = "hb_light_curve_batch: hb_set_data has not been called";
+        return HB_ERR_STATE;
+    }
+    if (n_chains < 0 || (n_chains > 0 && (!params || !templates))) return fail_arg(ctx, "hb_light_curve_batch: bad argument");
+    if (n_chains == 0 || ctx->N == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
+    CK(grow(ctx->d_lc, ctx->cap_lc, (size_t)n_chains * (size_t)ctx->N));
+    if ((rc = upload(ctx, ctx->d_params, params, (size_t)n_chains * NPARS)) != HB_OK) return rc;
+    if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, nullptr, nullptr, ctx->N, nullptr, ctx->d_lc)) != HB_OK) return rc;
+    return download(ctx, templates, ctx->d_lc, (size_t)n_chains * (size_t)ctx->N);
+}
+
+static int stage_times(hb_ctx* ctx, const double* times, long nt)
+{
+    if (nt > ctx->cap_times2) {
+        if (ctx->d_times2) cudaFree(ctx->d_times2);
+        ctx->d_times2 = nullptr;
+        ctx->cap_times2 = 0;
+        CK(cudaMalloc((void**)&ctx->d_times2, (size_t)nt * sizeof(double)));
+        ctx->cap_times2 = nt;
+    }
+    return upload(ctx, ctx->d_times2, times, (size_t)nt);
+}
+
+int hb_calc_light_curve(hb_ctx* ctx, const double* times, long nt, const double* pars, double* tmpl)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nt < 0 || !pars || (nt > 0 && (!times || !tmpl))) return fail_arg(ctx, "hb_calc_light_curve: bad argument");
+    if (nt == 0) return HB_OK;
+    if (nt > 0x7fffff00L) return fail_arg(ctx, "hb_calc_light_curve: nt too large");
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, 1)) != HB_OK) return rc;
+    if ((rc = ensure_scratch(ctx, nt)) != HB_OK) return rc;
+    if ((rc = stage_times(ctx, times, nt)) != HB_OK) return rc;
+    CK(grow(ctx->d_lc, ctx->cap_lc, (size_t)nt));
+    if ((rc = upload(ctx, ctx->d_params, pars, NPARS)) != HB_OK) return rc;
+    if ((rc = run_eval(ctx, ctx->d_params, 1, ctx->d_times2, nullptr, nullptr, nt, nullptr, ctx->d_lc)) != HB_OK) return rc;
+    return download(ctx, tmpl, ctx->d_lc, (size_t)nt);
+}
+
+int hb_chain_info_batch(hb_ctx* ctx, const double* params, long n_chains, double D, double* out)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n_chains < 0 || (n_chains > 0 && (!params || !out))) return fail_arg(ctx, "hb_chain_info_batch: bad argument");
+    if (n_chains == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
+    CK(grow(ctx->d_aux, ctx->cap_aux, (size_t)n_chains * 9));
+    if ((rc = upload(ctx, ctx->d_params, params, (size_t)n_chains * NPARS)) != HB_OK) return rc;
+    MagSetup ms = ctx->ms;
+    ms.mag_data[0] = D;
+    CK(launch_prologue(ctx->d_params, (int)n_chains, ms, ctx->d_cc, ctx->stream));
+    CK(launch_chain_info(ctx->d_cc, (int)n_chains, ctx->d_aux, ctx->stream));
+    ctx->launches += 2;
+    return download(ctx, out, ctx->d_aux, (size_t)n_chains * 9);
+}
+
+int hb_traj(hb_ctx* ctx, const double* times, long nt, const double* traj_pars, double* d_arr, double* Z1_arr,
+            double* Z2_arr, double* rr_arr, double* ff_arr)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nt < 0 || !traj_pars || (nt > 0 && (!times || !d_arr || !Z1_arr || !Z2_arr || !rr_arr || !ff_arr)))
+        return fail_arg(ctx, "hb_traj: bad argument");
+    if (nt == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = stage_times(ctx, times, nt)) != HB_OK) return rc;
+    CK(grow(ctx->d_aux, ctx->cap_aux, (size_t)nt * 5));
+    if ((rc = upload(ctx, ctx->d_small, traj_pars, 7)) != HB_OK) return rc;
+    double* o = ctx->d_aux;
+    CK(launch_traj(ctx->d_times2, (int)nt, ctx->d_small, o, o + nt, o + 2 * nt, o + 3 * nt, o + 4 * nt, ctx->stream));
+    ctx->launches += 1;
+    std::vector<double> h((size_t)nt * 5);
+    if ((rc = download(ctx, h.data(), o, (size_t)nt * 5)) != HB_OK) return rc;
+    std::memcpy(d_arr, h.data(), nt * sizeof(double));
+    std::memcpy(Z1_arr, h.data() + nt, nt * sizeof(double));
+    std::memcpy(Z2_arr, h.data() + 2 * nt, nt * sizeof(double));
+    std::memcpy(rr_arr, h.data() + 3 * nt, nt * sizeof(double));
+    std::memcpy(ff_arr, h.data() + 4 * nt, nt * sizeof(double));
+    return HB_OK;
+}
+
+int hb_order_statistic(hb_ctx* ctx, const double* x, long n, long k, double* out)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!x || !out || n <= 0 || k < 0 || k >= n || n > 0x7fffff00L) return fail_arg(ctx, "hb_order_statistic: bad argument");
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_scratch(ctx, n)) != HB_OK) return rc;
+    if ((rc = stage_times(ctx, x, n)) != HB_OK) return rc;
+    CK(launch_order_stat(ctx->d_times2, (int)n, (int)k, ctx->d_scratch, ctx->scratch_stride, ctx->d_small + 48, ctx->stream));
+    ctx->launches += 1;
+    double r[2];
+    if ((rc = download(ctx, r, ctx->d_small + 48, 2)) != HB_OK) return rc;
+    *out = r[0];
+    return HB_OK;
+}
+
+int hb_scalar(hb_ctx* ctx, int op, const double* args, int nargs, double* out)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    static const int need[9] = {1, 1, 1, 1, 1, 3, 8, 11, 9};
+    if (op < 0 || op > 8 || !args || !out || nargs != need[op]) return fail_arg(ctx, "hb_scalar: bad op / argument count");
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = upload(ctx, ctx->d_small, args, (size_t)nargs)) != HB_OK) return rc;
+    CK(launch_scalar(op, ctx->d_small, ctx->d_small + 32, ctx->stream));
+    ctx->launches += 1;
+    return download(ctx, out, ctx->d_small + 32, 1);
+}
+
+int hb_gaia_batch(hb_ctx* ctx, const double* p6, long n, double D, const double* data, const double* err, double* mags,
+                  double* logL)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && !p6) || (logL && (!data || !err))) return fail_arg(ctx, "hb_gaia_batch: bad argument");
+    if (n == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    CK(grow(ctx->d_aux, ctx->cap_aux, (size_t)n * 11));
+    double* d_p = ctx->d_aux;
+    double* d_m = d_p + (size_t)n * 6;
+    double* d_l = d_m + (size_t)n * 4;
+    if ((rc = upload(ctx, d_p, p6, (size_t)n * 6)) != HB_OK) return rc;
+    if (logL) {
+        double de[8];
+        for (int i = 0; i < 4; i++) { de[i] = data[i]; de[4 + i] = err[i]; }
+        if ((rc = upload(ctx, ctx->d_small, de, 8)) != HB_OK) return rc;
+    }
+    CK(launch_gaia(d_p, (int)n, D, ctx->d_small, ctx->d_small + 4, mags ? d_m : nullptr, logL ? d_l : nullptr, ctx->stream));
+    ctx->launches += 1;
+    if (mags && (rc = download(ctx, mags, d_m, (size_t)n * 4)) != HB_OK) return rc;
+    if (logL && (rc = download(ctx, logL, d_l, (size_t)n)) != HB_OK) return rc;
+    return HB_OK;
+}
+
+int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops)
+{
+    if (!ctx || !tflops) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    const int blocks = ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int iters = 2000;
+    double best = 0.;
+    double total_s = 0.;
+    if (seconds_target <= 0) seconds_target = 0.2;
+    for (int rep = 0; rep < 64 && total_s < seconds_target; rep++) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        CK(launch_fp64_peak(ctx->d_small + 40, blocks, iters, ctx->stream));
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        ctx->launches += 1;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)blocks * 256.0 * (double)iters * 32.0 * 2.0;
+        const double tf = flops / (ms * 1e-3) * 1e-12;
+        if (rep > 0) best = std::max(best, tf);  // first launch is warm-up
+        total_s += ms * 1e-3;
+        if (ms < 20.f) iters *= 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// hb_device.cuh -- device-side model of the heartbeat-star light curve (sm_100a, FP64).
+//
+// What is computed follows the reference (paths relative to /root/reference/src):
+//   likelihood3.c:125-185  traj           -> kepler_point()  (phase, fmod, starter, 5 Newton steps)
+//   likelihood3.c:224-337  beaming/ellipsoidal/reflection -> folded into 12 per-chain
+//                          coefficients by chain_prologue(), evaluated by raw_flux()
+//   likelihood3.c:353-389  eclipse_area   -> eclipse_area_dev()
+//   likelihood3.c:396-507,693-717 stellar relations -> dev_getT/_getR/...
+//   likelihood3.c:725-795  calc_mags, GAIA_mcmc.c:198-250 get_mags -> two_bb_mags()
+//   likelihood3.c:945-974  RocheOverflow  -> roche_overflow_dev()
+// HOW it is computed is not the reference's: everything that does not depend on the time
+// sample is hoisted into ChainConst once per chain, the true anomaly is never formed
+// (cos/sin nu come algebraically from cos/sin E), the harmonics of omega+nu come from
+// Chebyshev recurrences, and star 2 (omega+pi) reuses star 1's harmonics with signs.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr int NPARS = 21;  // likelihood3.h:20
+
+// physical constants, likelihood3.h:4-10,31
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 2.0 * 3.14159265358979323846;  // == fl(2*PI) used by fmod(M, 2*PI)
+constexpr double kG = 6.6743e-8;
+constexpr double kC = 2.998e10;
+constexpr double kMsun = 1.9885e33;
+constexpr double kRsun = 6.955e10;
+constexpr double kSecDay = 86400.0;
+constexpr double kBig = 1.e15;
+
+// Per-chain folded constants (written by chain_prologue, read by the point kernels).
+struct ChainConst {
+    // orbit
+    double e, sq1me2;  // eccentricity, sqrt(1-e^2)
+    double T0s, Ps;    // T0*86400, P[s]  (exactly the reference's T0_cgs / P_cgs)
+    double cw, sw;     // cos/sin omega0
+    double ci, si;     // cos/sin inc
+    double ar;         // a / RSUN
+    // raw flux u = K0 + K1 c + b^2 (a0 + a1 s + a2 c2 + b (b0 + b1 c2 + b (c1 s + c3 s3 + b (d0 + d2 c2 + d4 c4))))
+    double K0, K1, a0, a1, a2, b0, b1, c1, c3, d0, d2, d4;
+    // eclipse (radii in Rsun, sorted big/small as eclipse_area does)
+    double Rb, Rs, ecl1, ecl2;  // ecl_k = Norm_k / (pi R_k^2)
+    // normalisation: model = A (u - median) + ft,  A = ft (1 - blending)
+    double blend, ft;
+    // per-chain additive chi^2 (Gaia magnitude / colour terms) and flags
+    double chi2_extra;
+    double flag;  // bit 0: Roche overflow, bit 1: model is NaN by construction (e >= 1 or NaN e)
+    // diagnostics (hb_chain_info): R1 R2 T1 T2 G B-V V-G G-T
+    double info[8];
+};
+
+struct MagSetup {
+    double mag_data[5];  // D, G, B-V, V-G, G-T   (mcmc_wrapper2.c:302-317)
+    double magerr[4];
+    int use_gmag, use_color;  // likelihood3.h:11-12 made runtime
+};
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// ---------------------------------------------------------------------------
+// stellar relations (likelihood3.c:396-507)
+// ---------------------------------------------------------------------------
+__device__ inline double interp_nodes(double m, const double* mn, const double* yn, int n)
+{
+    if (m <= mn[0]) return yn[0];
+    if (m >= mn[n - 1]) return yn[n - 1];
+    double r = yn[n - 1];
+    for (int j = 1; j < n; j++) {
+        if (m < mn[j]) {
+            r = yn[j - 1] + (m - mn[j - 1]) * (yn[j] - yn[j - 1]) / (mn[j] - mn[j - 1]);
+            break;
+        }
+    }
+    return r;
+}
+
+__device__ inline double dev_getT(double logM)
+{
+    const double mn[16] = {0.1, 0.26, 0.47, 0.59, 0.69, 0.87, 0.98, 1.085, 1.4, 1.65, 2.0, 2.5, 3.0, 4.4, 15., 40.};
+    const double tn[16] = {3.491, 3.531, 3.547, 3.584, 3.644, 3.712, 3.745, 3.774,
+                           3.823, 3.863, 3.913, 3.991, 4.057, 4.182, 4.477, 4.623};
+    return interp_nodes(pow(10., logM), mn, tn, 16);
+}
+
+__device__ inline double dev_getR(double logM)
+{
+    const double mn[10] = {0.07, 0.2, 0.356, 0.655, 0.784, 0.787, 1.377, 4.4, 15., 40.};
+    const double rn[10] = {-0.953, -0.627, -0.423, -0.154, -0.082, -0.087, 0.295, 0.477, 0.792, 1.041};
+    return interp_nodes(pow(10., logM), mn, rn, 10);
+}
+
+__device__ inline double dev_envelope_temp(double) { return 0.0224; }
+
+__device__ inline double dev_envelope_radius(double logM)
+{
+    const double n = 4.22, slope = 15.68, floor_ = 0.01, corner = 1.055, ceil_ = 0.17;
+    double m = pow(10., logM);
+    return 1 / (1 / ceil_ + 1 / (slope * pow((pow(m, n) + pow(corner, n)), (1 / n)) - (slope * corner - floor_)));
+}
+
+__device__ inline double dev_alpha_beam(double logT)  // likelihood3.c:194-209
+{
+    const double al[4] = {6.5, 4.0, 2.5, 1.2};
+    const double lt[4] = {3.5, 3.7, 3.9, 4.5};
+    if (logT >= lt[3]) return 1.2 / 4;
+    if (logT < lt[0]) return 6.5 / 4;
+    int j = 3;
+    while (logT < lt[j]) j--;
+    return ((al[j + 1] + (al[j + 1] - al[j]) / (lt[j + 1] - lt[j]) * (logT - lt[j + 1])) / 4);
+}
+
+// likelihood3.c:760-789 (gaia == 0: exp()-1 and /(1-blending)) and GAIA_mcmc.c:214-249
+// (gaia == 1: expm1, no blending).  out = {G, B-V, V-G, G-T}
+__device__ inline void two_bb_mags(double R1, double R2, double T1, double T2, double D, double blending, int gaia,
+                                   double out[4])
+{
+    const double lam[4] = {442, 540, 673, 750};
+    const double h = 6.626e-27, k = 1.38e-16, pc = 3.086e18;
+    double mag[4];
+    R1 *= kRsun;
+    R2 *= kRsun;
+    for (int j = 0; j < 4; j++) {
+        double nu = kC / (lam[j] * 1e-7);
+        double pl = 2. * h * (nu * nu * nu) / sq(kC);
+        double f;
+        if (!gaia) {
+            f = kPi * (R1 * R1 * (pl / (exp(h * nu / (k * T1)) - 1.)) + R2 * R2 * (pl / (exp(h * nu / (k * T2)) - 1.))) /
+                (sq(D) * sq(pc));
+            f = f / (1 - blending);
+        } else {
+            f = kPi * (sq(R1) * (pl / expm1(h * nu / (k * T1))) + sq(R2) * (pl / expm1(h * nu / (k * T2)))) /
+                (sq(D) * sq(pc));
+        }
+        mag[j] = -2.5 * log10(f) - 48.6;
+    }
+    out[0] = mag[2];
+    out[1] = mag[0] - mag[1];
+    out[2] = mag[1] - mag[2];
+    out[3] = mag[2] - mag[3];
+}
+
+__device__ inline double eggleton_dev(double q)  // likelihood3.c:945-948
+{
+    double q23 = pow(q, 2. / 3);
+    return 0.49 * q23 / (0.6 * q23 + log(1 + pow(q, 1. / 3)));
+}
+
+// ---------------------------------------------------------------------------
+// chain prologue: everything that does not depend on the time sample
+// ---------------------------------------------------------------------------
+__device__ inline void chain_prologue(const double* __restrict__ p, const MagSetup& ms, ChainConst& cc)
+{
+    const double logM1 = p[0], logM2 = p[1];
+    const double Pd = pow(10., p[2]);
+    const double e = p[3], inc = p[4], omega0 = p[5], T0 = p[6];
+    const double mu[2] = {p[9], p[11]}, tau[2] = {p[10], p[12]};
+    const double aref[2] = {p[13], p[14]};
+    const double blending = p[19], ft = p[20];
+
+    const double M[2] = {pow(10., logM1), pow(10., logM2)};
+    // radii / temperatures (likelihood3.c:693-717)
+    const double R[2] = {pow(10., dev_getR(logM1) + p[7] * dev_envelope_radius(logM1)),
+                         pow(10., dev_getR(logM2) + p[8] * dev_envelope_radius(logM2))};
+    const double Te[2] = {pow(10., dev_getT(logM1) + p[17] * dev_envelope_temp(logM1)),
+                          pow(10., dev_getT(logM2) + p[18] * dev_envelope_temp(logM2))};
+    // luminosity fractions (likelihood3.c:612-614)
+    const double L1 = sq(R[0]) * sq(sq(Te[0])), L2 = sq(R[1]) * sq(sq(Te[1]));
+    const double Nrm[2] = {L1 / (L1 + L2), L2 / (L1 + L2)};
+    // beaming alphas (likelihood3.c:617-624)
+    const double ab[2] = {dev_alpha_beam(log10(Te[0])) * exp(p[15]), dev_alpha_beam(log10(Te[1])) * exp(p[16])};
+
+    double si, ci, sw, cw;
+    sincos(inc, &si, &ci);
+    sincos(omega0, &sw, &cw);
+    const double si2 = si * si, si3 = si2 * si, si4 = si2 * si2;
+    const double ome2 = 1 - sq(e);
+
+    cc.e = e;
+    cc.sq1me2 = sqrt(ome2);
+    cc.T0s = T0 * kSecDay;
+    cc.Ps = Pd * kSecDay;
+    cc.cw = cw;
+    cc.sw = sw;
+    cc.ci = ci;
+    cc.si = si;
+    // semi-major axis as traj() forms it (likelihood3.c:141-142)
+    {
+        const double Mtot = M[0] * kMsun + M[1] * kMsun;
+        const double a = pow(kG * Mtot * sq(cc.Ps) / sq(2 * kPi), 1. / 3.);
+        cc.ar = a / kRsun;
+    }
+
+    const double ppm = 1.e-6;
+    const double Pm13 = pow(Pd, -1. / 3), Pm43 = pow(Pd, -4. / 3), Pm83 = pow(Pd, -8. / 3), Pm103 = pow(Pd, -10. / 3);
+    const double Prot = Pd * pow(1 - e, 3. / 2);
+
+    double K0 = 0, K1 = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, c1 = 0, c3 = 0, d0 = 0, d2 = 0, d4 = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double Ma = M[k], Mb = M[1 - k];
+        const double Rs = R[k], Ro = R[1 - k];  // own radius (ellipsoidal), companion radius (reflection)
+        const double sgn = (k == 0) ? 1.0 : -1.0;  // star 2 sees omega0 + pi: odd harmonics flip
+        const double N = Nrm[k];
+        const double q = Mb / Ma;
+        // beaming, likelihood3.c:224-236 (pow(1+q, 2/3) == 1, quirk Q1)
+        const double B = -2830. * ab[k] * q * pow(Ma, 1. / 3) * Pm13 * si / cc.sq1me2 * ppm;
+        // ellipsoidal coefficient set, likelihood3.c:258-264
+        const double al11 = 15 * mu[k] * (2 + tau[k]) / (32 * (3 - mu[k]));
+        const double al21 = 3 * (15 + mu[k]) * (1 + tau[k]) / (20 * (3 - mu[k]));
+        const double al2b1 = 15 * (1 - mu[k]) * (3 + tau[k]) / (64 * (3 - mu[k]));
+        const double al01 = al21 / 9, al0b1 = 3 * al2b1 / 20, al31 = 5 * al11 / 3, al41 = 7 * al2b1 / 4;
+        const double R3 = Rs * Rs * Rs, R4 = R3 * Rs, R5 = R4 * Rs;
+        const double qq = q / (1 + q);
+        const double Mm53 = pow(Ma, -5. / 3) * q / pow(1 + q, 5. / 3) * Pm103;  // order-5 common factor
+        const double Mm43 = pow(Ma, -4. / 3) * q / pow(1 + q, 4. / 3) * Pm83;   // order-4 common factor
+        const double AM1 = 13435. * 2 * al01 * (2 - 3 * si2) / Ma / sq(Prot) * R3 * ppm;
+        const double AM2 = 13435. * 3 * al01 * (2 - 3 * si2) / Ma * qq / sq(Pd) * R3 * ppm;       // x beta^3
+        const double C21 = 13435. * al21 * si2 / Ma * qq / sq(Pd) * R3 * ppm;                     // x beta^3 cos2x
+        const double AM3 = 759. * al0b1 * (8 - 40 * si2 + 35 * si4) * Mm53 * R5 * ppm;            // x beta^5
+        const double S1 = 3194. * al11 * (4 * si - 5 * si3) * Mm43 * R4 * ppm;                    // x beta^4 sin x
+        const double C22 = 759. * al2b1 * (6 * si2 - 7 * si4) * Mm53 * R5 * ppm;                  // x beta^5 cos2x
+        const double S3 = 3194. * al31 * si3 * Mm43 * R4 * ppm;                                   // x beta^4 sin3x
+        const double C4 = 759. * al41 * si4 * Mm53 * R5 * ppm;                                    // x beta^5 cos4x
+        // reflection, likelihood3.c:322-337
+        const double Rf = 56514. * aref[k] * pow(1 + q, -2. / 3) * pow(Ma, -2. / 3) * Pm43 * sq(Ro) * ppm;  // x beta^2
+
+        K0 += N * (1 + AM1);
+        K1 += sgn * N * B;
+        a0 += N * Rf * (0.64 + 0.18 * si2);
+        a1 += -sgn * N * Rf * si;
+        a2 += -N * Rf * 0.18 * si2;
+        b0 += N * AM2;
+        b1 += N * C21;
+        c1 += sgn * N * S1;
+        c3 += sgn * N * S3;
+        d0 += N * AM3;
+        d2 += N * C22;
+        d4 += N * C4;
+    }
+    cc.K0 = K0; cc.K1 = K1; cc.a0 = a0; cc.a1 = a1; cc.a2 = a2; cc.b0 = b0; cc.b1 = b1;
+    cc.c1 = c1; cc.c3 = c3; cc.d0 = d0; cc.d2 = d2; cc.d4 = d4;
+
+    cc.Rb = fmax(R[0], R[1]);
+    cc.Rs = fmin(R[0], R[1]);
+    cc.ecl1 = Nrm[0] / (kPi * sq(R[0]));
+    cc.ecl2 = Nrm[1] / (kPi * sq(R[1]));
+    cc.blend = blending;
+    cc.ft = ft;
+
+    // Gaia magnitude / colour chi^2 terms (likelihood3.c:834-860)
+    double mags[4];
+    two_bb_mags(R[0], R[1], Te[0], Te[1], ms.mag_data[0], blending, 0, mags);
+    double extra = 0.;
+    if (ms.use_gmag) {
+        double r = (mags[0] - ms.mag_data[1]) / ms.magerr[0];
+        extra += r * r;
+    }
+    if (ms.use_color) {
+        for (int i = 1; i < 4; i++) {
+            double r = (mags[i] - ms.mag_data[i + 1]) / ms.magerr[i];
+            extra += r * r;
+        }
+    }
+    cc.chi2_extra = extra;
+
+    // Roche overflow (likelihood3.c:953-974)
+    int roche;
+    {
+        const double M1 = M[0] * kMsun, M2 = M[1] * kMsun;
+        const double q = M1 / M2;
+        const double sep = pow(kG * (M1 + M2) * sq(cc.Ps) / (4.0 * kPi * kPi), 1. / 3.);
+        const double r1 = R[0] * kRsun / (sep * (1 - e));
+        const double r2 = R[1] * kRsun / (sep * (1 - e));
+        roche = ((eggleton_dev(q) < r1) || (eggleton_dev(1 / q) < r2)) ? 1 : 0;
+    }
+    // e >= 1 (reachable, quirk Q4) or NaN e: the reference's template is NaN at every sample
+    const int nan_model = !(e < 1.0) ? 1 : 0;
+    cc.flag = (double)(roche | (nan_model << 1));
+
+    cc.info[0] = R[0]; cc.info[1] = R[1]; cc.info[2] = Te[0]; cc.info[3] = Te[1];
+    cc.info[4] = mags[0]; cc.info[5] = mags[1]; cc.info[6] = mags[2]; cc.info[7] = mags[3];
+}
+
+// ---------------------------------------------------------------------------
+// per-sample pieces
+// ---------------------------------------------------------------------------
+
+// Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153).  One truncated
+// quotient + one exact FMA remainder; the quotient is corrected when it is off by one.
+__device__ __forceinline__ double fmod_twopi(double M)
+{
+    const double y = kTwoPi;
+    const double am = fabs(M);
+    if (!(am < 1.0e15)) return fmod(M, y);  // huge / inf / NaN: library path
+    double q = trunc(am * (1.0 / y));
+    double r = fma(-q, y, am);
+    const double adj = (r < 0.0) ? -1.0 : ((r >= y) ? 1.0 : 0.0);
+    q += adj;
+    r = fma(-q, y, am);  // exact: 0 <= r < y is representable
+    return copysign(r, M);
+}
+
+struct OrbitPoint {
+    double cE, sE, den;  // cos E, sin E, 1 - e cos E
+};
+
+// likelihood3.c:149-160: mean anomaly in the reference's operation order (non-contracted),
+// starter E0 = M + 0.85 e sign(sin M), exactly five Newton steps.
+__device__ __forceinline__ OrbitPoint kepler_point(double t, const double e, const double T0s, const double Ps)
+{
+    const double tsec = __dmul_rn(t, kSecDay);
+    double M = __ddiv_rn(__dmul_rn(kTwoPi, __dsub_rn(tsec, T0s)), Ps);
+    M = fmod_twopi(M);
+    // sign(sin M) for |M| < fl(2 pi): positive on (0, fl(pi)], negative above (sin(fl(pi)) > 0)
+    const double am = fabs(M);
+    double sg = (am <= kPi) ? 1.0 : -1.0;
+    sg = (M < 0.0) ? -sg : sg;
+    sg = (am == 0.0) ? 0.0 : sg;
+    double E = M + (0.85 * e) * sg;
+    double sE, cE;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        sincos(E, &sE, &cE);
+        const double num = __dsub_rn(__dsub_rn(E, __dmul_rn(e, sE)), M);
+        const double den = __dsub_rn(1.0, __dmul_rn(e, cE));
+        E = __dsub_rn(E, __ddiv_rn(num, den));
+    }
+    sincos(E, &sE, &cE);
+    OrbitPoint o;
+    o.cE = cE;
+    o.sE = sE;
+    o.den = __dsub_rn(1.0, __dmul_rn(e, cE));
+    return o;
+}
+
+// likelihood3.c:353-389 with R1 >= R2 already sorted and d already in Rsun.  Written with
+// explicitly rounded (never FMA-contracted) operations in the reference's order: at the
+// contact points (d == dc, d == R1 +- R2) h/R reaches 1 and a differently rounded h_sq
+// would turn asin() into NaN where the reference is finite (quirk Q10).  Only in-eclipse
+// samples come here, so the few extra instructions are free.
+static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, double d)
+{
+    const double R1s = __dmul_rn(R1, R1), R2s = __dmul_rn(R2, R2);
+    double area = 0.;
+    const double dc = sqrt(__dsub_rn(R1s, R2s));
+    const double sum = __dadd_rn(R1, R2), dif = __dsub_rn(R1, R2);
+    const double full = __dmul_rn(__dmul_rn(kPi, R2), R2);
+    if (d < dif) area = full;
+    const bool partial_out = (d > dc) & (d < sum);
+    const bool partial_in = (d <= dc) & (d >= dif);
+    if (partial_out | partial_in) {
+        const double dd = __dmul_rn(d, d);
+        const double four_dd = __dmul_rn(__dmul_rn(4., d), d);
+        const double a = __dmul_rn(__dmul_rn(four_dd, R1), R1);                 // 4 d d R1 R1
+        const double b = __dadd_rn(__dsub_rn(dd, R2s), R1s);                    // d d - R2 R2 + R1 R1
+        const double h_sq = __ddiv_rn(__dsub_rn(a, __dmul_rn(b, b)), four_dd);
+        const double h = sqrt(h_sq);
+        const double hh = __dmul_rn(h, h);
+        const double A1 = __dsub_rn(__dmul_rn(R1s, asin(__ddiv_rn(h, R1))), __dmul_rn(h, sqrt(__dsub_rn(R1s, hh))));
+        const double A2 = __dsub_rn(__dmul_rn(R2s, asin(__ddiv_rn(h, R2))), __dmul_rn(h, sqrt(__dsub_rn(R2s, hh))));
+        area = partial_out ? __dadd_rn(A1, A2) : __dsub_rn(full, __dadd_rn(-A1, A2));
+    }
+    return area;
+}
+
+// Raw (un-normalised) template value Amag1 + Amag2 of likelihood3.c:649-675 at one sample.
+__device__ __forceinline__ double raw_flux(const ChainConst& cc, double t)
+{
+    const OrbitPoint o = kepler_point(t, cc.e, cc.T0s, cc.Ps);
+    const double beta = 1.0 / o.den;  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
+    const double cnu = (o.cE - cc.e) * beta;
+    const double snu = cc.sq1me2 * o.sE * beta;
+    const double c = cc.cw * cnu - cc.sw * snu;  // cos(omega0 + nu)
+    const double s = cc.sw * cnu + cc.cw * snu;  // sin(omega0 + nu)
+    const double c2 = fma(2.0 * c, c, -1.0);     // cos 2x
+    const double s3 = s * fma(-4.0 * s, s, 3.0); // sin 3x
+    const double c4 = fma(2.0 * c2, c2, -1.0);   // cos 4x
+
+    const double P5 = fma(cc.d4, c4, fma(cc.d2, c2, cc.d0));
+    const double P4 = fma(cc.c3, s3, cc.c1 * s);
+    const double P3 = fma(cc.b1, c2, cc.b0);
+    const double P2 = fma(cc.a2, c2, fma(cc.a1, s, cc.a0));
+    const double poly = fma(beta, fma(beta, fma(beta, P5, P4), P3), P2);
+    double u = fma(beta * beta, poly, fma(cc.K1, c, cc.K0));
+
+    // eclipse: projected separation in Rsun (likelihood3.c:173-176, 365)
+    const double sc = s * cc.ci;
+    const double proj2 = fma(c, c, sc * sc);
+    const double rr = cc.ar * o.den;
+    const double d2 = rr * rr * proj2;
+    const double lim = cc.Rb + cc.Rs;
+    if (d2 < lim * lim * (1.0 + 1e-9)) {
+        const double d = fabs(rr * sqrt(proj2));
+        if (!(d >= lim)) {
+            const double area = eclipse_area_dev(cc.Rb, cc.Rs, d);
+            const double zz = s * cc.si;  // sign of ZZ (likelihood3.c:173,669-670)
+            if (zz < 0.0) u -= area * cc.ecl2;
+            else if (zz > 0.0) u -= area * cc.ecl1;
+        }
+    }
+    return u;
+}
+
+// likelihood3.c:681-685 in the reference's order: ((u - med) + 1) blended, times flux_tune
+__device__ __forceinline__ double finish_template(double u, double med, double blend, double ft)
+{
+    double v = __dadd_rn(__dsub_rn(u, med), 1.0);
+    return __dmul_rn(__dadd_rn(blend, __dmul_rn(v, __dsub_rn(1.0, blend))), ft);
+}
+
+}  // namespace hb

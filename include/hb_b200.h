@@ -1,0 +1,100 @@
+/*
+ * hb_b200.h -- C ABI of libhb_b200.so: the B200 (sm_100a) replacement for the hot path of
+ * sidruns30/HB_MCMC -- the light-curve model + chi^2 log-likelihood of likelihood3.c evaluated
+ * for every chain / temperature rung of the parallel-tempering driver mcmc_wrapper2.c.
+ *
+ * Plain C, caller-owned buffers, `int` status codes (0 = HB_OK).  No torch / C++ types cross
+ * this boundary.  File:line citations are into the reference tree (/root/reference/src).
+ *
+ * Parameter vector (21 doubles per chain, likelihood3.c:533-578):
+ *   0 logM1  1 logM2  2 logP[d]  3 e  4 inc  5 omega0  6 T0[d]  7 rr1  8 rr2  9 mu1  10 tau1
+ *   11 mu2  12 tau2  13 alpha_ref1  14 alpha_ref2  15 ln xbeam1  16 ln xbeam2  17 aTeff1
+ *   18 aTeff2  19 blending  20 flux_tune
+ *
+ * There is no CPU fallback: every entry point that computes runs on the device and fails
+ * with HB_ERR_CUDA when no sm_100 device / driver is usable.
+ */
+#ifndef HB_B200_H
+#define HB_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_NPARS 21 /* likelihood3.h:20 */
+
+enum {
+    HB_OK = 0,
+    HB_ERR_ARG = 1,   /* bad argument (NULL, negative size, data not set) */
+    HB_ERR_CUDA = 2,  /* CUDA runtime error; text in hb_last_error() */
+    HB_ERR_STATE = 3  /* call order (e.g. likelihood before hb_set_data) */
+};
+
+typedef struct hb_ctx hb_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+/* One context per device / host thread group.  Calls on one context are serialised by an
+ * internal mutex, so the reference's 25 OpenMP threads (mcmc_wrapper2.c:78-83,383) may share it. */
+int hb_create(hb_ctx** out, int device);
+void hb_destroy(hb_ctx* ctx);
+const char* hb_last_error(const hb_ctx* ctx); /* valid until the next call on ctx */
+const char* hb_global_error(void);            /* error text when hb_create itself failed */
+int hb_device_info(hb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, long* global_mem_mb);
+/* Use an existing CUDA stream (e.g. torch's current stream) for all work of this context;
+ * NULL restores the context's own stream. */
+int hb_set_stream(hb_ctx* ctx, void* cuda_stream);
+int hb_sync(hb_ctx* ctx);
+
+/* ---- data ------------------------------------------------------------------------------ */
+/* Upload the observed light curve once (mcmc_wrapper2.c:257-298: t_data, a_data, e_data).
+ * err[] is clamped to >= 1e-5 in the DEVICE copy (likelihood3.c:824-827, quirk Q2); the host
+ * array is left untouched -- the shim below reproduces the in-place side effect. */
+int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* err, long n);
+/* mag_data[5] = {D, G, B-V, V-G, G-T}, magerr[4] (mcmc_wrapper2.c:302-328); use_gmag/use_color
+ * are likelihood3.h:11-12 made runtime.  Defaults: {1000,1,1,1,1}, {1e15 x4}, 1, 0. */
+int hb_set_mags(hb_ctx* ctx, const double* mag_data, const double* magerr, int use_gmag, int use_color);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* logL[c] = loglikelihood(t, flux, err, N, params[c], mag_data, magerr)   (likelihood3.c:809-873)
+ * for c < n_chains; params row-major [n_chains][21].  Host buffers; returns after the result
+ * is in logL.  Roche-overflow chains give exactly -5e14 (likelihood3.c:863-869). */
+int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, double* logL);
+/* Same with DEVICE buffers, asynchronous on the context's stream (no copies, no sync). */
+int hb_loglikelihood_batch_dev(hb_ctx* ctx, const double* d_params, long n_chains, double* d_logL);
+/* templates[c][i] = calc_light_curve(t, N, params[c])[i]   (likelihood3.c:530-686) on the
+ * uploaded time grid.  Host buffers, [n_chains][N] row-major. */
+int hb_light_curve_batch(hb_ctx* ctx, const double* params, long n_chains, double* templates);
+/* calc_light_curve on an arbitrary time array (the pyHB / driver call: pyHB.pyx:66,
+ * mcmc_wrapper2.c:632,659).  Does not disturb the uploaded data set. */
+int hb_calc_light_curve(hb_ctx* ctx, const double* times, long nt, const double* pars, double* tmpl);
+
+/* ---- per-chain helpers ----------------------------------------------------------------- */
+/* out[c][9] = {R1, R2, Teff1, Teff2, G, B-V, V-G, G-T, RocheOverflow}: calc_radii_and_Teffs
+ * (likelihood3.c:693-717), calc_mags at distance D (:725-795), RocheOverflow (:953-974). */
+int hb_chain_info_batch(hb_ctx* ctx, const double* params, long n_chains, double D, double* out);
+/* traj() of likelihood3.c:125-185; traj_pars[7] = {M1,M2 [g], P [s], e, inc, omega0, T0 [s]} */
+int hb_traj(hb_ctx* ctx, const double* times, long nt, const double* traj_pars, double* d_arr, double* Z1_arr,
+            double* Z2_arr, double* rr_arr, double* ff_arr);
+/* Exact k-th smallest (0-based) of x[0..n): the order statistic remove_median() obtains by
+ * sorting a copy (likelihood3.c:86-105).  NaN in x gives NaN. */
+int hb_order_statistic(hb_ctx* ctx, const double* x, long n, long k, double* out);
+/* Scalar model functions evaluated on the device.  op / args:
+ *   0 _getT(logM)  1 _getR(logM)  2 envelope_Temp(logM)  3 envelope_Radius(logM)
+ *   4 get_alpha_beam(logT)  5 eclipse_area(R1,R2,d)  6 beaming(8 args)  7 ellipsoidal(11 args)
+ *   8 reflection(9 args)          (likelihood3.c:194-209,224-389,396-507) */
+int hb_scalar(hb_ctx* ctx, int op, const double* args, int nargs, double* out);
+/* Gaia flavour (GAIA_mcmc.c:198-269): p6[n][6] = {logM1,logM2,rr1,rr2,aT1,aT2}; mags[n][4] and/or
+ * logL[n] (either may be NULL); data[4], err[4] needed when logL != NULL. */
+int hb_gaia_batch(hb_ctx* ctx, const double* p6, long n, double D, const double* data, const double* err,
+                  double* mags, double* logL);
+
+/* ---- measurement ----------------------------------------------------------------------- */
+/* DFMA throughput of the device in TFLOP/s (2 flop per FMA), the FP64 roofline denominator. */
+int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);
+/* Number of kernel launches issued by this context since creation. */
+long hb_launch_count(const hb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HB_B200_H */

@@ -1,0 +1,64 @@
+// Host build of hb_device.cuh (TEST ONLY): lets the CPU test-suite exercise the exact source
+// of the device model (prologue folding, Kepler solve, flux polynomial, eclipse) against the
+// oracle without a GPU.  CUDA intrinsics are mapped to their IEEE host equivalents; the
+// product never uses this file.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __drcp_rn(double a) { volatile double r = 1.0 / a; return r; }
+static inline void hb_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+#define sincos hb_sincos
+static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }
+static inline long long __double_as_longlong(double x) { long long d; memcpy(&d, &x, 8); return d; }
+static inline int __double2hiint(double x) { return (int)(__double_as_longlong(x) >> 32); }
+static inline int __double2loint(double x) { return (int)(__double_as_longlong(x) & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) { return __longlong_as_double(((long long)hi << 32) | (unsigned int)lo); }
+static inline double __int2double_rn(int x) { return (double)x; }
+static inline int __double2int_rn(double x) { return (int)nearbyint(x); }
+#define HB_HOST_EMUL 1
+#include "hb_device_host.cuh"
+using namespace hb;
+
+static MagSetup default_mags(const double* md, const double* me, int g, int c)
+{
+    MagSetup ms;
+    for (int i = 0; i < 5; i++) ms.mag_data[i] = md[i];
+    for (int i = 0; i < 4; i++) ms.magerr[i] = me[i];
+    ms.use_gmag = g;
+    ms.use_color = c;
+    return ms;
+}
+
+extern "C" int emul_const_size(void) { return (int)(sizeof(ChainConst) / sizeof(double)); }
+
+extern "C" void emul_prologue(const double* p, const double* md, const double* me, int g, int c, double* out)
+{
+    ChainConst cc;
+    chain_prologue(p, default_mags(md, me, g, c), cc);
+    memcpy(out, &cc, sizeof(cc));
+}
+
+// raw (un-normalised) template, likelihood3.c:673
+extern "C" void emul_raw(const double* p, const double* t, long n, double* out)
+{
+    const double md[5] = {1000, 1, 1, 1, 1}, me[4] = {1e15, 1e15, 1e15, 1e15};
+    ChainConst cc;
+    chain_prologue(p, default_mags(md, me, 1, 0), cc);
+    for (long i = 0; i < n; i++) out[i] = raw_flux(cc, t[i]);
+}
+
+extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
+{
+    for (long i = 0; i < n; i++) out[i] = finish_template(u[i], med, blend, ft);
+}
+
+extern "C" double emul_fmod_twopi(double M) { return fmod_twopi(M); }

@@ -1,0 +1,95 @@
+"""CPU coverage of the device model source: hb_device.cuh compiled for the host (intrinsics
+mapped to IEEE host ops, tests/host_emul/emul.cpp) and compared with the oracle.  Catches
+algebra / folding / starter bugs without a GPU; the GPU tests then only add the device libm."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hb_mcmc_b200 import workload as wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "host_emul")
+dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = open(os.path.join(ROOT, "hb_mcmc_b200", "csrc", "hb_device.cuh")).read()
+    src = src.replace("#include <cuda_runtime.h>", "")
+    with open(os.path.join(EMUL, "hb_device_host.cuh"), "w") as f:
+        f.write(src)
+    so = os.path.join(EMUL, "libemul.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(EMUL, "emul.cpp")],
+                   check=True, cwd=EMUL)
+    L = C.CDLL(so)
+    L.emul_raw.argtypes = [dp, dp, C.c_long, dp]
+    L.emul_finish.argtypes = [dp, C.c_long, C.c_double, C.c_double, C.c_double, dp]
+    L.emul_fmod_twopi.restype = C.c_double
+    L.emul_fmod_twopi.argtypes = [C.c_double]
+    L.emul_prologue.argtypes = [dp, dp, dp, C.c_int, C.c_int, dp]
+    return L
+
+
+def raw(L, p, t):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    out = np.empty(t.size)
+    L.emul_raw(p.ctypes.data_as(dp), t.ctypes.data_as(dp), t.size, out.ctypes.data_as(dp))
+    return out
+
+
+def test_fmod_exact(emul):
+    rng = np.random.default_rng(0)
+    y = 2 * 3.14159265358979323846
+    xs = np.concatenate([rng.uniform(-3e5, 3e5, 20000), np.arange(-50, 50) * y, np.nextafter(np.arange(1, 60) * y, 0),
+                         np.nextafter(np.arange(1, 60) * y, 1e9), [0.0, -0.0, 1e-300, 5e14, -7e14]])
+    for x in xs:
+        assert emul.emul_fmod_twopi(float(x)) == np.fmod(x, y), x
+    assert np.isnan(emul.emul_fmod_twopi(float("inf")))
+
+
+@pytest.mark.parametrize("truth,N,tol", [(wl.TRUTH_A, 20000, 2e-13), (wl.TRUTH_B, 50000, 1e-14)])
+def test_raw_template_truths(emul, orc, truth, N, tol):
+    t = wl.time_grid(N)
+    _, want = orc.calc_light_curve(t, truth, raw=True)
+    got = raw(emul, truth, t)
+    assert np.abs(got - want).max() < tol
+
+
+def test_raw_template_random_draws(emul, orc):
+    for truth, emax, seed in ((wl.TRUTH_A, 0.95, 3), (wl.TRUTH_B, 0.99, 4)):
+        t = wl.time_grid(3000) * 7.0 - 5.0  # negative and positive phases, several periods
+        P = wl.draw_chains(64, truth, lambda P: np.zeros(len(P)), seed=seed, e_max=emax)
+        worst = 0.0
+        for p in P:
+            _, want = orc.calc_light_curve(t, p, raw=True)
+            got = raw(emul, p, t)
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            scale = np.maximum(np.abs(want), 1.0)
+            worst = max(worst, np.nanmax(np.abs(got - want) / scale))
+        assert worst < 1e-11, worst
+
+
+def test_finish_matches_reference_order(emul, orc):
+    t = wl.time_grid(1001)
+    lc, u = orc.calc_light_curve(t, wl.TRUTH_A, raw=True)
+    med = np.sort(u)[orc.median_rank(u.size)]
+    out = np.empty_like(u)
+    emul.emul_finish(u.ctypes.data_as(dp), u.size, med, wl.TRUTH_A[19], wl.TRUTH_A[20], out.ctypes.data_as(dp))
+    assert np.array_equal(out, lc)
+
+
+def test_prologue_flags(emul, orc, golden):
+    md = np.array([1000.0, 1, 1, 1, 1])
+    me = np.full(4, 1e15)
+    n = emul.emul_const_size()
+    for p, flag in zip(golden["roche_params"], golden["roche_flags"]):
+        cc = np.empty(n)
+        p = np.ascontiguousarray(p)
+        emul.emul_prologue(p.ctypes.data_as(dp), md.ctypes.data_as(dp), me.ctypes.data_as(dp), 1, 0, cc.ctypes.data_as(dp))
+        assert (int(cc[28]) & 1) == int(flag)
+        R1, R2, T1, T2 = orc.radii_teffs(p)
+        np.testing.assert_allclose(cc[29:33], [R1, R2, T1, T2], rtol=1e-14)
