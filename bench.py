@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark of hb_mcmc_b200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: the batched light-curve model +
+log-likelihood (likelihood3.c:809-873) for `n_chains` parameter vectors on the resident light
+curve.  Workload at any N: BASELINE.json configs[1] per GPU (4096 chains x 20 000 TESS 2-min
+points, truth A of test_likelihoods.c:33-36, prior draws with Roche-overflow draws rejected) --
+chains are independent, so ranks shard them with no data-path collective ("scaling": "weak").
+
+One JSON line on stdout (rank 0):
+  value      model-point logL evals/s, whole job, inputs resident in HBM (device-buffer C ABI),
+             CUDA-event time per step, L2 flushed between steps, max over ranks
+  e2e        same metric through hb_loglikelihood_batch with HOST buffers (H2D of the parameter
+             batch from pinned memory + D2H of logL inside every step)
+  roofline   FP64 CUDA-core roofline of k_chain_eval: 520 algorithmic flop / model point
+              / kernel duration (events on the launching stream) against the DFMA
+             peak measured on this box by hb_fp64_peak in the same run
+  cpu_baseline  the reference's own loglikelihood() (oracle/_ref, or the oracle port when the
+             compiled reference is absent) on all host cores over a bounded sample
+`--impl reference` times that CPU path alone on the same config and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from hb_mcmc_b200 import workload as wl  # noqa: E402
+
+METRIC = "model_point_logL_evals_per_sec"
+UNIT = "points/s"
+FLOP_PER_POINT = 520.0  # 156 plain + 6 sincos x 40 + 8 div x 14 + 1 sqrt x 14
+NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(wl.CONFIGS))
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
+    ap.add_argument("--points", type=int, default=0, help="override points per light curve")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic)")
+    return ap.parse_args()
+
+
+def workload_spec(args):
+    cfg = dict(wl.CONFIGS[args.workload])
+    if args.workload in ("C3", "C5"):
+        # multi-GPU configs name a global chain count over 8 GPUs; per-GPU share is fixed (weak scaling)
+        cfg["n_chains"] //= 8
+    if args.chains:
+        cfg["n_chains"] = args.chains
+    if args.points:
+        cfg["n_points"] = args.points
+    cfg["truth_vec"] = wl.TRUTH_A if cfg["truth"] == "A" else wl.TRUTH_B
+    return cfg
+
+
+def gaia_setup(truth, G_truth):
+    # mag_data = {D=100, G(truth)+0.02, 1,1,1}, magerr = {0.05, BIG x3}, USE_GMAG only
+    return np.array([100.0, G_truth + 0.02, 1.0, 1.0, 1.0]), np.array([0.05, 1e15, 1e15, 1e15])
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                 str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.05):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference arm
+# --------------------------------------------------------------------------------------------
+def cpu_backend():
+    import oracle
+    oracle.build(ref=True)
+    if oracle.have_reference():
+        return oracle.Reference(), "reference"
+    return oracle.Oracle(), "port"
+
+
+def cpu_inputs(cfg, backend):
+    """Dataset + parameter draws for the CPU arm, made with the CPU backend itself."""
+    t, flux, err = wl.make_dataset(cfg["n_points"], cfg["truth_vec"], backend.calc_light_curve)
+    roche = lambda P: np.array([backend.roche_overflow(p) for p in P])  # noqa: E731
+    return t, flux, err, roche
+
+
+def run_cpu_sample(backend, t, flux, err, P, mags, threads):
+    t0 = time.perf_counter()
+    out = backend.loglikelihood_batch(t, flux, err, P, mag_data=mags[0], magerr=mags[1], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return dt, out
+
+
+def reference_arm(args, cfg, rank):
+    if rank != 0:
+        return
+    backend, kind = cpu_backend()
+    cores = os.cpu_count() or 1
+    N = cfg["n_points"]
+    t, flux, err, roche = cpu_inputs(cfg, backend)
+    mags = (None, None)
+    if cfg["gaia"]:
+        mags = gaia_setup(cfg["truth_vec"], backend.calc_mags(cfg["truth_vec"], 100.0)[0])
+    # bounded sample per step: sized from a one-chain-per-core probe so that K steps stay within ~2 min
+    P_all = wl.draw_chains(max(4 * cores, 64), cfg["truth_vec"], roche, seed=1)
+    probe_dt, _ = run_cpu_sample(backend, t, flux, err, P_all[:cores], mags, cores)
+    per_round = max(probe_dt, 1e-3)
+    step_target = min(0.5, 120.0 / max(args.steps + args.warmup, 1))
+    rounds = max(1, int(step_target / per_round))
+    n_step = rounds * cores
+    P = wl.draw_chains(n_step, cfg["truth_vec"], roche, seed=1)
+    for _ in range(args.warmup):
+        run_cpu_sample(backend, t, flux, err, P, mags, cores)
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = run_cpu_sample(backend, t, flux, err, P, mags, cores)
+        total += dt
+    ms = total / args.steps * 1e3
+    value = n_step * N / (ms * 1e-3)
+    sample = f"{n_step} of {cfg['n_chains']} chains x {N} points per step, {cores} threads (dynamic schedule)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": config_block(args, cfg, extra={"cpu_step": sample}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_block(args, cfg, extra=None):
+    c = {
+        "workload": f"{args.workload}: {cfg['n_chains']} chains x {cfg['n_points']} points per GPU (TESS 2-min cadence), "
+                    f"truth {cfg['truth']}, prior draws with Roche-overflow draws rejected"
+                    + (", Gaia G-mag term" if cfg["gaia"] else ""),
+        "n_chains_per_gpu": cfg["n_chains"], "n_points": cfg["n_points"], "n_pars": 21,
+        "sharding": "chains split over ranks, no data-path collective",
+        "l2": "flushed between timed steps (512 MiB write)" if not args.no_flush else "not flushed",
+    }
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def gpu_arm(args, cfg, rank, local_rank, world):
+    import torch
+
+    import hb_mcmc_b200 as hb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hb_mcmc_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = hb.Context(local_rank)
+    # a real (non-NULL) torch stream, made current, so torch.cuda.Event and the library's launches
+    # share one stream (a NULL handle would put the library back on its private stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    N, n = cfg["n_points"], cfg["n_chains"]
+    truth = cfg["truth_vec"]
+
+    # identical synthetic data on every rank (generated by the GPU library itself), own chain shard
+    t, flux, err = wl.make_dataset(N, truth, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    if cfg["gaia"]:
+        md, me = gaia_setup(truth, ctx.chain_info(truth[None], 100.0)[0, 4])
+        ctx.set_mags(md, me, 1, 0)
+    P = wl.draw_chains(n, truth, ctx.roche_overflow, seed=1 + rank)
+
+    d_params = torch.from_numpy(P).to("cuda")
+    d_logL = torch.empty(n, dtype=torch.float64, device="cuda")
+    flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    peak_tf = ctx.fp64_peak_tflops(0.5)
+
+    def step_dev():
+        ctx.loglikelihood_dev(d_params.data_ptr(), n, d_logL.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    ctx.time_kernels(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kernel_ms = []
+    launches0 = ctx.launch_count
+    barrier()
+    t_begin = time.perf_counter()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(k & 0xFF)  # evicts the 126 MB L2; outside the per-step events
+        ev0[k].record(stream)
+        step_dev()
+        ev1[k].record(stream)
+        kernel_ms.append(ctx.last_eval_kernel_ms())  # waits for this step's kernel
+    barrier()
+    t_end = time.perf_counter()
+    launches = ctx.launch_count - launches0
+    ctx.time_kernels(False)
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    if rank == 0:
+        time.sleep(0.1)
+        sampler.stop()
+    logL_dev = d_logL.cpu().numpy()
+
+    # ---- end to end through the host-buffer C ABI ("e2e") ----
+    out = np.empty(n)
+    for _ in range(2):
+        ctx.loglikelihood_into(P, out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.loglikelihood_into(P, out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    assert np.array_equal(out, logL_dev, equal_nan=True), "host-buffer and device-buffer paths disagree"
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        pts_per_step = float(n) * N * world
+        value = pts_per_step / (ms_per_step * 1e-3)
+        e2e_value = pts_per_step / (e2e_s / args.steps)
+        k_ms = float(np.mean(kernel_ms))
+        achieved_tf = float(n) * N * FLOP_PER_POINT / (k_ms * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_block(args, cfg),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes), "d2h_bytes_per_step": int(out.nbytes)},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(t_begin, t_end),
+            "roofline": {
+                "bound": "fp64", "kernel": "k_chain_eval", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+                "flop_per_point": FLOP_PER_POINT, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "peak_source": "hb_fp64_peak DFMA probe on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                               f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
+                "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
+            },
+            "nan_fraction": float(np.isnan(logL_dev).mean()),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg(cfg, t, flux, err, P, logL_dev)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def cpu_baseline_leg(cfg, t, flux, err, P, logL_gpu):
+    """Reference CPU path on the box's host cores over a bounded sample of the SAME inputs
+    (about 20 core-seconds); also re-checks parity on that sample."""
+    backend, kind = cpu_backend()
+    cores = os.cpu_count() or 1
+    mags = (None, None)
+    if cfg["gaia"]:
+        mags = gaia_setup(cfg["truth_vec"], backend.calc_mags(cfg["truth_vec"], 100.0)[0])
+    probe_dt, _ = run_cpu_sample(backend, t, flux, err, P[:cores], mags, cores)
+    rounds = max(1, min(int(20.0 / max(probe_dt * cores, 1e-3)), len(P) // cores))
+    n_s = min(len(P), rounds * cores)
+    dt, out = run_cpu_sample(backend, t, flux, err, P[:n_s], mags, cores)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = np.nanmax(np.abs(out - logL_gpu[:n_s]) / np.abs(out))
+    return {"value": n_s * len(t) / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {n_s} of {len(P)} chains x {len(t)} points, {cores} threads",
+            "max_rel_err_gpu_vs_cpu_on_sample": float(rel)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = workload_spec(args)
+    if args.impl == "reference":
+        reference_arm(args, cfg, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    gpu_arm(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,7 +28,7 @@ struct hb_ctx {
     long launches = 0;
 
     // observed light curve (device)
-    double *d_t = nullptr, *d_flux = nullptr, *d_w = nullptr;
+    double *d_t = nullptr, *d_flux = nullptr, *d_w = nullptr;  // d_t: seconds (t * 86400)
     long N = 0;
     bool has_data = false;
     MagSetup ms;
@@ -53,6 +53,11 @@ struct hb_ctx {
     // pinned host staging
     double* h_pin = nullptr;
     size_t cap_pin = 0;
+
+    // events bracketing the last k_chain_eval launch on its stream (hb_last_eval_kernel_ms)
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    bool ev_valid = false;
+    bool time_kernels = false;
 };
 
 namespace {
@@ -166,8 +171,13 @@ int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, con
              long N, double* d_logL, double* d_lc)
 {
     CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->stream));
+    if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_flux, d_w, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
                          d_logL, d_lc, ctx->d_counter, ctx->stream));
+    if (ctx->time_kernels) {
+        CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
+        ctx->ev_valid = true;
+    }
     ctx->launches += 2;
     return HB_OK;
 }
@@ -230,6 +240,7 @@ int hb_create(hb_ctx** out, int device)
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_counter, sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_small, 64 * sizeof(double)) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess &&
               configure_eval() == cudaSuccess;
     if (!ok) {
         set_global(std::string("hb_create: ") + cudaGetErrorString(cudaGetLastError()));
@@ -252,6 +263,8 @@ void hb_destroy(hb_ctx* ctx)
         cudaFree(ctx->d_scratch); cudaFree(ctx->d_counter); cudaFree(ctx->d_lc);
         cudaFree(ctx->d_times2); cudaFree(ctx->d_small); cudaFree(ctx->d_aux);
         if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+        if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+        if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     }
     delete ctx;
@@ -310,6 +323,8 @@ int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* 
     for (long i = 0; i < n; i++) w[i] = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
     int rc;
     if ((rc = upload(ctx, ctx->d_t, t, (size_t)n)) != HB_OK) return rc;
+    CK(launch_to_seconds(ctx->d_t, (int)n, ctx->d_t, ctx->stream));  // d_t holds t * 86400 from here on
+    ctx->launches += (n > 0);
     if ((rc = upload(ctx, ctx->d_flux, flux, (size_t)n)) != HB_OK) return rc;
     if ((rc = upload(ctx, ctx->d_w, w.data(), (size_t)n)) != HB_OK) return rc;
     ctx->N = n;
@@ -415,6 +430,8 @@ int hb_calc_light_curve(hb_ctx* ctx, const double* times, long nt, const double*
     if ((rc = ensure_chains(ctx, 1)) != HB_OK) return rc;
     if ((rc = ensure_scratch(ctx, nt)) != HB_OK) return rc;
     if ((rc = stage_times(ctx, times, nt)) != HB_OK) return rc;
+    CK(launch_to_seconds(ctx->d_times2, (int)nt, ctx->d_times2, ctx->stream));
+    ctx->launches += 1;
     CK(grow(ctx->d_lc, ctx->cap_lc, (size_t)nt));
     if ((rc = upload(ctx, ctx->d_params, pars, NPARS)) != HB_OK) return rc;
     if ((rc = run_eval(ctx, ctx->d_params, 1, ctx->d_times2, nullptr, nullptr, nt, nullptr, ctx->d_lc)) != HB_OK) return rc;
@@ -520,6 +537,31 @@ int hb_gaia_batch(hb_ctx* ctx, const double* p6, long n, double D, const double*
     ctx->launches += 1;
     if (mags && (rc = download(ctx, mags, d_m, (size_t)n * 4)) != HB_OK) return rc;
     if (logL && (rc = download(ctx, logL, d_l, (size_t)n)) != HB_OK) return rc;
+    return HB_OK;
+}
+
+int hb_time_kernels(hb_ctx* ctx, int enable)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->time_kernels = enable != 0;
+    ctx->ev_valid = false;
+    return HB_OK;
+}
+
+int hb_last_eval_kernel_ms(hb_ctx* ctx, double* ms)
+{
+    if (!ctx || !ms) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->ev_valid) {
+        ctx->err = "hb_last_eval_kernel_ms: no timed launch (call hb_time_kernels(ctx, 1) first)";
+        return HB_ERR_STATE;
+    }
+    DeviceGuard g(ctx->device);
+    CK(cudaEventSynchronize(ctx->ev_k1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, ctx->ev_k0, ctx->ev_k1));
+    *ms = (double)f;
     return HB_OK;
 }
 

@@ -17,9 +17,14 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef HB_NEWTON_UNROLL
+#define HB_NEWTON_UNROLL 1
+#endif
+
 namespace hb {
 
 constexpr int NPARS = 21;  // likelihood3.h:20
+constexpr int kNewtonUnroll = HB_NEWTON_UNROLL;  // 1 = rolled Newton loop (small I-cache footprint)
 
 // physical constants, likelihood3.h:4-10,31
 constexpr double kPi = 3.14159265358979323846;
@@ -36,6 +41,7 @@ struct ChainConst {
     // orbit
     double e, sq1me2;  // eccentricity, sqrt(1-e^2)
     double T0s, Ps;    // T0*86400, P[s]  (exactly the reference's T0_cgs / P_cgs)
+    double rPs;        // RN(1/Ps): seed of the exact phase division
     double cw, sw;     // cos/sin omega0
     double ci, si;     // cos/sin inc
     double ar;         // a / RSUN
@@ -48,6 +54,8 @@ struct ChainConst {
     // per-chain additive chi^2 (Gaia magnitude / colour terms) and flags
     double chi2_extra;
     double flag;  // bit 0: Roche overflow, bit 1: model is NaN by construction (e >= 1 or NaN e)
+    double seed;  // 32-bit hash of the parameter bits: sampling jitter of the select (a chain's
+                  // result does not depend on where it sits in the batch)
     // diagnostics (hb_chain_info): R1 R2 T1 T2 G B-V V-G G-T
     double info[8];
 };
@@ -182,6 +190,7 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     cc.sq1me2 = sqrt(ome2);
     cc.T0s = T0 * kSecDay;
     cc.Ps = Pd * kSecDay;
+    cc.rPs = __drcp_rn(cc.Ps);
     cc.cw = cw;
     cc.sw = sw;
     cc.ci = ci;
@@ -279,6 +288,15 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     // e >= 1 (reachable, quirk Q4) or NaN e: the reference's template is NaN at every sample
     const int nan_model = !(e < 1.0) ? 1 : 0;
     cc.flag = (double)(roche | (nan_model << 1));
+    {
+        uint32_t h = 0x811c9dc5u;
+        for (int i = 0; i < NPARS; i++) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(p[i]);
+            h = (h ^ (uint32_t)b) * 0x01000193u;
+            h = (h ^ (uint32_t)(b >> 32)) * 0x01000193u;
+        }
+        cc.seed = (double)h;
+    }
 
     cc.info[0] = R[0]; cc.info[1] = R[1]; cc.info[2] = Te[0]; cc.info[3] = Te[1];
     cc.info[4] = mags[0]; cc.info[5] = mags[1]; cc.info[6] = mags[2]; cc.info[7] = mags[3];
@@ -288,18 +306,111 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
 // per-sample pieces
 // ---------------------------------------------------------------------------
 
-// Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153).  One truncated
-// quotient + one exact FMA remainder; the quotient is corrected when it is off by one.
+// ---- lean FP64 primitives --------------------------------------------------------------
+// The CUDA library sincos()/division cost ~3 non-FP64 instructions per FP64 one (range and
+// special-case handling, 64-bit immediates moved through uniform registers); measured with
+// ncu that made the model pass issue-bound at 34 % FP64-pipe utilisation.  The versions below
+// keep the FP64 pipe as the only busy pipe: coefficients sit in the constant bank (operands of
+// DFMA, no UMOV), quadrant logic is 9 integer ops, divisions are a MUFU seed + Newton steps.
+
+#ifndef HB_HOST_EMUL
+__device__ __forceinline__ double rcp_seed(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RCP64H, ~2^-20 relative
+    return y;
+}
+#else
+static inline double rcp_seed(double x) { return (double)(float)(1.0 / x); }
+#endif
+
+// 1/x to ~1 ulp for normal, finite x (two Newton steps on the MUFU seed)
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y = rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// a/b to ~1 ulp: one Newton step on the seed, then a residual correction of the quotient
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    double y = rcp_seed(b);
+    const double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    const double q = a * y;
+    const double r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+
+// fdlibm __kernel_sin / __kernel_cos minimax coefficients on [-pi/4, pi/4]
+__constant__ double kSinC[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+// pi/2 split in three (Cody-Waite), 2/pi, and the round-to-integer magic number 1.5 * 2^52
+__constant__ double kRed[5] = {1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983880e-33,
+                               6.36619772367581382433e-01, 6755399441055744.0};
+
+// sin and cos of x, ~1 ulp, for |x| <= 1e5 (Kepler iterates are O(10)); the library handles the rest.
+static __device__ __noinline__ void sincos_library(double x, double* s, double* c) { sincos(x, s, c); }
+
+__device__ __forceinline__ void sincos_lean(double x, double& s_out, double& c_out)
+{
+    if (!(fabs(x) <= 1.0e5)) {  // cold: wild Newton iterates at e -> 1, inf, NaN
+        double s, c;
+        sincos_library(x, &s, &c);
+        s_out = s;
+        c_out = c;
+        return;
+    }
+    const double t = fma(x, kRed[3], kRed[4]);
+    const int k = __double2loint(t);  // nearest integer to x * 2/pi sits in the low word
+    const double kd = t - kRed[4];
+    double r = fma(-kd, kRed[0], x);
+    r = fma(-kd, kRed[1], r);
+    r = fma(-kd, kRed[2], r);
+    const double z = r * r;
+    double ps = fma(z, kSinC[5], kSinC[4]);
+    ps = fma(z, ps, kSinC[3]);
+    ps = fma(z, ps, kSinC[2]);
+    ps = fma(z, ps, kSinC[1]);
+    ps = fma(z, ps, kSinC[0]);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, kCosC[5], kCosC[4]);
+    pc = fma(z, pc, kCosC[3]);
+    pc = fma(z, pc, kCosC[2]);
+    pc = fma(z, pc, kCosC[1]);
+    pc = fma(z, pc, kCosC[0]);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant: k odd swaps, bit 1 of k (sin) / of k+1 (cos) flips the sign
+    const bool odd = k & 1;
+    const double sa = odd ? cr : sr;
+    const double ca = odd ? sr : cr;
+    const int ssign = (k & 2) << 30;
+    const int csign = ((k + 1) & 2) << 30;
+    s_out = __hiloint2double(__double2hiint(sa) ^ ssign, __double2loint(sa));
+    c_out = __hiloint2double(__double2hiint(ca) ^ csign, __double2loint(ca));
+}
+
+static __device__ __noinline__ double fmod_library(double a, double b) { return fmod(a, b); }
+
+// Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153): a rounded quotient
+// from the magic-number trick, one exact FMA remainder, and a rare off-by-one repair.
 __device__ __forceinline__ double fmod_twopi(double M)
 {
     const double y = kTwoPi;
     const double am = fabs(M);
-    if (!(am < 1.0e15)) return fmod(M, y);  // huge / inf / NaN: library path
-    double q = trunc(am * (1.0 / y));
+    if (!(am < 1.0e15)) return fmod_library(M, y);  // huge / inf / NaN: library path
+    const double magic = 6755399441055744.0;
+    double q = fma(am, 1.0 / y, magic - 0.5) - magic;  // rint(am / y - 0.5) ~ floor
     double r = fma(-q, y, am);
-    const double adj = (r < 0.0) ? -1.0 : ((r >= y) ? 1.0 : 0.0);
-    q += adj;
-    r = fma(-q, y, am);  // exact: 0 <= r < y is representable
+    if (r < 0.0 || r >= y) {  // quotient off by one (am within rounding of a multiple of y)
+        q += (r < 0.0) ? -1.0 : 1.0;
+        r = fma(-q, y, am);   // exact: 0 <= r < y is representable
+    }
     return copysign(r, M);
 }
 
@@ -307,32 +418,36 @@ struct OrbitPoint {
     double cE, sE, den;  // cos E, sin E, 1 - e cos E
 };
 
-// likelihood3.c:149-160: mean anomaly in the reference's operation order (non-contracted),
-// starter E0 = M + 0.85 e sign(sin M), exactly five Newton steps.
-__device__ __forceinline__ OrbitPoint kepler_point(double t, const double e, const double T0s, const double Ps)
+// likelihood3.c:149-160.  tsec = t * 86400 exactly as the reference forms it.  The mean anomaly
+// is bit-identical with the reference's 2 pi (t - T0) / P: the two products are explicitly
+// rounded and the division is the correctly rounded Markstein sequence on rP = RN(1/P).
+// Starter E0 = M + 0.85 e sign(sin M), exactly five Newton steps.
+__device__ __forceinline__ OrbitPoint kepler_point(double tsec, const double e, const double T0s, const double Ps,
+                                                  const double rPs)
 {
-    const double tsec = __dmul_rn(t, kSecDay);
-    double M = __ddiv_rn(__dmul_rn(kTwoPi, __dsub_rn(tsec, T0s)), Ps);
+    const double x = __dmul_rn(kTwoPi, __dsub_rn(tsec, T0s));
+    const double q0 = __dmul_rn(x, rPs);
+    double M = fma(fma(-Ps, q0, x), rPs, q0);
     M = fmod_twopi(M);
     // sign(sin M) for |M| < fl(2 pi): positive on (0, fl(pi)], negative above (sin(fl(pi)) > 0)
     const double am = fabs(M);
     double sg = (am <= kPi) ? 1.0 : -1.0;
     sg = (M < 0.0) ? -sg : sg;
     sg = (am == 0.0) ? 0.0 : sg;
-    double E = M + (0.85 * e) * sg;
+    double E = fma(0.85 * e, sg, M);
     double sE, cE;
-#pragma unroll
+#pragma unroll kNewtonUnroll
     for (int k = 0; k < 5; k++) {
-        sincos(E, &sE, &cE);
-        const double num = __dsub_rn(__dsub_rn(E, __dmul_rn(e, sE)), M);
-        const double den = __dsub_rn(1.0, __dmul_rn(e, cE));
-        E = __dsub_rn(E, __ddiv_rn(num, den));
+        sincos_lean(E, sE, cE);
+        const double num = fma(-e, sE, E) - M;
+        const double den = fma(-e, cE, 1.0);
+        E -= div_fast(num, den);
     }
-    sincos(E, &sE, &cE);
+    sincos_lean(E, sE, cE);
     OrbitPoint o;
     o.cE = cE;
     o.sE = sE;
-    o.den = __dsub_rn(1.0, __dmul_rn(e, cE));
+    o.den = fma(-e, cE, 1.0);
     return o;
 }
 
@@ -366,11 +481,12 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
     return area;
 }
 
-// Raw (un-normalised) template value Amag1 + Amag2 of likelihood3.c:649-675 at one sample.
-__device__ __forceinline__ double raw_flux(const ChainConst& cc, double t)
+// Raw (un-normalised) template value Amag1 + Amag2 of likelihood3.c:649-675 at one sample
+// (tsec = t * 86400, formed once per data set).
+__device__ __forceinline__ double raw_flux(const ChainConst& cc, double tsec)
 {
-    const OrbitPoint o = kepler_point(t, cc.e, cc.T0s, cc.Ps);
-    const double beta = 1.0 / o.den;  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
+    const OrbitPoint o = kepler_point(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs);
+    const double beta = rcp_fast(o.den);  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
     const double cnu = (o.cE - cc.e) * beta;
     const double snu = cc.sq1me2 * o.sE * beta;
     const double c = cc.cw * cnu - cc.sw * snu;  // cos(omega0 + nu)

@@ -43,8 +43,9 @@ __device__ __forceinline__ double block_sum_double(double v, double* red)
 
 struct EvalShared {
     ChainConst cc;
-    SelectCtl ctl;
-    double red[32];
+    SelectCtl<kEvalThreads> ctl;
+    double red[3 * 32];
+    double pivot;  // chi^2 expansion point u0 (a template value near the median)
     uint64_t candA[kCandA];
     uint64_t candB[kCandB];
 };
@@ -59,18 +60,34 @@ __device__ __forceinline__ int median_rank(int N)
     return r < N ? r : N - 1;
 }
 
+// One chain at a time per CTA (persistent CTAs, atomic chain scheduler).  Per chain:
+//   pre-sample  every thread evaluates the model at one jittered-stride sample; the block sorts
+//               the kThreads values; sample order statistics give a bracket [lo, hi] around the
+//               reference's median rank and the expansion point u0 of the chi^2.
+//   model pass  u_i at every sample (the FP64-bound part): key stored to scratch, #(u < lo)
+//               counted, u in [lo, hi] appended to a shared-memory candidate list, and the three
+//               sums of   chi^2(m) = S0 + 2 d S1 + d^2 S2,   d = -A (m - u0),
+//               S0 = sum ((A (u_i - u0) + ft - f_i) w_i)^2,  S1 = sum (A (u_i - u0) + ft - f_i) w_i^2,
+//               S2 = sum w_i^2   (model_i = A (u_i - m) + ft, A = ft (1 - blending), likelihood3.c:681-685)
+//   select      exact order statistic among the candidates (hb_select.cuh); the stored template
+//               is only re-read when the bracket missed (rare) or when the caller wants the
+//               light curve itself (lc_out).
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
-k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ t,
+k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
              const double* __restrict__ flux, const double* __restrict__ w, int N, uint64_t* __restrict__ scratch,
              size_t scratch_stride, double* __restrict__ logL, double* __restrict__ lc_out, int* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     uint64_t* tmpl = scratch + (size_t)blockIdx.x * 3 * scratch_stride;
-    SelectBuf bufs[4] = {{sm.candB, kCandB}, {sm.candA, kCandA}, {tmpl + scratch_stride, N}, {tmpl + 2 * scratch_stride, N}};
+    uint64_t* gbufB = tmpl + scratch_stride;
+    uint64_t* gbufC = tmpl + 2 * scratch_stride;
+    const SelectBuf bufs[4] = {{sm.candB, kCandB}, {sm.candA, kCandA}, {gbufB, N}, {gbufC, N}};
     __shared__ int s_chain;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const int krank = median_rank(N);
 
     for (;;) {
         // dynamic chain scheduler: chains differ in cost (eclipse fraction, Roche early-out)
@@ -84,28 +101,87 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             for (int i = tid; i < (int)(sizeof(ChainConst) / sizeof(double)); i += kThreads) dst[i] = src[i];
         }
         __syncthreads();
-        const int flag = (int)sm.cc.flag;
+        const ChainConst& cc = sm.cc;
+        const int flag = (int)cc.flag;
         const bool roche = flag & 1, nan_model = flag & 2;
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
         if (nan_model || (roche && lc_out == nullptr) || N <= 0) {
             // quirk Q13: the reference evaluates the model and then discards it on Roche overflow
             if (lc_out != nullptr)
                 for (int i = tid; i < N; i += kThreads) lc_out[(size_t)chain * N + i] = qnan;
             if (tid == 0 && logL != nullptr)
-                logL[chain] = roche ? -0.5 * kBig : (nan_model ? qnan : -0.5 * sm.cc.chi2_extra);
+                logL[chain] = roche ? -0.5 * kBig : (nan_model ? qnan : -0.5 * cc.chi2_extra);
             __syncthreads();
             continue;
         }
 
-        // ---- pass B: model ----
-        int nanflag = 0;
-        {
-            const ChainConst& cc = sm.cc;
-            for (int i = tid; i < N; i += kThreads) {
-                const double u = raw_flux(cc, t[i]);
-                nanflag |= (u != u);
-                tmpl[i] = dkey(u);
+        // ---- pre-sample: bracket of the median rank + expansion point ----
+        const bool bracketed = N > kThreads;
+        uint64_t* cand = sm.candA;  // first-round survivors
+        int cand_cap = kCandA;
+        double lo = -INFINITY, hi = INFINITY;
+        if (bracketed) {
+            const uint32_t seed = (uint32_t)cc.seed;
+            const double us = raw_flux(cc, tsec[sample_index(tid, kThreads, N, seed)]);
+            // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
+            const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
+            int r_lo, r_hi, r_mid;
+            bracket_ranks(kThreads, N, krank, 2.5f, r_lo, r_hi, r_mid);
+            const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)kThreads);
+            if ((int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // large N: survivors go to global scratch
+                cand = gbufB;
+                cand_cap = N;
+            }
+            if (tid == 0) {
+                sm.ctl.cnt = 0;
+                if (r_lo < 0) sm.ctl.lo = 0ull;
+                if (r_hi > kThreads - 1) sm.ctl.hi = ~0ull;
+            }
+            if (tid == r_lo) sm.ctl.lo = sorted;
+            if (tid == r_hi) sm.ctl.hi = sorted;
+            if (tid == r_mid) sm.pivot = dunkey(sorted);
+            __syncthreads();
+            lo = dunkey(sm.ctl.lo);
+            hi = dunkey(sm.ctl.hi);
+        } else {
+            if (tid == 0) {
+                sm.ctl.cnt = 0;
+                sm.pivot = cc.K0;  // template values are K0 + O(1e-2)
+            }
+            __syncthreads();
+        }
+        const double u0 = sm.pivot;
+        const double A = cc.ft * (1.0 - cc.blend), ft = cc.ft;
+
+        // ---- model pass ----
+        int nanflag = 0, c_lt = 0;
+        double S0 = 0., S1 = 0., S2 = 0.;
+        for (int base = 0; base < N; base += kThreads) {
+            const int i = base + tid;
+            const bool valid = i < N;
+            const double u = raw_flux(cc, tsec[valid ? i : N - 1]);
+            nanflag |= (u != u);
+            if (valid) tmpl[i] = dkey(u);
+            c_lt += (valid & (u < lo));
+            const bool inr = valid & (u >= lo) & (u <= hi);
+            const unsigned mask = __ballot_sync(0xffffffffu, inr);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                int basepos = 0;
+                if (lane == leader) basepos = atomicAdd(&sm.ctl.cnt, __popc(mask));
+                basepos = __shfl_sync(0xffffffffu, basepos, leader);
+                if (inr) {
+                    const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
+                    if (pos < cand_cap) cand[pos] = dkey(u);
+                }
+            }
+            if (flux != nullptr && valid) {
+                const double wi = w[i];
+                const double a = fma(A, u - u0, ft - flux[i]);
+                const double r = a * wi;
+                S0 = fma(r, r, S0);
+                S1 = fma(r, wi, S1);
+                S2 = fma(wi, wi, S2);
             }
         }
         const int any_nan = __syncthreads_or(nanflag);
@@ -118,23 +194,49 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         }
 
         // ---- exact order statistic ----
-        const double med = dunkey(block_select_key<kThreads>(tmpl, N, median_rank(N), sm.ctl, bufs, 4,
-                                                            0x5bd1e995u * (uint32_t)(chain + 1)));
+        c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
+        const int c_in = sm.ctl.cnt;
+        __syncthreads();
+        const uint32_t seed2 = (uint32_t)cc.seed ^ 0x9e3779b9u;
+        uint64_t mkey;
+        if (krank >= c_lt && krank < c_lt + c_in && c_in <= cand_cap)
+            mkey = block_select_key<kThreads>(cand, c_in, krank - c_lt, sm.ctl, bufs, 4, seed2);
+        else  // the bracket missed (or overflowed): select on the stored template
+            mkey = block_select_key<kThreads>(tmpl, N, krank, sm.ctl, bufs, 4, seed2);
+        const double med = dunkey(mkey);
 
-        // ---- pass D: normalise, chi^2 ----
-        const double blend = sm.cc.blend, ft = sm.cc.ft;
-        double acc = 0.;
-        for (int i = tid; i < N; i += kThreads) {
-            const double model = finish_template(dunkey(tmpl[i]), med, blend, ft);
-            if (lc_out != nullptr) lc_out[(size_t)chain * N + i] = model;
-            if (flux != nullptr) {
-                const double r = (model - flux[i]) * w[i];
-                acc = fma(r, r, acc);
-            }
+        // ---- results ----
+        if (lc_out != nullptr) {
+            const double blend = cc.blend;
+            for (int i = tid; i < N; i += kThreads)
+                lc_out[(size_t)chain * N + i] = finish_template(dunkey(tmpl[i]), med, blend, ft);
         }
         if (logL != nullptr) {
-            const double chi2 = block_sum_double<kThreads>(acc, sm.red);
-            if (tid == 0) logL[chain] = roche ? -0.5 * kBig : -0.5 * (chi2 + sm.cc.chi2_extra);
+            // three block sums in one go
+            const int wid = tid >> 5;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                S0 += __shfl_xor_sync(0xffffffffu, S0, o);
+                S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+                S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+            }
+            if (lane == 0) {
+                sm.red[wid] = S0;
+                sm.red[32 + wid] = S1;
+                sm.red[64 + wid] = S2;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double t0 = 0., t1 = 0., t2 = 0.;
+                for (int i = 0; i < kThreads / 32; i++) {
+                    t0 += sm.red[i];
+                    t1 += sm.red[32 + i];
+                    t2 += sm.red[64 + i];
+                }
+                const double d = -A * (med - u0);
+                const double chi2 = t0 + d * (2.0 * t1 + d * t2);
+                logL[chain] = roche ? -0.5 * kBig : -0.5 * (chi2 + cc.chi2_extra);
+            }
         }
         __syncthreads();
     }
@@ -183,7 +285,7 @@ __global__ void k_traj(const double* __restrict__ times, int Nt, const double* _
     const double P = tp[2], e = tp[3], inc = tp[4], w0 = tp[5], T0 = tp[6];
     const double Mtot = Ma + Mb;
     const double a = pow(kG * Mtot * sq(P) / sq(2 * kPi), 1. / 3.);
-    const OrbitPoint o = kepler_point(times[i], e, T0, P);
+    const OrbitPoint o = kepler_point(__dmul_rn(times[i], kSecDay), e, T0, P, __drcp_rn(P));
     const double r = a * o.den;
     const double sq1 = sqrt(1 - e * e);
     const double nu = atan2(sq1 * o.sE, o.cE - e);
@@ -286,6 +388,13 @@ __global__ void k_chain_info(const ChainConst* __restrict__ cc, int n, double* _
     out[(size_t)c * 9 + 8] = (double)(((int)cc[c].flag) & 1);
 }
 
+// tsec[i] = t[i] * 86400 (likelihood3.c:149), once per uploaded time grid
+__global__ void k_to_seconds(const double* __restrict__ t, int n, double* __restrict__ tsec)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tsec[i] = __dmul_rn(t[i], kSecDay);
+}
+
 // DFMA throughput probe: 8 independent accumulators per thread, `iters` x 8 x 4 DFMA each.
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b)
 {
@@ -365,6 +474,13 @@ cudaError_t launch_chain_info(const ChainConst* cc, int n, double* out, cudaStre
 {
     if (n <= 0) return cudaSuccess;
     k_chain_info<<<(n + 127) / 128, 128, 0, s>>>(cc, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_to_seconds(const double* t, int n, double* tsec, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_to_seconds<<<(n + 255) / 256, 256, 0, s>>>(t, n, tsec);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,7 @@ cudaError_t launch_scalar(int op, const double* args, double* out, cudaStream_t 
 cudaError_t launch_gaia(const double* p6, int n, double D, const double* data, const double* err, double* mags,
                         double* logL, cudaStream_t s);
 cudaError_t launch_chain_info(const ChainConst* cc, int n, double* out, cudaStream_t s);
+cudaError_t launch_to_seconds(const double* t, int n, double* tsec, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t s);
 
 }  // namespace hb

@@ -2,25 +2,25 @@
 //
 // Replaces the reference's copy + Lomuto quicksort + sorted[mid] of remove_median()
 // (likelihood3.c:36-105).  The reference needs one order statistic, not a sorted array, so
-// the device version is a sampling select (Floyd-Rivest style) done with integer keys:
-//   round:  draw S jittered-stride samples -> rank them by counting -> take two sample
-//           order statistics lo/hi that bracket the target rank -> one pass that counts
-//           keys < lo and compacts keys in [lo, hi] into a smaller buffer.
-//   finish: <= kDirect survivors are ranked by counting; the key with the target rank wins.
-//   ties / bad luck: a round that does not shrink the problem is retried with a new jitter;
-//           after kMaxFails misses a 64-step bisection on the key bits (tie-proof) finishes.
-// All comparisons are on order-preserving 64-bit integer keys, so nothing here touches the
-// FP64 pipe that the model pass saturates.  NaN-free input is a precondition (the caller
-// short-circuits NaN templates, see k_chain_eval).
+// the device version is a sampling select (Floyd-Rivest style) on order-preserving integer keys:
+//   round:  S = blockDim jittered-stride samples (one per thread) -> bitonic sort across the
+//           block (shuffles below stride 32, shared memory above) -> two sample order statistics
+//           lo/hi bracket the target rank -> one pass counts keys < lo and compacts keys in
+//           [lo, hi] into a smaller buffer (warp-aggregated append).
+//   finish: <= blockDim survivors are sorted directly; sorted[k] wins.
+//   ties / bad luck: a round that does not shrink the problem is retried with a new jitter and a
+//           wider bracket; after kMaxFails misses a 64-step bisection on the key bits (tie-proof).
+// k_chain_eval runs the FIRST round inside its model pass (the bracket comes from a pre-sample of
+// the model itself), so the common case never re-reads the template.
+// Nothing here touches the FP64 pipe that the model pass saturates.  NaN-free input is a
+// precondition (callers short-circuit NaN templates).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace hb {
 
-constexpr int kDirect = 512;    // survivors ranked directly
-constexpr int kMaxFails = 4;    // unsuccessful rounds before the bisection fallback
-constexpr int kSampMax = 512;   // largest sample
+constexpr int kMaxFails = 4;  // unsuccessful rounds before the bisection fallback
 
 __device__ __forceinline__ uint64_t dkey(double x)
 {
@@ -39,14 +39,25 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x)
     return x;
 }
 
+// index of sample j of S in [0, n): stratified with a hashed jitter (defeats aliasing of the
+// stride with the orbital period)
+__device__ __forceinline__ int sample_index(int j, int S, int n, uint32_t seed)
+{
+    const uint32_t h = mix32(seed ^ mix32((uint32_t)j + 0x9e3779b9u));
+    const float jit = (float)(h >> 8) * (1.0f / 16777216.0f);
+    long long idx = (long long)(((double)j + (double)jit) * (double)n / (double)S);
+    return (int)(idx > n - 1 ? n - 1 : idx);
+}
+
 struct SelectBuf {
     uint64_t* ptr;
     int cap;
 };
 
 // Shared-memory control block of the select (the key buffers are passed separately).
+template <int kThreads>
 struct SelectCtl {
-    uint64_t samp[kSampMax];
+    uint64_t xch[kThreads];  // exchange buffer of the sort / sorted sample
     uint64_t lo, hi, result;
     int cnt;
     int ired[32];
@@ -67,64 +78,105 @@ __device__ __forceinline__ int block_sum_int(int v, int* red)
     return t;
 }
 
-// Rank `n` keys by counting; returns (to every thread) the key whose rank is k.
+// Bitonic sort of one key per thread across the block: afterwards thread t holds sorted[t].
+// Strides below 32 exchange through shuffles, the others through xch[] (kThreads entries).
 template <int kThreads>
-__device__ uint64_t select_direct(const uint64_t* keys, int n, int k, SelectCtl& ctl)
+__device__ __noinline__ uint64_t block_sort(uint64_t key, uint64_t* xch)
 {
-    for (int j = threadIdx.x; j < n; j += kThreads) {
-        const uint64_t x = keys[j];
-        int r = 0;
-        for (int i = 0; i < n; i++) {
-            const uint64_t y = keys[i];
-            r += (y < x) | ((y == x) & (i < j));
+    static_assert((kThreads & (kThreads - 1)) == 0, "block size must be a power of two");
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int k = 2; k <= kThreads; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t other;
+            if (j >= 32) {
+                xch[tid] = key;
+                __syncthreads();
+                other = xch[tid ^ j];
+                __syncthreads();
+            } else {
+                const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)key, j);
+                const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
+                other = ((uint64_t)hi << 32) | lo;
+            }
+            const bool take_min = (((tid & k) == 0) == ((tid & j) == 0));
+            const bool less = other < key;
+            key = (less == take_min) ? other : key;
         }
-        if (r == k) ctl.result = x;
     }
-    __syncthreads();
-    return ctl.result;
+    return key;
+}
+
+// Bracket ranks (in a sorted sample of S) around the target quantile q = (k + 0.5) / n.
+__device__ __forceinline__ void bracket_ranks(int S, int n, int k, float z, int& r_lo, int& r_hi, int& r_mid)
+{
+    const float q = ((float)k + 0.5f) / (float)n;
+    const float ks = q * (float)S;
+    int m = (int)ceilf(z * sqrtf((float)S * q * (1.0f - q))) + 1;
+    if (m < 2) m = 2;
+    r_lo = (int)floorf(ks) - m;
+    r_hi = (int)ceilf(ks) + m;
+    r_mid = (int)ks;
+    if (r_mid > S - 1) r_mid = S - 1;
 }
 
 // Tie-proof fallback: smallest key K with #(keys <= K) >= k+1, by bisection on the bits.
 template <int kThreads>
-__device__ uint64_t select_bisect(const uint64_t* keys, int n, int k, SelectCtl& ctl)
+__device__ __noinline__ uint64_t select_bisect(const uint64_t* keys, int n, int k, int* ired)
 {
     uint64_t lo = 0, hi = ~0ull;
     while (lo < hi) {
         const uint64_t mid = lo + ((hi - lo) >> 1);
         int c = 0;
         for (int i = threadIdx.x; i < n; i += kThreads) c += (keys[i] <= mid);
-        c = block_sum_int<kThreads>(c, ctl.ired);
+        c = block_sum_int<kThreads>(c, ired);
         if (c >= k + 1) hi = mid; else lo = mid + 1;
     }
     return lo;
 }
 
-// Exact k-th smallest (0-based) of keys[0..n).  `keys` may live in global or shared memory
-// and is not modified.  `bufs` are nb scratch key buffers (any mix of shared / global) that
-// must not alias `keys`; at least two, and the largest must hold n keys.
+// Exact k-th smallest (0-based) of keys[0..n).  `keys` may live in global or shared memory and
+// is not modified.  `bufs` are nb scratch key buffers (any mix of shared / global) that must not
+// alias `keys`; at least two, and the largest must hold n keys.  Returns the key to every thread.
 template <int kThreads>
-__device__ uint64_t block_select_key(const uint64_t* keys, int n, int k, SelectCtl& ctl, const SelectBuf* bufs,
-                                     int nb, uint32_t seed)
+__device__ __noinline__ uint64_t block_select_key(const uint64_t* keys, int n, int k, SelectCtl<kThreads>& ctl,
+                                                  const SelectBuf* bufs, int nb, uint32_t seed)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t* cur = keys;
     int cur_n = n, cur_k = k, fails = 0;
     for (int round = 0;; ++round) {
-        if (cur_n <= kDirect) return select_direct<kThreads>(cur, cur_n, cur_k, ctl);
-        if (fails >= kMaxFails) return select_bisect<kThreads>(cur, cur_n, cur_k, ctl);
+        if (cur_n <= kThreads) {
+            // finish: sort the survivors (padded with the largest key) and read sorted[k]
+            const uint64_t mine = (tid < cur_n) ? cur[tid] : ~0ull;
+            __syncthreads();
+            const uint64_t s = block_sort<kThreads>(mine, ctl.xch);
+            if (tid == cur_k) ctl.result = s;
+            __syncthreads();
+            return ctl.result;
+        }
+        if (fails >= kMaxFails) return select_bisect<kThreads>(cur, cur_n, cur_k, ctl.ired);
 
-        // ---- sample ----
-        const int S = (cur_n >= 16384) ? kSampMax : 256;
-        const float q = ((float)cur_k + 0.5f) / (float)cur_n;
-        const float ks = q * (float)S;
-        // bracket half-width in sample ranks: z sigma of the binomial rank error, widened after a miss
-        const float z = 2.5f + 1.0f * (float)fails;
-        int m = (int)ceilf(z * sqrtf((float)S * q * (1.0f - q))) + 1;
-        if (m < 2) m = 2;
-        const int r_lo = (int)floorf(ks) - m, r_hi = (int)ceilf(ks) + m;
-        const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)S);
-        const int expect = (int)(frac * (float)cur_n * 1.5f) + 64;
+        // ---- sample + sort ----
+        const uint64_t smp = cur[sample_index(tid, kThreads, cur_n, seed + 0x632be5abu * (uint32_t)(round + 1))];
+        __syncthreads();
+        const uint64_t sorted = block_sort<kThreads>(smp, ctl.xch);
+        int r_lo, r_hi, r_mid;
+        bracket_ranks(kThreads, cur_n, cur_k, 2.5f + 1.0f * (float)fails, r_lo, r_hi, r_mid);
+        if (tid == 0) {
+            ctl.cnt = 0;
+            if (r_lo < 0) ctl.lo = 0ull;               // below every key
+            if (r_hi > kThreads - 1) ctl.hi = ~0ull;   // above every key
+        }
+        if (tid == r_lo) ctl.lo = sorted;
+        if (tid == r_hi) ctl.hi = sorted;
+        __syncthreads();
+        const uint64_t lo = ctl.lo, hi = ctl.hi;
+
         // smallest scratch buffer (not the current one) that should hold the survivors
+        const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)kThreads);
+        const int expect = (int)(frac * (float)cur_n * 1.5f) + 64;
         int pick = -1, big = -1;
         for (int b = 0; b < nb; b++) {
             if (bufs[b].ptr == cur) continue;
@@ -134,32 +186,6 @@ __device__ uint64_t block_select_key(const uint64_t* keys, int n, int k, SelectC
         if (pick < 0) pick = big;
         uint64_t* out = bufs[pick].ptr;
         const int cap = bufs[pick].cap;
-
-        for (int j = tid; j < S; j += kThreads) {
-            const uint32_t h = mix32(seed ^ mix32((uint32_t)(round * 4099 + j) + 0x9e3779b9u));
-            const float jit = (float)(h >> 8) * (1.0f / 16777216.0f);
-            long long idx = (long long)(((double)j + (double)jit) * (double)cur_n / (double)S);
-            if (idx > cur_n - 1) idx = cur_n - 1;
-            ctl.samp[j] = cur[idx];
-        }
-        if (tid == 0) {
-            ctl.lo = 0ull;       // below every key  (-> nothing is "less than lo")
-            ctl.hi = ~0ull;      // above every key
-            ctl.cnt = 0;
-        }
-        __syncthreads();
-        for (int j = tid; j < S; j += kThreads) {
-            const uint64_t x = ctl.samp[j];
-            int r = 0;
-            for (int i = 0; i < S; i++) {
-                const uint64_t y = ctl.samp[i];
-                r += (y < x) | ((y == x) & (i < j));
-            }
-            if (r == r_lo) ctl.lo = x;
-            if (r == r_hi) ctl.hi = x;
-        }
-        __syncthreads();
-        const uint64_t lo = ctl.lo, hi = ctl.hi;
 
         // ---- count + compact pass ----
         int c_lt = 0;

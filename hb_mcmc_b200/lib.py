@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "hb_create", "hb_destroy", "hb_last_error", "hb_global_error", "hb_device_info", "hb_set_stream", "hb_sync",
     "hb_set_data", "hb_set_mags", "hb_loglikelihood_batch", "hb_loglikelihood_batch_dev", "hb_light_curve_batch",
     "hb_calc_light_curve", "hb_chain_info_batch", "hb_traj", "hb_order_statistic", "hb_scalar", "hb_gaia_batch", "hb_fp64_peak",
-    "hb_launch_count",
+    "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count",
 )
 
 _lib = None
@@ -71,6 +71,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_order_statistic.argtypes = [vp, _dp, l, l, _dp]
     L.hb_gaia_batch.argtypes = [vp, _dp, l, d, _dp, _dp, _dp, _dp]
     L.hb_fp64_peak.argtypes = [vp, d, _dp]
+    L.hb_time_kernels.argtypes = [vp, i]
+    L.hb_last_eval_kernel_ms.argtypes = [vp, _dp]
     L.hb_launch_count.argtypes = [vp]
     L.hb_launch_count.restype = l
     if path == _build.LIB:
@@ -224,6 +226,14 @@ class Context:
         ll = np.empty(p.shape[0])
         self._ck(self._L.hb_gaia_batch(self._h, _p(p), p.shape[0], float(D), _p(dd), _p(ee), _p(mags), _p(ll)))
         return mags, ll
+
+    def time_kernels(self, enable: bool = True) -> None:
+        self._ck(self._L.hb_time_kernels(self._h, int(enable)))
+
+    def last_eval_kernel_ms(self) -> float:
+        out = C.c_double()
+        self._ck(self._L.hb_last_eval_kernel_ms(self._h, C.byref(out)))
+        return out.value
 
     def fp64_peak_tflops(self, seconds: float = 0.3) -> float:
         out = C.c_double()

@@ -91,6 +91,10 @@ int hb_gaia_batch(hb_ctx* ctx, const double* p6, long n, double D, const double*
 /* ---- measurement ----------------------------------------------------------------------- */
 /* DFMA throughput of the device in TFLOP/s (2 flop per FMA), the FP64 roofline denominator. */
 int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);
+/* When enabled, every likelihood / light-curve call records CUDA events around its k_chain_eval
+ * launch on the launching stream; hb_last_eval_kernel_ms waits for and returns that duration. */
+int hb_time_kernels(hb_ctx* ctx, int enable);
+int hb_last_eval_kernel_ms(hb_ctx* ctx, double* ms);
 /* Number of kernel launches issued by this context since creation. */
 long hb_launch_count(const hb_ctx* ctx);
 

@@ -25,6 +25,7 @@ static inline double __hiloint2double(int hi, int lo) { return __longlong_as_dou
 static inline double __int2double_rn(int x) { return (double)x; }
 static inline int __double2int_rn(double x) { return (int)nearbyint(x); }
 #define HB_HOST_EMUL 1
+#define __constant__ static const
 #include "hb_device_host.cuh"
 using namespace hb;
 
@@ -53,7 +54,7 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out)
     const double md[5] = {1000, 1, 1, 1, 1}, me[4] = {1e15, 1e15, 1e15, 1e15};
     ChainConst cc;
     chain_prologue(p, default_mags(md, me, 1, 0), cc);
-    for (long i = 0; i < n; i++) out[i] = raw_flux(cc, t[i]);
+    for (long i = 0; i < n; i++) out[i] = raw_flux(cc, __dmul_rn(t[i], kSecDay));
 }
 
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
@@ -62,3 +63,21 @@ extern "C" void emul_finish(const double* u, long n, double med, double blend, d
 }
 
 extern "C" double emul_fmod_twopi(double M) { return fmod_twopi(M); }
+
+extern "C" void emul_sincos(const double* x, long n, double* s, double* c)
+{
+    for (long i = 0; i < n; i++) sincos_lean(x[i], s[i], c[i]);
+}
+extern "C" void emul_div(const double* a, const double* b, long n, double* q, double* r)
+{
+    for (long i = 0; i < n; i++) { q[i] = div_fast(a[i], b[i]); r[i] = rcp_fast(b[i]); }
+}
+// the Markstein phase division of kepler_point: must equal IEEE x / P
+extern "C" void emul_phase_div(const double* x, const double* P, long n, double* out)
+{
+    for (long i = 0; i < n; i++) {
+        const double rP = __drcp_rn(P[i]);
+        const double q0 = __dmul_rn(x[i], rP);
+        out[i] = fma(fma(-P[i], q0, x[i]), rP, q0);
+    }
+}
