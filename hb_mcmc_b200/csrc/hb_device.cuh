@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #ifndef HB_NEWTON_UNROLL
-#define HB_NEWTON_UNROLL 1
+#define HB_NEWTON_UNROLL 5
 #endif
 
 namespace hb {
@@ -314,6 +314,13 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
 // DFMA, no UMOV), quadrant logic is 9 integer ops, divisions are a MUFU seed + Newton steps.
 
 #ifndef HB_HOST_EMUL
+// true when the predicate holds on every lane that is executing this call together
+__device__ __forceinline__ bool warp_all(bool p) { return __all_sync(__activemask(), p); }
+#else
+static inline bool warp_all(bool p) { return p; }
+#endif
+
+#ifndef HB_HOST_EMUL
 __device__ __forceinline__ double rcp_seed(double x)
 {
     double y;
@@ -354,45 +361,59 @@ __constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.3888888888874109
 __constant__ double kRed[5] = {1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983880e-33,
                                6.36619772367581382433e-01, 6755399441055744.0};
 
-// sin and cos of x, ~1 ulp, for |x| <= 1e5 (Kepler iterates are O(10)); the library handles the rest.
+// All per-sample routines below are written V samples wide (V = 1 or 2 per thread): the V
+// dependency chains are independent, so the FP64 pipe (8-cycle DFMA latency, one warp
+// instruction per 2 cycles per SM sub-partition, measured) always has a second chain to issue
+// from, and the per-sample bookkeeping (constant loads, loop control) is shared.
+
 static __device__ __noinline__ void sincos_library(double x, double* s, double* c) { sincos(x, s, c); }
 
-__device__ __forceinline__ void sincos_lean(double x, double& s_out, double& c_out)
+// sin and cos, ~1 ulp, for |x| <= 1e5 (Kepler iterates are O(10)); the library handles the rest.
+template <int V>
+__device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out)[V], double (&c_out)[V])
 {
-    if (!(fabs(x) <= 1.0e5)) {  // cold: wild Newton iterates at e -> 1, inf, NaN
-        double s, c;
-        sincos_library(x, &s, &c);
-        s_out = s;
-        c_out = c;
-        return;
+    bool cold = false;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        cold |= (__double2hiint(x[j]) & 0x7fffffff) > 0x40f86a00;  // |x| > ~1e5, inf, NaN
+        const double t = fma(x[j], kRed[3], kRed[4]);
+        const int k = __double2loint(t);  // nearest integer to x * 2/pi sits in the low word
+        const double kd = t - kRed[4];
+        double r = fma(-kd, kRed[0], x[j]);
+        r = fma(-kd, kRed[1], r);
+        r = fma(-kd, kRed[2], r);
+        const double z = r * r;
+        double ps = fma(z, kSinC[5], kSinC[4]);
+        double pc = fma(z, kCosC[5], kCosC[4]);
+        ps = fma(z, ps, kSinC[3]);
+        pc = fma(z, pc, kCosC[3]);
+        ps = fma(z, ps, kSinC[2]);
+        pc = fma(z, pc, kCosC[2]);
+        ps = fma(z, ps, kSinC[1]);
+        pc = fma(z, pc, kCosC[1]);
+        ps = fma(z, ps, kSinC[0]);
+        pc = fma(z, pc, kCosC[0]);
+        const double sr = fma(z * r, ps, r);
+        const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+        // quadrant: k odd swaps, bit 1 of k (sin) / of k+1 (cos) flips the sign
+        const bool odd = k & 1;
+        const double sa = odd ? cr : sr;
+        const double ca = odd ? sr : cr;
+        const int ssign = (k & 2) << 30;
+        const int csign = ((k + 1) & 2) << 30;
+        s_out[j] = __hiloint2double(__double2hiint(sa) ^ ssign, __double2loint(sa));
+        c_out[j] = __hiloint2double(__double2hiint(ca) ^ csign, __double2loint(ca));
     }
-    const double t = fma(x, kRed[3], kRed[4]);
-    const int k = __double2loint(t);  // nearest integer to x * 2/pi sits in the low word
-    const double kd = t - kRed[4];
-    double r = fma(-kd, kRed[0], x);
-    r = fma(-kd, kRed[1], r);
-    r = fma(-kd, kRed[2], r);
-    const double z = r * r;
-    double ps = fma(z, kSinC[5], kSinC[4]);
-    ps = fma(z, ps, kSinC[3]);
-    ps = fma(z, ps, kSinC[2]);
-    ps = fma(z, ps, kSinC[1]);
-    ps = fma(z, ps, kSinC[0]);
-    const double sr = fma(z * r, ps, r);
-    double pc = fma(z, kCosC[5], kCosC[4]);
-    pc = fma(z, pc, kCosC[3]);
-    pc = fma(z, pc, kCosC[2]);
-    pc = fma(z, pc, kCosC[1]);
-    pc = fma(z, pc, kCosC[0]);
-    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-    // quadrant: k odd swaps, bit 1 of k (sin) / of k+1 (cos) flips the sign
-    const bool odd = k & 1;
-    const double sa = odd ? cr : sr;
-    const double ca = odd ? sr : cr;
-    const int ssign = (k & 2) << 30;
-    const int csign = ((k + 1) & 2) << 30;
-    s_out = __hiloint2double(__double2hiint(sa) ^ ssign, __double2loint(sa));
-    c_out = __hiloint2double(__double2hiint(ca) ^ csign, __double2loint(ca));
+    if (cold) {  // wild Newton iterates at e -> 1, inf, NaN
+#pragma unroll
+        for (int j = 0; j < V; j++)
+            if ((__double2hiint(x[j]) & 0x7fffffff) > 0x40f86a00) {
+                double s, c;
+                sincos_library(x[j], &s, &c);
+                s_out[j] = s;
+                c_out[j] = c;
+            }
+    }
 }
 
 static __device__ __noinline__ double fmod_library(double a, double b) { return fmod(a, b); }
@@ -414,41 +435,65 @@ __device__ __forceinline__ double fmod_twopi(double M)
     return copysign(r, M);
 }
 
-struct OrbitPoint {
-    double cE, sE, den;  // cos E, sin E, 1 - e cos E
-};
-
 // likelihood3.c:149-160.  tsec = t * 86400 exactly as the reference forms it.  The mean anomaly
 // is bit-identical with the reference's 2 pi (t - T0) / P: the two products are explicitly
 // rounded and the division is the correctly rounded Markstein sequence on rP = RN(1/P).
-// Starter E0 = M + 0.85 e sign(sin M), exactly five Newton steps.
-__device__ __forceinline__ OrbitPoint kepler_point(double tsec, const double e, const double T0s, const double Ps,
-                                                  const double rPs)
+// Starter E0 = M + 0.85 e sign(sin M), exactly five Newton steps.  Outputs cos E, sin E and
+// den = 1 - e cos E.
+template <int V>
+__device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
+                                              const double rPs, double (&cE)[V], double (&sE)[V], double (&den)[V])
 {
-    const double x = __dmul_rn(kTwoPi, __dsub_rn(tsec, T0s));
-    const double q0 = __dmul_rn(x, rPs);
-    double M = fma(fma(-Ps, q0, x), rPs, q0);
-    M = fmod_twopi(M);
-    // sign(sin M) for |M| < fl(2 pi): positive on (0, fl(pi)], negative above (sin(fl(pi)) > 0)
-    const double am = fabs(M);
-    double sg = (am <= kPi) ? 1.0 : -1.0;
-    sg = (M < 0.0) ? -sg : sg;
-    sg = (am == 0.0) ? 0.0 : sg;
-    double E = fma(0.85 * e, sg, M);
-    double sE, cE;
+    double M[V], E[V], dE[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        const double x = __dmul_rn(kTwoPi, __dsub_rn(tsec[j], T0s));
+        const double q0 = __dmul_rn(x, rPs);
+        const double m = fmod_twopi(fma(fma(-Ps, q0, x), rPs, q0));
+        // sign(sin M) for |M| < fl(2 pi): positive on (0, fl(pi)], negative above (sin(fl(pi)) > 0)
+        const double am = fabs(m);
+        double sg = (am <= kPi) ? 1.0 : -1.0;
+        sg = (m < 0.0) ? -sg : sg;
+        sg = (am == 0.0) ? 0.0 : sg;
+        M[j] = m;
+        E[j] = fma(0.85 * e, sg, m);
+    }
+    // The reference always takes five Newton steps.  Once a step is below 2^-27 the next iterate
+    // is the root to rounding (quadratic convergence: the following step is ~C step^2 < 1e-16) and
+    // the reference's remaining steps only move E by rounding noise of f(E) -- the same noise any
+    // other sin/cos implementation produces.  So the warp leaves the loop as soon as ALL its lanes
+    // have such a step (warp-uniform, no divergence); lanes that never converge (the e -> 1 tail
+    // near periastron) run all five steps exactly like the reference.
+    bool tiny = false;
 #pragma unroll kNewtonUnroll
     for (int k = 0; k < 5; k++) {
-        sincos_lean(E, sE, cE);
-        const double num = fma(-e, sE, E) - M;
-        const double den = fma(-e, cE, 1.0);
-        E -= div_fast(num, den);
+        sincos_lean<V>(E, sE, cE);
+        tiny = true;
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const double num = fma(-e, sE[j], E[j]) - M[j];
+            const double dn = fma(-e, cE[j], 1.0);
+            const double En = E[j] - div_fast(num, dn);
+            dE[j] = E[j] - En;  // the step actually applied (exact difference of neighbours)
+            E[j] = En;
+            tiny &= (__double2hiint(dE[j]) & 0x7fffffff) < 0x3e400000;  // |dE| < 2^-27
+        }
+        tiny = warp_all(tiny);
+        if (tiny) break;
     }
-    sincos_lean(E, sE, cE);
-    OrbitPoint o;
-    o.cE = cE;
-    o.sE = sE;
-    o.den = fma(-e, cE, 1.0);
-    return o;
+    if (tiny) {
+        // sin/cos(E_prev - dE) to first order: the neglected dE^2/2 < 3e-17 is relative
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const double c0 = cE[j], s0 = sE[j];
+            cE[j] = fma(s0, dE[j], c0);
+            sE[j] = fma(-c0, dE[j], s0);
+        }
+    } else {
+        sincos_lean<V>(E, sE, cE);
+    }
+#pragma unroll
+    for (int j = 0; j < V; j++) den[j] = fma(-e, cE[j], 1.0);
 }
 
 // likelihood3.c:353-389 with R1 >= R2 already sorted and d already in Rsun.  Written with
@@ -481,43 +526,56 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
     return area;
 }
 
-// Raw (un-normalised) template value Amag1 + Amag2 of likelihood3.c:649-675 at one sample
+// Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
-__device__ __forceinline__ double raw_flux(const ChainConst& cc, double tsec)
+template <int V>
+__device__ __forceinline__ void raw_flux(const ChainConst& cc, const double (&tsec)[V], double (&u)[V])
 {
-    const OrbitPoint o = kepler_point(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs);
-    const double beta = rcp_fast(o.den);  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
-    const double cnu = (o.cE - cc.e) * beta;
-    const double snu = cc.sq1me2 * o.sE * beta;
-    const double c = cc.cw * cnu - cc.sw * snu;  // cos(omega0 + nu)
-    const double s = cc.sw * cnu + cc.cw * snu;  // sin(omega0 + nu)
-    const double c2 = fma(2.0 * c, c, -1.0);     // cos 2x
-    const double s3 = s * fma(-4.0 * s, s, 3.0); // sin 3x
-    const double c4 = fma(2.0 * c2, c2, -1.0);   // cos 4x
+    double cE[V], sE[V], den[V];
+    kepler_points<V>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, cE, sE, den);
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        const double beta = rcp_fast(den[j]);  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
+        const double cnu = (cE[j] - cc.e) * beta;
+        const double snu = cc.sq1me2 * sE[j] * beta;
+        const double c = cc.cw * cnu - cc.sw * snu;  // cos(omega0 + nu)
+        const double s = cc.sw * cnu + cc.cw * snu;  // sin(omega0 + nu)
+        const double c2 = fma(2.0 * c, c, -1.0);     // cos 2x
+        const double s3 = s * fma(-4.0 * s, s, 3.0); // sin 3x
+        const double c4 = fma(2.0 * c2, c2, -1.0);   // cos 4x
 
-    const double P5 = fma(cc.d4, c4, fma(cc.d2, c2, cc.d0));
-    const double P4 = fma(cc.c3, s3, cc.c1 * s);
-    const double P3 = fma(cc.b1, c2, cc.b0);
-    const double P2 = fma(cc.a2, c2, fma(cc.a1, s, cc.a0));
-    const double poly = fma(beta, fma(beta, fma(beta, P5, P4), P3), P2);
-    double u = fma(beta * beta, poly, fma(cc.K1, c, cc.K0));
+        const double P5 = fma(cc.d4, c4, fma(cc.d2, c2, cc.d0));
+        const double P4 = fma(cc.c3, s3, cc.c1 * s);
+        const double P3 = fma(cc.b1, c2, cc.b0);
+        const double P2 = fma(cc.a2, c2, fma(cc.a1, s, cc.a0));
+        const double poly = fma(beta, fma(beta, fma(beta, P5, P4), P3), P2);
+        double uj = fma(beta * beta, poly, fma(cc.K1, c, cc.K0));
 
-    // eclipse: projected separation in Rsun (likelihood3.c:173-176, 365)
-    const double sc = s * cc.ci;
-    const double proj2 = fma(c, c, sc * sc);
-    const double rr = cc.ar * o.den;
-    const double d2 = rr * rr * proj2;
-    const double lim = cc.Rb + cc.Rs;
-    if (d2 < lim * lim * (1.0 + 1e-9)) {
-        const double d = fabs(rr * sqrt(proj2));
-        if (!(d >= lim)) {
-            const double area = eclipse_area_dev(cc.Rb, cc.Rs, d);
-            const double zz = s * cc.si;  // sign of ZZ (likelihood3.c:173,669-670)
-            if (zz < 0.0) u -= area * cc.ecl2;
-            else if (zz > 0.0) u -= area * cc.ecl1;
+        // eclipse: projected separation in Rsun (likelihood3.c:173-176, 365)
+        const double sc = s * cc.ci;
+        const double proj2 = fma(c, c, sc * sc);
+        const double rr = cc.ar * den[j];
+        const double d2 = rr * rr * proj2;
+        const double lim = cc.Rb + cc.Rs;
+        if (d2 < lim * lim * (1.0 + 1e-9)) {
+            const double d = fabs(rr * sqrt(proj2));
+            if (!(d >= lim)) {
+                const double area = eclipse_area_dev(cc.Rb, cc.Rs, d);
+                const double zz = s * cc.si;  // sign of ZZ (likelihood3.c:173,669-670)
+                if (zz < 0.0) uj -= area * cc.ecl2;
+                else if (zz > 0.0) uj -= area * cc.ecl1;
+            }
         }
+        u[j] = uj;
     }
-    return u;
+}
+
+__device__ __forceinline__ double raw_flux1(const ChainConst& cc, double tsec)
+{
+    const double t[1] = {tsec};
+    double u[1];
+    raw_flux<1>(cc, t, u);
+    return u[0];
 }
 
 // likelihood3.c:681-685 in the reference's order: ((u - med) + 1) blended, times flux_tune

@@ -122,7 +122,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         double lo = -INFINITY, hi = INFINITY;
         if (bracketed) {
             const uint32_t seed = (uint32_t)cc.seed;
-            const double us = raw_flux(cc, tsec[sample_index(tid, kThreads, N, seed)]);
+            const double us = raw_flux1(cc, tsec[sample_index(tid, kThreads, N, seed)]);
             // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
             const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
             int r_lo, r_hi, r_mid;
@@ -153,35 +153,47 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const double u0 = sm.pivot;
         const double A = cc.ft * (1.0 - cc.blend), ft = cc.ft;
 
-        // ---- model pass ----
+        // ---- model pass: kPointsPerThread samples per thread and iteration ----
         int nanflag = 0, c_lt = 0;
         double S0 = 0., S1 = 0., S2 = 0.;
-        for (int base = 0; base < N; base += kThreads) {
-            const int i = base + tid;
-            const bool valid = i < N;
-            const double u = raw_flux(cc, tsec[valid ? i : N - 1]);
-            nanflag |= (u != u);
-            if (valid) tmpl[i] = dkey(u);
-            c_lt += (valid & (u < lo));
-            const bool inr = valid & (u >= lo) & (u <= hi);
-            const unsigned mask = __ballot_sync(0xffffffffu, inr);
-            if (mask) {
-                const int leader = __ffs(mask) - 1;
-                int basepos = 0;
-                if (lane == leader) basepos = atomicAdd(&sm.ctl.cnt, __popc(mask));
-                basepos = __shfl_sync(0xffffffffu, basepos, leader);
-                if (inr) {
-                    const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
-                    if (pos < cand_cap) cand[pos] = dkey(u);
-                }
+        constexpr int V = kPointsPerThread;
+        for (int base = 0; base < N; base += V * kThreads) {
+            int idx[V];
+            double ts[V], u[V];
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                idx[j] = base + j * kThreads + tid;
+                ts[j] = tsec[idx[j] < N ? idx[j] : N - 1];
             }
-            if (flux != nullptr && valid) {
-                const double wi = w[i];
-                const double a = fma(A, u - u0, ft - flux[i]);
-                const double r = a * wi;
-                S0 = fma(r, r, S0);
-                S1 = fma(r, wi, S1);
-                S2 = fma(wi, wi, S2);
+            raw_flux<V>(cc, ts, u);
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const int i = idx[j];
+                const bool valid = i < N;
+                const double uj = u[j];
+                nanflag |= (uj != uj);
+                if (valid) tmpl[i] = dkey(uj);
+                c_lt += (valid & (uj < lo));
+                const bool inr = valid & (uj >= lo) & (uj <= hi);
+                const unsigned mask = __ballot_sync(0xffffffffu, inr);
+                if (mask) {
+                    const int leader = __ffs(mask) - 1;
+                    int basepos = 0;
+                    if (lane == leader) basepos = atomicAdd(&sm.ctl.cnt, __popc(mask));
+                    basepos = __shfl_sync(0xffffffffu, basepos, leader);
+                    if (inr) {
+                        const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
+                        if (pos < cand_cap) cand[pos] = dkey(uj);
+                    }
+                }
+                if (flux != nullptr && valid) {
+                    const double wi = w[i];
+                    const double a = fma(A, uj - u0, ft - flux[i]);
+                    const double r = a * wi;
+                    S0 = fma(r, r, S0);
+                    S1 = fma(r, wi, S1);
+                    S2 = fma(wi, wi, S2);
+                }
             }
         }
         const int any_nan = __syncthreads_or(nanflag);
@@ -285,10 +297,12 @@ __global__ void k_traj(const double* __restrict__ times, int Nt, const double* _
     const double P = tp[2], e = tp[3], inc = tp[4], w0 = tp[5], T0 = tp[6];
     const double Mtot = Ma + Mb;
     const double a = pow(kG * Mtot * sq(P) / sq(2 * kPi), 1. / 3.);
-    const OrbitPoint o = kepler_point(__dmul_rn(times[i], kSecDay), e, T0, P, __drcp_rn(P));
-    const double r = a * o.den;
+    const double ts[1] = {__dmul_rn(times[i], kSecDay)};
+    double cE[1], sE[1], den[1];
+    kepler_points<1>(ts, e, T0, P, __drcp_rn(P), cE, sE, den);
+    const double r = a * den[0];
     const double sq1 = sqrt(1 - e * e);
-    const double nu = atan2(sq1 * o.sE, o.cE - e);
+    const double nu = atan2(sq1 * sE[0], cE[0] - e);
     double sw, cw, si, ci;
     sincos(w0 + nu, &sw, &cw);
     sincos(inc, &si, &ci);

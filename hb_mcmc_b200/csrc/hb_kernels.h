@@ -9,10 +9,27 @@ namespace hb {
 struct ChainConst;
 struct MagSetup;
 
-constexpr int kEvalThreads = 256;   // threads per CTA of k_chain_eval
-constexpr int kEvalCtasPerSm = 2;   // resident CTAs per SM (register budget: 128/thread)
-constexpr int kCandA = 8192;        // shared-memory survivor buffers of the select (keys)
-constexpr int kCandB = 2048;
+// tuning knobs (overridable with -D for sweeps; the defaults are the measured best on B200)
+#ifndef HB_EVAL_THREADS
+#define HB_EVAL_THREADS 256
+#endif
+#ifndef HB_EVAL_CTAS
+#define HB_EVAL_CTAS 4
+#endif
+#ifndef HB_CAND_A
+#define HB_CAND_A 4096
+#endif
+#ifndef HB_CAND_B
+#define HB_CAND_B 1024
+#endif
+#ifndef HB_POINTS_PER_THREAD
+#define HB_POINTS_PER_THREAD 1
+#endif
+constexpr int kPointsPerThread = HB_POINTS_PER_THREAD;  // independent samples in flight per thread
+constexpr int kEvalThreads = HB_EVAL_THREADS;  // threads per CTA of k_chain_eval
+constexpr int kEvalCtasPerSm = HB_EVAL_CTAS;   // resident CTAs per SM (sets the register budget)
+constexpr int kCandA = HB_CAND_A;              // shared-memory survivor buffers of the select (keys)
+constexpr int kCandB = HB_CAND_B;
 
 size_t eval_smem_bytes();
 cudaError_t configure_eval();

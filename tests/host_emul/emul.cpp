@@ -54,7 +54,15 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out)
     const double md[5] = {1000, 1, 1, 1, 1}, me[4] = {1e15, 1e15, 1e15, 1e15};
     ChainConst cc;
     chain_prologue(p, default_mags(md, me, 1, 0), cc);
-    for (long i = 0; i < n; i++) out[i] = raw_flux(cc, __dmul_rn(t[i], kSecDay));
+    long i = 0;
+    for (; i + 2 <= n; i += 2) {  // the two-wide path the kernel uses
+        const double ts[2] = {__dmul_rn(t[i], kSecDay), __dmul_rn(t[i + 1], kSecDay)};
+        double u[2];
+        raw_flux<2>(cc, ts, u);
+        out[i] = u[0];
+        out[i + 1] = u[1];
+    }
+    for (; i < n; i++) out[i] = raw_flux1(cc, __dmul_rn(t[i], kSecDay));
 }
 
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
@@ -66,7 +74,13 @@ extern "C" double emul_fmod_twopi(double M) { return fmod_twopi(M); }
 
 extern "C" void emul_sincos(const double* x, long n, double* s, double* c)
 {
-    for (long i = 0; i < n; i++) sincos_lean(x[i], s[i], c[i]);
+    for (long i = 0; i < n; i++) {
+        const double xv[1] = {x[i]};
+        double sv[1], cv[1];
+        sincos_lean<1>(xv, sv, cv);
+        s[i] = sv[0];
+        c[i] = cv[0];
+    }
 }
 extern "C" void emul_div(const double* a, const double* b, long n, double* q, double* r)
 {
