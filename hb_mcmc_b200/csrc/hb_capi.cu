@@ -500,6 +500,25 @@ int hb_order_statistic(hb_ctx* ctx, const double* x, long n, long k, double* out
     return HB_OK;
 }
 
+int hb_remove_median(hb_ctx* ctx, double* arr, long n)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && !arr) || n > 0x7fffff00L) return fail_arg(ctx, "hb_remove_median: bad argument");
+    if (n == 0) return HB_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_scratch(ctx, n)) != HB_OK) return rc;
+    if ((rc = stage_times(ctx, arr, n)) != HB_OK) return rc;
+    // index rule of likelihood3.c:97-101 (quirk Q3); n == 1 uses the only element
+    long k = (n % 2 == 0) ? n / 2 : n / 2 + 1;
+    if (k > n - 1) k = n - 1;
+    CK(launch_order_stat(ctx->d_times2, (int)n, (int)k, ctx->d_scratch, ctx->scratch_stride, ctx->d_small + 48, ctx->stream));
+    CK(launch_subtract(ctx->d_times2, (int)n, ctx->d_small + 48, ctx->stream));
+    ctx->launches += 2;
+    return download(ctx, arr, ctx->d_times2, (size_t)n);
+}
+
 int hb_scalar(hb_ctx* ctx, int op, const double* args, int nargs, double* out)
 {
     if (!ctx) return HB_ERR_ARG;

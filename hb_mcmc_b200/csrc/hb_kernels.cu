@@ -283,6 +283,13 @@ k_order_stat(const double* __restrict__ x, int n, int k, uint64_t* __restrict__ 
     if (threadIdx.x == 0) { out[0] = v; out[1] = 0.0; }
 }
 
+// arr[i] -= *value (remove_median's subtraction, likelihood3.c:103); value lives on the device
+__global__ void k_subtract(double* __restrict__ arr, int n, const double* __restrict__ value)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) arr[i] -= value[0];
+}
+
 // traj() of likelihood3.c:125-185 for one parameter set: d, Z1, Z2, r [cm], nu [rad].
 // tp = {M1, M2 [g], P [s], e, inc, omega0, T0 [s]}.  nu is reported through atan2 of the
 // algebraic sin/cos nu, which equals 2 atan(sqrt((1+e)/(1-e)) tan(E/2)) on (-pi, pi).
@@ -459,6 +466,13 @@ cudaError_t launch_order_stat(const double* x, int n, int k, uint64_t* scratch, 
                                          (int)sizeof(EvalShared));
     if (e != cudaSuccess) return e;
     k_order_stat<kEvalThreads><<<1, kEvalThreads, sizeof(EvalShared), s>>>(x, n, k, scratch, stride, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_subtract(double* arr, int n, const double* value, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_subtract<<<(n + 255) / 256, 256, 0, s>>>(arr, n, value);
     return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* 
                               int* counter, cudaStream_t s);
 cudaError_t launch_order_stat(const double* x, int n, int k, uint64_t* scratch, size_t stride, double* out,
                               cudaStream_t s);
+cudaError_t launch_subtract(double* arr, int n, const double* value, cudaStream_t s);
 cudaError_t launch_traj(const double* times, int Nt, const double* tp, double* d, double* Z1, double* Z2, double* rr,
                         double* ff, cudaStream_t s);
 cudaError_t launch_scalar(int op, const double* args, double* out, cudaStream_t s);

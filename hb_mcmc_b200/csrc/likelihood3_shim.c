@@ -1,0 +1,247 @@
+/*
+ * likelihood3_shim.c -- libhb_likelihood3.so: the entry points of the reference's likelihood3.h
+ * (likelihood3.h:68-89, plus the four helpers likelihood3.pxd:10-13 reaches into) with the SAME
+ * names, argument lists and side effects, computed on the B200 through the C ABI of hb_b200.h.
+ *
+ * Link the unmodified reference driver / binding against this library INSTEAD of compiling
+ * likelihood3.c:
+ *     gcc -O3 -std=c99 -fopenmp mcmc_wrapper2.c -L<dir> -lhb_likelihood3 -lhb_b200 -lm
+ *
+ * Every function that computes runs on the device.  There is no CPU fallback: if the context
+ * cannot be created (no B200, no driver) the first call prints the reason and abort()s, because
+ * the reference API has no error channel (SURVEY.md 8b "Error convention: none").
+ * Only set_limits / initialize_proposals (constant tables, likelihood3.c:986-1211) and the
+ * generic array helpers partition / quickSort (likelihood3.c:48-83, not on the hot path: the
+ * device model never sorts) are plain host C.
+ *
+ * Threading: the reference calls loglikelihood from up to 25 OpenMP threads on shared arrays
+ * (mcmc_wrapper2.c:383,488-489).  All calls funnel into one context whose C ABI serialises
+ * them; correctness is preserved, the batched entry point hb_loglikelihood_batch is the fast path.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hb_b200.h"
+
+/* the three structs of likelihood3.h:39-66, redeclared (binary layout is the contract) */
+struct bounds { double lo; double hi; };
+struct gauss_bounds { int flag; };
+typedef struct bounds bounds;
+typedef struct gauss_bounds gauss_bounds;
+
+#define NPARS HB_NPARS
+#define PI 3.14159265358979323846
+
+static hb_ctx *g_ctx = NULL;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_use_gmag = 1, g_use_color = 0; /* likelihood3.h:11-12 */
+
+/* cached copy of the last data set handed to loglikelihood() */
+static double *g_t = NULL, *g_f = NULL, *g_e = NULL;
+static long g_n = -1;
+
+static void die(const char *what, const char *why)
+{
+    fprintf(stderr, "libhb_likelihood3: %s failed: %s\n(no CPU fallback: a B200 and libhb_b200.so are required)\n", what, why);
+    abort();
+}
+
+static hb_ctx *ctx(void)
+{
+    pthread_mutex_lock(&g_mu);
+    if (!g_ctx) {
+        const char *dev = getenv("HB_DEVICE");
+        const char *env;
+        if (hb_create(&g_ctx, dev ? atoi(dev) : 0) != HB_OK) die("hb_create", hb_global_error());
+        if ((env = getenv("HB_USE_GMAG"))) g_use_gmag = atoi(env);
+        if ((env = getenv("HB_USE_COLOR_INFO"))) g_use_color = atoi(env);
+    }
+    pthread_mutex_unlock(&g_mu);
+    return g_ctx;
+}
+
+#define CK(call)                                                   \
+    do {                                                           \
+        if ((call) != HB_OK) die(#call, hb_last_error(g_ctx));     \
+    } while (0)
+
+/* runtime switch for the compile-time macros USE_GMAG / USE_COLOR_INFO (likelihood3.h:11-12) */
+void hb_shim_set_flags(int use_gmag, int use_color)
+{
+    ctx();
+    g_use_gmag = use_gmag;
+    g_use_color = use_color;
+}
+
+void hb_shim_shutdown(void)
+{
+    pthread_mutex_lock(&g_mu);
+    if (g_ctx) hb_destroy(g_ctx);
+    g_ctx = NULL;
+    free(g_t); free(g_f); free(g_e);
+    g_t = g_f = g_e = NULL;
+    g_n = -1;
+    pthread_mutex_unlock(&g_mu);
+}
+
+/* ---- likelihood3.h:68-70 ------------------------------------------------------------------ */
+double partition(double arr[], int low, int high)
+{
+    double pivot = arr[high];
+    int i = low - 1;
+    for (int j = low; j < high; j++)
+        if (arr[j] < pivot) {
+            i++;
+            double t = arr[i]; arr[i] = arr[j]; arr[j] = t;
+        }
+    double t = arr[i + 1]; arr[i + 1] = arr[high]; arr[high] = t;
+    return (i + 1);
+}
+
+void quickSort(double arr[], int low, int high)
+{
+    while (low < high) { /* recurse on the smaller side: bounded stack */
+        int p = (int)partition(arr, low, high);
+        if (p - low < high - p) { quickSort(arr, low, p - 1); low = p + 1; }
+        else { quickSort(arr, p + 1, high); high = p - 1; }
+    }
+}
+
+void remove_median(double *arr, long begin, long end)
+{
+    if (end > begin) CK(hb_remove_median(ctx(), arr + begin, end - begin));
+}
+
+/* ---- likelihood3.h:71-80 ------------------------------------------------------------------ */
+void traj(double *times, double *traj_pars, double *d_arr, double *Z1_arr, double *Z2_arr, double *rr_arr,
+          double *ff_arr, int Nt)
+{
+    CK(hb_traj(ctx(), times, Nt, traj_pars, d_arr, Z1_arr, Z2_arr, rr_arr, ff_arr));
+}
+
+static double scalar(int op, const double *a, int n)
+{
+    double out = 0.;
+    CK(hb_scalar(ctx(), op, a, n, &out));
+    return out;
+}
+
+double _getT(double logM) { return scalar(0, &logM, 1); }
+double _getR(double logM) { return scalar(1, &logM, 1); }
+double envelope_Temp(double logM) { return scalar(2, &logM, 1); }
+double envelope_Radius(double logM) { return scalar(3, &logM, 1); }
+double get_alpha_beam(double logT) { return scalar(4, &logT, 1); }
+
+double eclipse_area(double R1, double R2, double d)
+{
+    double a[3] = {R1, R2, d};
+    return scalar(5, a, 3);
+}
+
+double beaming(double P, double M1, double M2, double e, double inc, double omega0, double nu, double alpha_beam)
+{
+    double a[8] = {P, M1, M2, e, inc, omega0, nu, alpha_beam};
+    return scalar(6, a, 8);
+}
+
+double ellipsoidal(double P, double M1, double M2, double e, double inc, double omega0, double nu, double R1,
+                   double a_, double mu, double tau)
+{
+    double a[11] = {P, M1, M2, e, inc, omega0, nu, R1, a_, mu, tau};
+    return scalar(7, a, 11);
+}
+
+double reflection(double P, double M1, double M2, double e, double inc, double omega0, double nu, double R2,
+                  double alpha_ref1)
+{
+    double a[9] = {P, M1, M2, e, inc, omega0, nu, R2, alpha_ref1};
+    return scalar(8, a, 9);
+}
+
+/* ---- likelihood3.h:81-87 ------------------------------------------------------------------ */
+void calc_mags(double params[], double D, double *Gmg, double *BminusV, double *VminusG, double *GminusT)
+{
+    double o[9];
+    CK(hb_chain_info_batch(ctx(), params, 1, D, o));
+    *Gmg = o[4]; *BminusV = o[5]; *VminusG = o[6]; *GminusT = o[7];
+}
+
+void calc_light_curve(double *times, long Nt, double *pars, double *template_)
+{
+    CK(hb_calc_light_curve(ctx(), times, Nt, pars, template_));
+}
+
+void calc_radii_and_Teffs(double params[], double *R1, double *R2, double *Teff1, double *Teff2)
+{
+    double o[9];
+    CK(hb_chain_info_batch(ctx(), params, 1, 1000., o));
+    *R1 = o[0]; *R2 = o[1]; *Teff1 = o[2]; *Teff2 = o[3];
+}
+
+int RocheOverflow(double *pars)
+{
+    double o[9];
+    CK(hb_chain_info_batch(ctx(), pars, 1, 1000., o));
+    return (int)o[8];
+}
+
+double loglikelihood(double time[], double lightcurve[], double noise[], long N, double params[], double mag_data[],
+                     double magerr[])
+{
+    hb_ctx *c = ctx();
+    double out = 0.;
+    pthread_mutex_lock(&g_mu);
+    /* side effect of likelihood3.c:824-827: the caller's noise[] is clamped in place (quirk Q2) */
+    for (long i = 0; i < N; i++)
+        if (noise[i] < 1.e-5) noise[i] = 1.e-5;
+    size_t bytes = (size_t)(N > 0 ? N : 0) * sizeof(double);
+    if (N != g_n || memcmp(time, g_t, bytes) || memcmp(lightcurve, g_f, bytes) || memcmp(noise, g_e, bytes)) {
+        g_t = (double *)realloc(g_t, bytes + 8);
+        g_f = (double *)realloc(g_f, bytes + 8);
+        g_e = (double *)realloc(g_e, bytes + 8);
+        memcpy(g_t, time, bytes); memcpy(g_f, lightcurve, bytes); memcpy(g_e, noise, bytes);
+        g_n = N;
+        CK(hb_set_data(c, time, lightcurve, noise, N));
+    }
+    CK(hb_set_mags(c, mag_data, magerr, g_use_gmag, g_use_color));
+    CK(hb_loglikelihood_batch(c, params, 1, &out));
+    pthread_mutex_unlock(&g_mu);
+    return out;
+}
+
+/* ---- likelihood3.h:88-89: constant tables (likelihood3.c:986-1211) ------------------------ */
+void set_limits(bounds limited[], bounds limits[], gauss_bounds gauss_pars[], double LC_PERIOD)
+{
+    static const double lo[NPARS] = {-1.5, -1.5, -2.0, 0.0, 0.0, -PI, 0.0, -5., -5., 0.12, 0.3, 0.12, 0.3, 0.5, 0.5,
+                                     -0.3, -0.3, -5., -5., 0., 0.99};
+    static const double hi[NPARS] = {2.0, 2.0, 3.0, 1.0, PI, PI, 0.0, 5., 5., 0.20, 0.38, 0.20, 0.38, 1.5, 1.5,
+                                     0.3, 0.3, 5., 5., 1., 1.01};
+    for (int i = 0; i < NPARS; i++) {
+        limits[i].lo = lo[i];
+        limits[i].hi = hi[i];
+        limited[i].lo = 1;  /* 1 = reflecting */
+        limited[i].hi = 1;
+        gauss_pars[i].flag = (i >= 7 && i <= 18) ? 1 : 0;
+    }
+    limited[3].hi = 0.99;  /* quirk Q4: mode and limit of e swapped in the reference; kept */
+    limited[5].lo = 2;     /* 2 = periodic */
+    limited[5].hi = 2;
+    limits[6].hi = LC_PERIOD;
+}
+
+void initialize_proposals(double *sigma, double ***history)
+{
+    static const double base[NPARS] = {1e-2, 1e-2, 1e-8, 1e-2, 1e-3, 1e-3, 1e-3, 1e-1, 1e-1, 1e-2, 1e-2,
+                                       1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-1, 1e-1, 1e-3, 1e-5};
+    (void)history;
+    memcpy(sigma, base, sizeof(base));
+    if ((!g_use_color) || (!g_use_gmag)) { /* the enlarged set, likelihood3.c:1158-1179 */
+        sigma[0] = sigma[1] = 1e-1;
+        sigma[4] = sigma[5] = 1e-2;
+        sigma[6] = 1e-3;
+        for (int i = 9; i <= 18; i++) sigma[i] = 1e-1;
+    }
+}

@@ -27,7 +27,7 @@ class HBError(RuntimeError):
 ABI_SYMBOLS = (
     "hb_create", "hb_destroy", "hb_last_error", "hb_global_error", "hb_device_info", "hb_set_stream", "hb_sync",
     "hb_set_data", "hb_set_mags", "hb_loglikelihood_batch", "hb_loglikelihood_batch_dev", "hb_light_curve_batch",
-    "hb_calc_light_curve", "hb_chain_info_batch", "hb_traj", "hb_order_statistic", "hb_scalar", "hb_gaia_batch", "hb_fp64_peak",
+    "hb_calc_light_curve", "hb_chain_info_batch", "hb_traj", "hb_order_statistic", "hb_remove_median", "hb_scalar", "hb_gaia_batch", "hb_fp64_peak",
     "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count",
 )
 
@@ -69,6 +69,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_traj.argtypes = [vp, _dp, l, _dp] + [_dp] * 5
     L.hb_scalar.argtypes = [vp, i, _dp, i, _dp]
     L.hb_order_statistic.argtypes = [vp, _dp, l, l, _dp]
+    L.hb_remove_median.argtypes = [vp, _dp, l]
     L.hb_gaia_batch.argtypes = [vp, _dp, l, d, _dp, _dp, _dp, _dp]
     L.hb_fp64_peak.argtypes = [vp, d, _dp]
     L.hb_time_kernels.argtypes = [vp, i]
@@ -209,6 +210,11 @@ class Context:
         out = C.c_double()
         self._ck(self._L.hb_order_statistic(self._h, _p(a), a.size, int(k), C.byref(out)))
         return out.value
+
+    def remove_median(self, arr) -> np.ndarray:
+        a = _f64(arr).copy()
+        self._ck(self._L.hb_remove_median(self._h, _p(a), a.size))
+        return a
 
     def scalar(self, op: int, *args: float) -> float:
         a = _f64(args)

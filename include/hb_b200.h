@@ -78,6 +78,9 @@ int hb_traj(hb_ctx* ctx, const double* times, long nt, const double* traj_pars, 
 /* Exact k-th smallest (0-based) of x[0..n): the order statistic remove_median() obtains by
  * sorting a copy (likelihood3.c:86-105).  NaN in x gives NaN. */
 int hb_order_statistic(hb_ctx* ctx, const double* x, long n, long k, double* out);
+/* remove_median(arr, 0, n) of likelihood3.c:86-105 in place: subtracts the reference's "median"
+ * order statistic (even n: sorted[n/2], odd n: sorted[n/2+1], quirk Q3). */
+int hb_remove_median(hb_ctx* ctx, double* arr, long n);
 /* Scalar model functions evaluated on the device.  op / args:
  *   0 _getT(logM)  1 _getR(logM)  2 envelope_Temp(logM)  3 envelope_Radius(logM)
  *   4 get_alpha_beam(logT)  5 eclipse_area(R1,R2,d)  6 beaming(8 args)  7 ellipsoidal(11 args)
