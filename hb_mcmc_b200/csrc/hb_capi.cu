@@ -12,6 +12,7 @@
 #include "../../include/hb_b200.h"
 #include "hb_device.cuh"
 #include "hb_kernels.h"
+#include "hb_pt.cuh"
 
 using namespace hb;
 
@@ -616,5 +617,260 @@ int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops)
     *tflops = best;
     return HB_OK;
 }
+
+
+/* ---- parallel tempering ------------------------------------------------------------------ */
+}  // extern "C"
+
+struct hb_pt {
+    hb_ctx* ctx = nullptr;
+    PtConfig cfg;
+    PtConfig* d_cfg = nullptr;
+    int W = 0;
+    long iter = 0;
+    double *x = nullptr, *y = nullptr, *logLx = nullptr, *logLy = nullptr, *logPy = nullptr;
+    double *history = nullptr, *xmap = nullptr, *logLmap = nullptr, *tmp = nullptr;
+    int *index = nullptr, *jump = nullptr;
+    unsigned long long* counters = nullptr;
+};
+
+namespace {
+
+void fill_limits(PtConfig& c, int use_gmag, int use_color)
+{
+    // set_limits (likelihood3.c:986-1121) and initialize_proposals (:1123-1179)
+    static const double lo[21] = {-1.5, -1.5, -2.0, 0.0, 0.0, -kPi, 0.0, -5., -5., 0.12, 0.3, 0.12, 0.3, 0.5, 0.5,
+                                  -0.3, -0.3, -5., -5., 0., 0.99};
+    static const double hi[21] = {2.0, 2.0, 3.0, 1.0, kPi, kPi, 0.0, 5., 5., 0.20, 0.38, 0.20, 0.38, 1.5, 1.5,
+                                  0.3, 0.3, 5., 5., 1., 1.01};
+    static const double sg[21] = {1e-2, 1e-2, 1e-8, 1e-2, 1e-3, 1e-3, 1e-3, 1e-1, 1e-1, 1e-2, 1e-2,
+                                  1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-1, 1e-1, 1e-3, 1e-5};
+    for (int i = 0; i < 21; i++) {
+        c.lo[i] = lo[i];
+        c.hi[i] = hi[i];
+        c.mode_lo[i] = 1;
+        c.mode_hi[i] = 1;
+        c.gauss[i] = (i >= 7 && i <= 18) ? 1 : 0;
+        c.sigma[i] = sg[i];
+    }
+    c.mode_hi[3] = 0.99;  // quirk Q4
+    c.mode_lo[5] = c.mode_hi[5] = 2;
+    c.hi[6] = c.lc_period;
+    if ((!use_color) || (!use_gmag)) {
+        c.sigma[0] = c.sigma[1] = 1e-1;
+        c.sigma[4] = c.sigma[5] = 1e-2;
+        c.sigma[6] = 1e-3;
+        for (int i = 9; i <= 18; i++) c.sigma[i] = 1e-1;
+    }
+}
+
+int pt_eval_current(hb_pt* pt)
+{
+    hb_ctx* ctx = pt->ctx;
+    int rc;
+    if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
+    return run_eval(ctx, pt->x, pt->W, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, pt->logLx, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc_period, unsigned long long seed,
+                 double dtemp, int npast, int quirks)
+{
+    if (!ctx || !out) return HB_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n_temps < 1 || n_temps > kPtMaxTemps || n_ens < 1 || npast < 2 || !(dtemp > 1.0))
+        return fail_arg(ctx, "hb_pt_create: need 1 <= n_temps <= 128, n_ens >= 1, npast >= 2, dtemp > 1");
+    if (!ctx->has_data) {
+        ctx->err = "hb_pt_create: hb_set_data has not been called";
+        return HB_ERR_STATE;
+    }
+    DeviceGuard g(ctx->device);
+    hb_pt* pt = new hb_pt();
+    pt->ctx = ctx;
+    PtConfig& c = pt->cfg;
+    std::memset(&c, 0, sizeof(c));
+    c.n_temps = n_temps; c.n_ens = n_ens; c.npast = npast; c.quirks = quirks ? 1 : 0;
+    c.seed = seed; c.dtemp = dtemp;
+    c.temp[0] = 1.0;
+    for (int i = 1; i < n_temps; i++) c.temp[i] = c.temp[i - 1] * dtemp;
+    c.log_lc_period = log_lc_period;
+    c.lc_period = pow(10., log_lc_period);
+    c.gamma = 2.388 / sqrt(2. * kPtNpars);
+    fill_limits(c, ctx->ms.use_gmag, ctx->ms.use_color);
+    const int W = pt->W = n_temps * n_ens;
+    const size_t wd = (size_t)W * sizeof(double);
+    bool ok = cudaMalloc((void**)&pt->d_cfg, sizeof(PtConfig)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->x, wd * kPtNpars) == cudaSuccess && cudaMalloc((void**)&pt->y, wd * kPtNpars) == cudaSuccess &&
+              cudaMalloc((void**)&pt->logLx, wd) == cudaSuccess && cudaMalloc((void**)&pt->logLy, wd) == cudaSuccess &&
+              cudaMalloc((void**)&pt->logPy, wd) == cudaSuccess && cudaMalloc((void**)&pt->tmp, wd * (kPtNpars + 1)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->history, wd * kPtNpars * (size_t)npast) == cudaSuccess &&
+              cudaMalloc((void**)&pt->xmap, (size_t)n_ens * kPtNpars * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->logLmap, (size_t)n_ens * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->index, (size_t)W * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->jump, (size_t)W * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->counters, (size_t)n_ens * 8 * sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) {
+        fail_cuda(ctx, cudaGetLastError(), "hb_pt_create: cudaMalloc");
+        hb_pt_destroy(pt);
+        return HB_ERR_CUDA;
+    }
+    CK(cudaMemcpyAsync(pt->d_cfg, &c, sizeof(PtConfig), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(pt->history, 0, wd * kPtNpars * (size_t)npast, ctx->stream));
+    CK(cudaMemsetAsync(pt->counters, 0, (size_t)n_ens * 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(pt->xmap, 0, (size_t)n_ens * kPtNpars * sizeof(double), ctx->stream));
+    std::vector<int> idx((size_t)W);
+    for (int i = 0; i < W; i++) idx[i] = i % n_temps;  // index[i] = i (mcmc_wrapper2.c:333-338)
+    CK(cudaMemcpyAsync(pt->index, idx.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> ninf((size_t)n_ens, -INFINITY);
+    CK(cudaMemcpyAsync(pt->logLmap, ninf.data(), (size_t)n_ens * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = pt;
+    return HB_OK;
+}
+
+void hb_pt_destroy(hb_pt* pt)
+{
+    if (!pt) return;
+    {
+        DeviceGuard g(pt->ctx->device);
+        cudaStreamSynchronize(pt->ctx->stream);
+        cudaFree(pt->d_cfg); cudaFree(pt->x); cudaFree(pt->y); cudaFree(pt->logLx); cudaFree(pt->logLy);
+        cudaFree(pt->logPy); cudaFree(pt->tmp); cudaFree(pt->history); cudaFree(pt->xmap); cudaFree(pt->logLmap);
+        cudaFree(pt->index); cudaFree(pt->jump); cudaFree(pt->counters);
+    }
+    delete pt;
+}
+
+int hb_pt_init_random(hb_pt* pt)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(launch_pt_init_random(pt->d_cfg, pt->x, pt->W, ctx->stream));
+    ctx->launches += 1;
+    pt->iter = 0;
+    return pt_eval_current(pt);
+}
+
+int hb_pt_set_state(hb_pt* pt, const double* x)
+{
+    if (!pt || !x) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = upload(ctx, pt->x, x, (size_t)pt->W * kPtNpars)) != HB_OK) return rc;
+    return pt_eval_current(pt);
+}
+
+int hb_pt_step(hb_pt* pt, long n_iters)
+{
+    if (!pt || n_iters < 0) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
+    for (long k = 0; k < n_iters; k++) {
+        const unsigned it = (unsigned)pt->iter;
+        CK(launch_pt_propose(pt->d_cfg, it, pt->x, pt->index, pt->history, pt->y, pt->logPy, pt->jump, pt->W, ctx->stream));
+        if ((rc = run_eval(ctx, pt->y, pt->W, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, pt->logLy, nullptr)) != HB_OK) return rc;
+        CK(launch_pt_accept(pt->d_cfg, it, pt->x, pt->y, pt->logLx, pt->logLy, pt->logPy, pt->jump, pt->index, pt->history,
+                            pt->counters, pt->W, ctx->stream));
+        CK(launch_pt_swap(pt->d_cfg, it, pt->index, pt->logLx, pt->x, pt->counters, pt->xmap, pt->logLmap, pt->cfg.n_ens,
+                          ctx->stream));
+        ctx->launches += 3;
+        pt->iter++;
+    }
+    return HB_OK;
+}
+
+long hb_pt_iteration(const hb_pt* pt) { return pt ? pt->iter : -1; }
+
+int hb_pt_get_state(hb_pt* pt, double* x, double* logL, int* index)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (x && (rc = download(ctx, x, pt->x, (size_t)pt->W * kPtNpars)) != HB_OK) return rc;
+    if (logL && (rc = download(ctx, logL, pt->logLx, (size_t)pt->W)) != HB_OK) return rc;
+    if (index) {
+        CK(cudaMemcpyAsync(index, pt->index, (size_t)pt->W * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HB_OK;
+}
+
+int hb_pt_get_proposal(hb_pt* pt, double* y, double* logLy, double* logPy)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (y && (rc = download(ctx, y, pt->y, (size_t)pt->W * kPtNpars)) != HB_OK) return rc;
+    if (logLy && (rc = download(ctx, logLy, pt->logLy, (size_t)pt->W)) != HB_OK) return rc;
+    if (logPy && (rc = download(ctx, logPy, pt->logPy, (size_t)pt->W)) != HB_OK) return rc;
+    return HB_OK;
+}
+
+int hb_pt_get_cold(hb_pt* pt, double* x_cold, double* logL_cold)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    const int E = pt->cfg.n_ens;
+    CK(launch_pt_gather_cold(pt->d_cfg, pt->index, pt->x, pt->logLx, pt->tmp, pt->tmp + (size_t)E * kPtNpars, E, ctx->stream));
+    ctx->launches += 1;
+    int rc;
+    if (x_cold && (rc = download(ctx, x_cold, pt->tmp, (size_t)E * kPtNpars)) != HB_OK) return rc;
+    if (logL_cold && (rc = download(ctx, logL_cold, pt->tmp + (size_t)E * kPtNpars, (size_t)E)) != HB_OK) return rc;
+    return HB_OK;
+}
+
+int hb_pt_get_logL_by_rung(hb_pt* pt, double* out)
+{
+    if (!pt || !out) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(launch_pt_logL_by_rung(pt->d_cfg, pt->index, pt->logLx, pt->tmp, pt->W, ctx->stream));
+    ctx->launches += 1;
+    return download(ctx, out, pt->tmp, (size_t)pt->W);
+}
+
+int hb_pt_get_map(hb_pt* pt, double* xmap, double* logLmap)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (xmap && (rc = download(ctx, xmap, pt->xmap, (size_t)pt->cfg.n_ens * kPtNpars)) != HB_OK) return rc;
+    if (logLmap && (rc = download(ctx, logLmap, pt->logLmap, (size_t)pt->cfg.n_ens)) != HB_OK) return rc;
+    return HB_OK;
+}
+
+int hb_pt_get_counters(hb_pt* pt, unsigned long long* out)
+{
+    if (!pt || !out) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(out, pt->counters, (size_t)pt->cfg.n_ens * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+void* hb_pt_device_logL(hb_pt* pt) { return pt ? (void*)pt->logLx : nullptr; }
 
 }  // extern "C"

@@ -1,0 +1,165 @@
+// hb_pt.cu -- kernels of the device-resident parallel-tempering sampler (see hb_pt.cuh for the
+// algorithm, its reference citations and the positions on the reference's sampler bugs).
+//
+// Layout: E ensembles (independent PT ladders) x T rungs.  Chain state x[E*T][21], logL[E*T] is
+// indexed by chain SLOT; index[E][T] maps rung -> slot inside the ensemble (the reference swaps
+// this permutation, not the states, mcmc_wrapper2.c:812-816); the DE history ring is per RUNG
+// (history[j], mcmc_wrapper2.c:424,543-546).  One iteration = k_pt_propose -> k_prologue ->
+// k_chain_eval (the likelihood of all E*T proposals, one batch) -> k_pt_accept -> k_pt_swap.
+#include "hb_kernels.h"
+#include "hb_pt.cuh"
+
+namespace hb {
+
+__global__ void k_pt_init_random(const PtConfig* __restrict__ cfgp, double* __restrict__ x, int W)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const PtConfig& cfg = *cfgp;
+    PtRng g;
+    g.init(cfg.seed, (uint32_t)w, 0xFFFFFFFFu, 3u);
+    double* xw = x + (size_t)w * kPtNpars;
+    // uniform in the prior box, period pinned, T0 folded (mcmc_wrapper2.c:236-251)
+    for (int i = 0; i < kPtNpars; i++) {
+        const double u = g.next();
+        xw[i] = cfg.lo[i] + u * (cfg.hi[i] - cfg.lo[i]);
+    }
+    xw[2] = cfg.log_lc_period;
+    xw[6] = fmod(xw[6], cfg.lc_period);
+}
+
+__global__ void k_pt_propose(const PtConfig* __restrict__ cfgp, unsigned iter, const double* __restrict__ x,
+                             const int* __restrict__ index, const double* __restrict__ history, double* __restrict__ y,
+                             double* __restrict__ logPy, int* __restrict__ jump, int W)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;  // global rung id = ens * T + j
+    if (r >= W) return;
+    const PtConfig& cfg = *cfgp;
+    const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
+    const int c = ens * T + index[r];
+    double xl[kPtNpars], yl[kPtNpars], lp;
+    for (int i = 0; i < kPtNpars; i++) xl[i] = x[(size_t)c * kPtNpars + i];
+    const int jt = pt_propose(cfg, (uint32_t)r, iter, cfg.temp[j], xl, history + (size_t)r * cfg.npast * kPtNpars, yl, &lp);
+    for (int i = 0; i < kPtNpars; i++) y[(size_t)c * kPtNpars + i] = yl[i];
+    logPy[c] = lp;
+    jump[c] = jt;
+}
+
+// counters per ensemble: 0 acc (chain slot 0 accepted, the reference's `acc`), 1 DE trials of slot 0,
+// 2 DE accepted of slot 0, 3 accepted over all rungs, 4 proposals over all rungs, 5 swaps accepted,
+// 6 swaps proposed, 7 iterations
+__global__ void k_pt_accept(const PtConfig* __restrict__ cfgp, unsigned iter, double* __restrict__ x,
+                            const double* __restrict__ y, double* __restrict__ logLx, const double* __restrict__ logLy,
+                            const double* __restrict__ logPy, const int* __restrict__ jump, const int* __restrict__ index,
+                            double* __restrict__ history, unsigned long long* __restrict__ counters, int W)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= W) return;
+    const PtConfig& cfg = *cfgp;
+    const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
+    const int slot = index[r], c = ens * T + slot;
+    double xl[kPtNpars];
+    for (int i = 0; i < kPtNpars; i++) xl[i] = x[(size_t)c * kPtNpars + i];
+    const double logPx = pt_log_prior(xl, cfg.gauss);
+    const bool acc = pt_accept(cfg, (uint32_t)r, iter, cfg.temp[j], logLx[c], logLy[c], logPx, logPy[c]);
+    unsigned long long* cnt = counters + (size_t)ens * 8;
+    const int jt = jump[c];
+    if (slot == 0 && jt == 2) atomicAdd(&cnt[1], 1ull);
+    atomicAdd(&cnt[4], 1ull);
+    if (acc) {
+        for (int i = 0; i < kPtNpars; i++) {
+            xl[i] = y[(size_t)c * kPtNpars + i];
+            x[(size_t)c * kPtNpars + i] = xl[i];
+        }
+        logLx[c] = logLy[c];
+        atomicAdd(&cnt[3], 1ull);
+        if (slot == 0) {
+            atomicAdd(&cnt[0], 1ull);
+            if (jt == 2) atomicAdd(&cnt[2], 1ull);
+        }
+    }
+    // history[j][iter % NPAST] = x[chain_id]  (mcmc_wrapper2.c:381,543-546)
+    double* h = history + ((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars;
+    for (int i = 0; i < kPtNpars; i++) h[i] = xl[i];
+}
+
+__global__ void k_pt_swap(const PtConfig* __restrict__ cfgp, unsigned iter, int* __restrict__ index,
+                          const double* __restrict__ logLx, const double* __restrict__ x,
+                          unsigned long long* __restrict__ counters, double* __restrict__ xmap,
+                          double* __restrict__ logLmap, int E)
+{
+    const int ens = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ens >= E) return;
+    const PtConfig& cfg = *cfgp;
+    const int T = cfg.n_temps;
+    const int nacc = pt_swap_ensemble(cfg, (uint32_t)ens, iter, index + (size_t)ens * T, logLx + (size_t)ens * T);
+    unsigned long long* cnt = counters + (size_t)ens * 8;
+    cnt[5] += (unsigned long long)nacc;
+    cnt[6] += (unsigned long long)T;
+    cnt[7] += 1ull;
+    // MAP of the cold rung (mcmc_wrapper2.c:565-572)
+    const int c0 = ens * T + index[(size_t)ens * T];
+    if (logLx[c0] > logLmap[ens]) {
+        logLmap[ens] = logLx[c0];
+        for (int i = 0; i < kPtNpars; i++) xmap[(size_t)ens * kPtNpars + i] = x[(size_t)c0 * kPtNpars + i];
+    }
+}
+
+// gather the cold-rung state of every ensemble: out_x[E][21], out_logL[E]
+__global__ void k_pt_gather_cold(const PtConfig* __restrict__ cfgp, const int* __restrict__ index,
+                                 const double* __restrict__ x, const double* __restrict__ logLx,
+                                 double* __restrict__ out_x, double* __restrict__ out_logL, int E)
+{
+    const int ens = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ens >= E) return;
+    const int T = cfgp->n_temps;
+    const int c0 = ens * T + index[(size_t)ens * T];
+    out_logL[ens] = logLx[c0];
+    for (int i = 0; i < kPtNpars; i++) out_x[(size_t)ens * kPtNpars + i] = x[(size_t)c0 * kPtNpars + i];
+}
+
+// logL by rung (what logL.*.dat prints, mcmc_wrapper2.c:608-611)
+__global__ void k_pt_logL_by_rung(const PtConfig* __restrict__ cfgp, const int* __restrict__ index,
+                                  const double* __restrict__ logLx, double* __restrict__ out, int W)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= W) return;
+    const int T = cfgp->n_temps, ens = r / T;
+    out[r] = logLx[ens * T + index[r]];
+}
+
+#define LAUNCH1D(kern, n, s, ...)                                         \
+    do {                                                                  \
+        if ((n) > 0) kern<<<((n) + 127) / 128, 128, 0, s>>>(__VA_ARGS__); \
+        return cudaGetLastError();                                        \
+    } while (0)
+
+cudaError_t launch_pt_init_random(const PtConfig* cfg, double* x, int W, cudaStream_t s) { LAUNCH1D(k_pt_init_random, W, s, cfg, x, W); }
+cudaError_t launch_pt_propose(const PtConfig* cfg, unsigned iter, const double* x, const int* index, const double* history,
+                              double* y, double* logPy, int* jump, int W, cudaStream_t s)
+{
+    LAUNCH1D(k_pt_propose, W, s, cfg, iter, x, index, history, y, logPy, jump, W);
+}
+cudaError_t launch_pt_accept(const PtConfig* cfg, unsigned iter, double* x, const double* y, double* logLx,
+                             const double* logLy, const double* logPy, const int* jump, const int* index, double* history,
+                             unsigned long long* counters, int W, cudaStream_t s)
+{
+    LAUNCH1D(k_pt_accept, W, s, cfg, iter, x, y, logLx, logLy, logPy, jump, index, history, counters, W);
+}
+cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned iter, int* index, const double* logLx, const double* x,
+                           unsigned long long* counters, double* xmap, double* logLmap, int E, cudaStream_t s)
+{
+    LAUNCH1D(k_pt_swap, E, s, cfg, iter, index, logLx, x, counters, xmap, logLmap, E);
+}
+cudaError_t launch_pt_gather_cold(const PtConfig* cfg, const int* index, const double* x, const double* logLx,
+                                  double* out_x, double* out_logL, int E, cudaStream_t s)
+{
+    LAUNCH1D(k_pt_gather_cold, E, s, cfg, index, x, logLx, out_x, out_logL, E);
+}
+cudaError_t launch_pt_logL_by_rung(const PtConfig* cfg, const int* index, const double* logLx, double* out, int W,
+                                   cudaStream_t s)
+{
+    LAUNCH1D(k_pt_logL_by_rung, W, s, cfg, index, logLx, out, W);
+}
+
+}  // namespace hb

@@ -1,0 +1,251 @@
+// hb_pt.cuh -- parallel-tempering step of mcmc_wrapper2.c as device code (shared with the host
+// emulation used by the CPU tests).  One thread per rung (walker):
+//   propose  mcmc_wrapper2.c:390-481  jump scale, Gaussian (:1062-1088) or differential-evolution
+//            (:1091-1140) proposal, reflect / periodic bounds (:440-467), mass ordering, pinned
+//            period, T0 mod P, Gaussian priors get_logP (:703-765)
+//   accept   mcmc_wrapper2.c:492-546  Metropolis-Hastings with the rung temperature, history ring
+//   swap     mcmc_wrapper2.c:554-563 + ptmcmc :768-817  NCHAINS random adjacent-pair swaps
+//
+// RNG: Philox4x32-10, counter = (stream id, iteration, stage, draw block), key = seed.  It replaces
+// ran2/gasdev2 (:833-974, quirk Q7: the reference's per-rung streams are identical for every seed
+// > 0 because the shuffle table is never initialised) and libc rand() in the swaps; streams are
+// NOT bit-compatible with the reference by design -- parity for this layer is (a) deterministic
+// agreement with the oracle's restatement fed the same Philox stream and (b) statistical.
+//
+// Positions on the reference's sampler bugs, selected by PtConfig::quirks:
+//   quirks = 1 (default, "as compiled"): Q5 the mass-ordering block copies instead of swapping
+//     (y[1] = y[0] when y[1] > y[0]); Q6 the DE proposal always uses history sample a = 0 and adds
+//     epsilon = dx (gaussian(c,0,1e-4) - 0.5) with the uninitialised int c, which the reference
+//     built with gcc -O3 evaluates with c == 0, i.e. epsilon = dx (3989.42 - 0.5) -- measured on
+//     oracle/_ref/libref_mcmc.so; Q8 swaps ignore the prior (likelihood only).
+//   quirks = 0 ("as intended"): masses are swapped, a is uniform on the history, epsilon = 0.
+// Always: the current-state likelihood is cached (the reference re-evaluates it every step).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifndef HB_HOST_EMUL
+#include <cuda_runtime.h>
+#define HB_HD __host__ __device__ __forceinline__
+#else
+#define HB_HD static inline
+#endif
+
+namespace hb {
+
+constexpr int kPtNpars = 21;
+constexpr int kPtMaxTemps = 128;
+
+struct PtConfig {
+    int n_temps, n_ens, npast, quirks;
+    unsigned long long seed;
+    double dtemp;          // temperature ladder ratio, 1.4 (mcmc_wrapper2.c:331)
+    double temp[kPtMaxTemps];  // temp[0] = 1, temp[i] = temp[i-1] * dtemp (mcmc_wrapper2.c:332-338)
+    double log_lc_period;  // argv[3]
+    double lc_period;      // 10^log_lc_period
+    double gamma;          // 2.388 / sqrt(2 NPARS)  (mcmc_wrapper2.h:13)
+    double lo[kPtNpars], hi[kPtNpars], mode_lo[kPtNpars], mode_hi[kPtNpars], sigma[kPtNpars];
+    int gauss[kPtNpars];
+};
+
+// ---- Philox4x32-10 ----------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+HB_HD void philox_round(U4& c, uint32_t k0, uint32_t k1)
+{
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
+    U4 r;
+    r.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
+    r.y = (uint32_t)p1;
+    r.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
+    r.w = (uint32_t)p0;
+    c = r;
+}
+
+HB_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+{
+    for (int i = 0; i < 10; i++) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Sequential uniform doubles in (0,1) from the stream (id, iter, stage): block n of the stream is
+// philox(ctr = {id, iter, stage, n}) and yields two doubles.
+struct PtRng {
+    uint32_t id, iter, stage, n, k0, k1;
+    double spare;
+    int have;
+    HB_HD void init(unsigned long long seed, uint32_t id_, uint32_t iter_, uint32_t stage_)
+    {
+        id = id_; iter = iter_; stage = stage_; n = 0; have = 0; spare = 0.;
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+    }
+    HB_HD double next()
+    {
+        if (have) { have = 0; return spare; }
+        U4 c; c.x = id; c.y = iter; c.z = stage; c.w = n++;
+        const U4 r = philox4x32_10(c, k0, k1);
+        const uint64_t a = ((uint64_t)r.x << 21) | (r.y >> 11);
+        const uint64_t b = ((uint64_t)r.z << 21) | (r.w >> 11);
+        spare = ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+        have = 1;
+        return ((double)a + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    // two standard normals (Box-Muller)
+    HB_HD void normal2(double& z0, double& z1)
+    {
+        const double u1 = next(), u2 = next();
+        const double r = sqrt(-2.0 * log(u1));
+        const double a = 6.283185307179586 * u2;
+        z0 = r * cos(a);
+        z1 = r * sin(a);
+    }
+};
+
+// mcmc_wrapper2.c:1175-1178 with SQRT_2PI of mcmc_wrapper2.h:10
+HB_HD double pt_gaussian(double x, double mean, double sigma)
+{
+    return (1 / sigma / 2.5066282746) * exp(-pow((x - mean) / sigma, 2.) / 2.);
+}
+
+// mcmc_wrapper2.c:703-765
+HB_HD double pt_log_prior(const double* p, const int* gauss)
+{
+    const double mean[kPtNpars] = {0, 0, 0, 0, 0, 0, 0, 0., 0., 0.16, 0.34, 0.16, 0.34, 1., 1., 0., 0., 0., 0., 0, 0};
+    const double sig[kPtNpars] = {1e15, 1e15, 1e15, 1e15, 1e15, 1e15, 1e15, 1., 1., 0.04, 0.04, 0.04, 0.04, 0.2, 0.2,
+                                  0.1, 0.1, 1., 1., 1e15, 1e15};
+    double logP = 0.;
+    for (int i = 0; i < kPtNpars; i++)
+        if (gauss[i] == 1) logP += log(pt_gaussian(p[i], mean[i], sig[i]));
+    return logP;
+}
+
+// 21 Gaussian jumps of mcmc_wrapper2.c:1062-1088
+HB_HD void pt_gaussian_proposal(const double* x, const double* sigma, double scale, double temp, PtRng& g, double* y)
+{
+    const double sqtemp = sqrt(temp);
+    for (int n = 0; n < kPtNpars; n += 2) {
+        double z0, z1;
+        g.normal2(z0, z1);
+        y[n] = x[n] + z0 * sigma[n] * sqtemp * scale;
+        if (n + 1 < kPtNpars) y[n + 1] = x[n + 1] + z1 * sigma[n + 1] * sqtemp * scale;
+    }
+}
+
+// Boundary handling + fix-ups of mcmc_wrapper2.c:440-481, in place.
+HB_HD void pt_enforce_bounds(double* y, const PtConfig& cfg)
+{
+    for (int i = 0; i < kPtNpars; i++) {
+        const double lo = cfg.lo[i], hi = cfg.hi[i];
+        const bool rl = cfg.mode_lo[i] == 1, rh = cfg.mode_hi[i] == 1;
+        int guard = 0;
+        while (((rl && (y[i] < lo)) || (rh && (y[i] > hi))) && guard < 200000) {
+            if (y[i] < lo) y[i] = 2.0 * lo - y[i];
+            else y[i] = 2.0 * hi - y[i];
+            if (!(fabs(y[i]) < 1e300)) { y[i] = NAN; break; }  // +-inf would bounce forever
+            guard++;
+        }
+        if (guard >= 200000) y[i] = NAN;  // the reference would still be looping; the proposal is rejected
+        guard = 0;
+        while ((cfg.mode_lo[i] == 2) && (y[i] < lo) && guard++ < 200000) y[i] = hi + (y[i] - lo);
+        while ((cfg.mode_hi[i] == 2) && (y[i] > hi) && guard++ < 200000) y[i] = lo + (y[i] - hi);
+    }
+    if (y[1] > y[0]) {
+        if (cfg.quirks) {  // Q5: tmp is never used in the reference
+            y[1] = y[0];
+        } else {
+            const double t = y[1]; y[1] = y[0]; y[0] = t;
+        }
+    }
+    y[2] = cfg.log_lc_period;
+    y[6] = fmod(y[6], cfg.lc_period);
+}
+
+// One proposal for rung `rung_id` (global id = ens * n_temps + j) at iteration `iter`.
+// history = this rung's ring buffer [npast][21].  Returns jump type (1 Gaussian, 2 DE) and fills
+// y[21], *logPy.
+HB_HD int pt_propose(const PtConfig& cfg, uint32_t rung_id, uint32_t iter, double temp, const double* x,
+                     const double* history, double* y, double* logPy)
+{
+    PtRng g;
+    g.init(cfg.seed, rung_id, iter, 0u);
+    const double alpha = g.next();
+    const double jscale = pow(10., -6. + 6. * alpha);
+    int jump_type = 1;
+    const bool de = (g.next() < 0.5) && ((long long)iter > (long long)cfg.npast);
+    if (!de) {
+        pt_gaussian_proposal(x, cfg.sigma, jscale, temp, g, y);
+    } else {
+        int a = 0, b;
+        if (!cfg.quirks) a = (int)(g.next() * cfg.npast);
+        do { b = (int)(g.next() * cfg.npast); } while (b == a);
+        const bool scaled = g.next() < 0.9;
+        // Q6 "as compiled": epsilon = dx (gaussian(0, 0, 1e-4) - 0.5)
+        const double eps_fac = cfg.quirks ? (pt_gaussian(0., 0., 1.e-4) - 0.5) : 0.0;
+        double dx_mag = 0.;
+        for (int n = 0; n < kPtNpars; n += 2) {
+            double z0 = 1. / cfg.gamma, z1 = 1. / cfg.gamma;
+            if (scaled) g.normal2(z0, z1);
+            for (int m = n; m < n + 2 && m < kPtNpars; m++) {
+                double dx = history[b * kPtNpars + m] - history[a * kPtNpars + m];
+                const double eps = dx * eps_fac;
+                if (scaled) dx *= (m == n ? z0 : z1) * cfg.gamma;
+                dx += eps;
+                y[m] = x[m] + dx;
+                dx_mag += (x[m] - y[m]) * (x[m] - y[m]);
+            }
+        }
+        jump_type = 2;
+        if (dx_mag < 1e-6) {  // mcmc_wrapper2.c:432-436
+            pt_gaussian_proposal(x, cfg.sigma, jscale, temp, g, y);
+            jump_type = 1;
+        }
+    }
+    pt_enforce_bounds(y, cfg);
+    *logPy = pt_log_prior(y, cfg.gauss);
+    return jump_type;
+}
+
+// Metropolis-Hastings decision of mcmc_wrapper2.c:492-505 (NaN H rejects)
+HB_HD bool pt_accept(const PtConfig& cfg, uint32_t rung_id, uint32_t iter, double temp, double logLx, double logLy,
+                     double logPx, double logPy)
+{
+    PtRng g;
+    g.init(cfg.seed, rung_id, iter, 1u);
+    const double alpha = g.next();
+    const double H = exp((logLy - logLx) / temp + (logPy - logPx));
+    return alpha <= H;
+}
+
+// n_temps swap proposals for one ensemble (mcmc_wrapper2.c:554-563, 796-816).  index[] maps
+// rung -> chain slot within the ensemble; logL is indexed by chain slot.  Returns accepted count.
+HB_HD int pt_swap_ensemble(const PtConfig& cfg, uint32_t ens, uint32_t iter, int* index, const double* logL)
+{
+    PtRng g;
+    g.init(cfg.seed, 0x80000000u | ens, iter, 2u);
+    int accepted = 0;
+    if (cfg.n_temps < 2) return 0;
+    for (int s = 0; s < cfg.n_temps; s++) {
+        int b = (int)(g.next() * (double)(cfg.n_temps - 1));
+        if (b > cfg.n_temps - 2) b = cfg.n_temps - 2;
+        const int a = b + 1;
+        const int olda = index[a], oldb = index[b];
+        const double heat1 = cfg.temp[a], heat2 = cfg.temp[b];
+        const double dlogL = logL[oldb] - logL[olda];
+        const double H = (heat2 - heat1) / (heat2 * heat1);
+        const double alpha = exp(dlogL * H);
+        const double beta = g.next();
+        if (alpha >= beta) {
+            index[a] = oldb;
+            index[b] = olda;
+            accepted++;
+        }
+    }
+    return accepted;
+}
+
+}  // namespace hb

@@ -29,6 +29,9 @@ ABI_SYMBOLS = (
     "hb_set_data", "hb_set_mags", "hb_loglikelihood_batch", "hb_loglikelihood_batch_dev", "hb_light_curve_batch",
     "hb_calc_light_curve", "hb_chain_info_batch", "hb_traj", "hb_order_statistic", "hb_remove_median", "hb_scalar", "hb_gaia_batch", "hb_fp64_peak",
     "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count",
+    "hb_pt_create", "hb_pt_destroy", "hb_pt_init_random", "hb_pt_set_state", "hb_pt_step", "hb_pt_iteration",
+    "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
+    "hb_pt_get_counters", "hb_pt_device_logL",
 )
 
 _lib = None
@@ -76,6 +79,23 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_last_eval_kernel_ms.argtypes = [vp, _dp]
     L.hb_launch_count.argtypes = [vp]
     L.hb_launch_count.restype = l
+    ull = C.c_ulonglong
+    L.hb_pt_create.argtypes = [vp, C.POINTER(vp), i, i, d, ull, d, i, i]
+    L.hb_pt_destroy.argtypes = [vp]
+    L.hb_pt_destroy.restype = None
+    L.hb_pt_init_random.argtypes = [vp]
+    L.hb_pt_set_state.argtypes = [vp, _dp]
+    L.hb_pt_step.argtypes = [vp, l]
+    L.hb_pt_iteration.argtypes = [vp]
+    L.hb_pt_iteration.restype = l
+    L.hb_pt_get_state.argtypes = [vp, _dp, _dp, C.POINTER(i)]
+    L.hb_pt_get_proposal.argtypes = [vp, _dp, _dp, _dp]
+    L.hb_pt_get_cold.argtypes = [vp, _dp, _dp]
+    L.hb_pt_get_logL_by_rung.argtypes = [vp, _dp]
+    L.hb_pt_get_map.argtypes = [vp, _dp, _dp]
+    L.hb_pt_get_counters.argtypes = [vp, C.POINTER(ull)]
+    L.hb_pt_device_logL.argtypes = [vp]
+    L.hb_pt_device_logL.restype = vp
     if path == _build.LIB:
         _lib = L
     return L

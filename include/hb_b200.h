@@ -91,6 +91,38 @@ int hb_scalar(hb_ctx* ctx, int op, const double* args, int nargs, double* out);
 int hb_gaia_batch(hb_ctx* ctx, const double* p6, long n, double D, const double* data, const double* err,
                   double* mags, double* logL);
 
+/* ---- device-resident parallel tempering ------------------------------------------------ */
+/* The step/swap loop of mcmc_wrapper2.c:378-563 with all chain state on the device: n_ens
+ * independent ladders of n_temps rungs (the reference: 1 x NCHAINS = 50, mcmc_wrapper2.h:11),
+ * temperatures dtemp^j (1.4, :331-339), DE history of npast samples per rung (500, :12).
+ * Philox4x32-10 keyed on (seed, rung, iteration) replaces ran2/gasdev2/rand().  quirks != 0 keeps
+ * the reference's sampler bugs as compiled (Q5, Q6, Q8 of SURVEY Appendix B; see hb_pt.cuh).
+ * Needs hb_set_data first; limits and proposal sigmas are those of set_limits /
+ * initialize_proposals (likelihood3.c:986-1179) for the context's use_gmag / use_color. */
+typedef struct hb_pt hb_pt;
+int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc_period, unsigned long long seed,
+                 double dtemp, int npast, int quirks);
+void hb_pt_destroy(hb_pt* pt);
+/* uniform draws in the prior box, period pinned, T0 mod P (mcmc_wrapper2.c:236-251) + first logL */
+int hb_pt_init_random(hb_pt* pt);
+/* x[n_ens*n_temps][21] by chain slot (slot = ens*n_temps + chain id) + first logL */
+int hb_pt_set_state(hb_pt* pt, const double* x);
+/* n_iters full iterations: every rung proposes, is evaluated (ONE likelihood per rung: the
+ * current-state value is cached, the reference re-evaluates it, :488), accepts/rejects; then
+ * n_temps swap proposals per ensemble (:554-563) and the MAP update (:565-572) */
+int hb_pt_step(hb_pt* pt, long n_iters);
+long hb_pt_iteration(const hb_pt* pt);
+int hb_pt_get_state(hb_pt* pt, double* x, double* logL, int* index);       /* any may be NULL */
+int hb_pt_get_proposal(hb_pt* pt, double* y, double* logLy, double* logPy); /* last proposals, by slot */
+int hb_pt_get_cold(hb_pt* pt, double* x_cold, double* logL_cold);          /* rung 0: [n_ens][21], [n_ens] */
+int hb_pt_get_logL_by_rung(hb_pt* pt, double* out);                        /* [n_ens][n_temps] */
+int hb_pt_get_map(hb_pt* pt, double* xmap, double* logLmap);               /* [n_ens][21], [n_ens] */
+/* per ensemble 8 counters: acc of slot 0, DE trials / DE acc of slot 0 (the reference's acc, DEtrial,
+ * DEacc), accepted / proposed over all rungs, swaps accepted / proposed, iterations */
+int hb_pt_get_counters(hb_pt* pt, unsigned long long* out);
+/* device pointer of logL[n_ens*n_temps] (for an NCCL all-gather by the caller) */
+void* hb_pt_device_logL(hb_pt* pt);
+
 /* ---- measurement ----------------------------------------------------------------------- */
 /* DFMA throughput of the device in TFLOP/s (2 flop per FMA), the FP64 roofline denominator. */
 int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);

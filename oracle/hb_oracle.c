@@ -607,3 +607,174 @@ void orc_loglikelihood_batch(const double *time, const double *flux, const doubl
     }
     free(clamped);
 }
+
+/* ------------------------------------------------------------------ */
+/* parallel-tempering step with the Philox stream of the device path   */
+/* ------------------------------------------------------------------ */
+/* The reference's RNG (ran2/gasdev2/rand, mcmc_wrapper2.c:796-974) is replaced on the device by
+ * Philox4x32-10 (Salmon et al. 2011).  To check the device step deterministically the oracle
+ * draws from the same counter-based stream: block n of stream (id, iter, stage) is
+ * philox(counter = {id, iter, stage, n}, key = seed) and yields two uniforms in (0,1). */
+#include <stdint.h>
+
+static void philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+typedef struct {
+    uint32_t id, iter, stage, block, k0, k1;
+    double buf[2];
+    int left;
+} orc_stream;
+
+static void stream_open(orc_stream *s, unsigned long long seed, uint32_t id, uint32_t iter, uint32_t stage)
+{
+    s->id = id; s->iter = iter; s->stage = stage; s->block = 0; s->left = 0;
+    s->k0 = (uint32_t)seed; s->k1 = (uint32_t)(seed >> 32);
+}
+
+static double stream_next(orc_stream *s)
+{
+    if (s->left == 0) {
+        uint32_t ctr[4] = {s->id, s->iter, s->stage, s->block++}, r[4];
+        philox4x32_10(ctr, s->k0, s->k1, r);
+        uint64_t a = ((uint64_t)r[0] << 21) | (r[1] >> 11);
+        uint64_t b = ((uint64_t)r[2] << 21) | (r[3] >> 11);
+        s->buf[0] = ((double)a + 0.5) / 9007199254740992.0;
+        s->buf[1] = ((double)b + 0.5) / 9007199254740992.0;
+        s->left = 2;
+    }
+    return s->buf[2 - s->left--];
+}
+
+void orc_pt_uniforms(unsigned long long seed, unsigned id, unsigned iter, unsigned stage, int n, double *out)
+{
+    orc_stream s;
+    stream_open(&s, seed, id, iter, stage);
+    for (int i = 0; i < n; i++) out[i] = stream_next(&s);
+}
+
+/* known-answer test vector of Random123 (kat_vectors: philox4x32 10 rounds) */
+void orc_philox_raw(const unsigned *ctr, const unsigned *key, unsigned *out)
+{
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, r[4];
+    philox4x32_10(c, key[0], key[1], r);
+    for (int i = 0; i < 4; i++) out[i] = r[i];
+}
+
+static void stream_normal_pair(orc_stream *s, double *z0, double *z1)
+{
+    double u1 = stream_next(s), u2 = stream_next(s);
+    double r = sqrt(-2.0 * log(u1)), a = 6.283185307179586 * u2;
+    *z0 = r * cos(a);
+    *z1 = r * sin(a);
+}
+
+/* Gaussian jump, mcmc_wrapper2.c:1062-1088 (normals consumed in pairs, component order) */
+static void gaussian_jump(orc_stream *s, const double *x, const double *sigma, double scale, double temp, double *y)
+{
+    double sq = sqrt(temp), z[ORC_NPARS + 1];
+    for (int n = 0; n < ORC_NPARS; n += 2) stream_normal_pair(s, &z[n], &z[n + 1]);
+    for (int n = 0; n < ORC_NPARS; n++) y[n] = x[n] + z[n] * sigma[n] * sq * scale;
+}
+
+/* One proposal (mcmc_wrapper2.c:390-485) for stream `id` at iteration `iter`; history is this
+ * rung's ring [npast][21]; quirks as in hb_pt.cuh.  Returns the jump type (1 Gaussian, 2 DE). */
+int orc_pt_propose(unsigned long long seed, unsigned id, unsigned iter, double temp, int npast, int quirks,
+                   const double *x, const double *history, const double *lo, const double *hi,
+                   const double *mode_lo, const double *mode_hi, const int *gauss, const double *sigma,
+                   double log_lc_period, double *y, double *logPy)
+{
+    orc_stream s;
+    stream_open(&s, seed, id, iter, 0u);
+    double alpha = stream_next(&s);
+    double jscale = pow(10., -6. + 6. * alpha);
+    int type = 1;
+    int de = (stream_next(&s) < 0.5) && ((long)iter > (long)npast);
+    if (!de) {
+        gaussian_jump(&s, x, sigma, jscale, temp, y);
+    } else {
+        const double gamma = 2.388 / sqrt(2. * ORC_NPARS); /* mcmc_wrapper2.h:13 */
+        int a = 0, b;
+        if (!quirks) a = (int)(stream_next(&s) * npast);
+        do { b = (int)(stream_next(&s) * npast); } while (b == a);
+        int scaled = stream_next(&s) < 0.9;
+        double eps_fac = quirks ? (gaussian_pdf(0., 0., 1.e-4) - 0.5) : 0.0; /* Q6 as compiled (c == 0) */
+        double z[ORC_NPARS + 1], mag = 0.;
+        if (scaled)
+            for (int n = 0; n < ORC_NPARS; n += 2) stream_normal_pair(&s, &z[n], &z[n + 1]);
+        for (int n = 0; n < ORC_NPARS; n++) {
+            double dx = history[b * ORC_NPARS + n] - history[a * ORC_NPARS + n];
+            double eps = dx * eps_fac;
+            if (scaled) dx *= z[n] * gamma;
+            dx += eps;
+            y[n] = x[n] + dx;
+            mag += (x[n] - y[n]) * (x[n] - y[n]);
+        }
+        type = 2;
+        if (mag < 1e-6) {
+            gaussian_jump(&s, x, sigma, jscale, temp, y);
+            type = 1;
+        }
+    }
+    /* bounds + fix-ups; the "as intended" variant swaps the masses instead of copying */
+    if (quirks) {
+        orc_enforce_bounds(y, lo, hi, mode_lo, mode_hi, log_lc_period, pow(10., log_lc_period));
+    } else {
+        double y0 = y[0], y1 = y[1];
+        (void)y0; (void)y1;
+        /* run the reference fix-ups on a copy with masses pre-swapped so that its copy is a no-op */
+        for (int i = 0; i < ORC_NPARS; i++) {
+            while (((mode_lo[i] == 1) && (y[i] < lo[i])) || ((mode_hi[i] == 1) && (y[i] > hi[i]))) {
+                if (y[i] < lo[i]) y[i] = 2.0 * lo[i] - y[i];
+                else y[i] = 2.0 * hi[i] - y[i];
+            }
+            while ((mode_lo[i] == 2) && (y[i] < lo[i])) y[i] = hi[i] + (y[i] - lo[i]);
+            while ((mode_hi[i] == 2) && (y[i] > hi[i])) y[i] = lo[i] + (y[i] - hi[i]);
+        }
+        if (y[1] > y[0]) { double t = y[1]; y[1] = y[0]; y[0] = t; }
+        y[2] = log_lc_period;
+        y[6] = fmod(y[6], pow(10., log_lc_period));
+    }
+    *logPy = orc_get_logP(y, gauss);
+    return type;
+}
+
+/* MH decision (mcmc_wrapper2.c:492-505) with the accept stream (stage 1) */
+int orc_pt_accept(unsigned long long seed, unsigned id, unsigned iter, double temp, double logLx, double logLy,
+                  double logPx, double logPy)
+{
+    orc_stream s;
+    stream_open(&s, seed, id, iter, 1u);
+    double alpha = stream_next(&s);
+    return alpha <= orc_hastings(logLx, logLy, logPx, logPy, temp);
+}
+
+/* n_temps swap proposals (mcmc_wrapper2.c:554-563) with the swap stream (stage 2, id = 2^31 | ens) */
+int orc_pt_swap_ensemble(unsigned long long seed, unsigned ens, unsigned iter, int n_temps, const double *temp,
+                         int *index, const double *logL)
+{
+    orc_stream s;
+    stream_open(&s, seed, 0x80000000u | ens, iter, 2u);
+    int acc = 0;
+    for (int k = 0; k < n_temps && n_temps > 1; k++) {
+        int b = (int)(stream_next(&s) * (double)(n_temps - 1));
+        if (b > n_temps - 2) b = n_temps - 2;
+        double beta = stream_next(&s);
+        acc += orc_pt_swap_pair(index, temp, logL, b, beta);
+    }
+    return acc;
+}

@@ -52,3 +52,21 @@ double orc_hastings(double logLx, double logLy, double logPx, double logPy, doub
 }
 #endif
 #endif
+
+/* parallel-tempering step on the device's Philox stream (declared late: see hb_oracle.c) */
+#ifdef __cplusplus
+extern "C" {
+#endif
+void orc_pt_uniforms(unsigned long long seed, unsigned id, unsigned iter, unsigned stage, int n, double *out);
+void orc_philox_raw(const unsigned *ctr, const unsigned *key, unsigned *out);
+int orc_pt_propose(unsigned long long seed, unsigned id, unsigned iter, double temp, int npast, int quirks,
+                   const double *x, const double *history, const double *lo, const double *hi,
+                   const double *mode_lo, const double *mode_hi, const int *gauss, const double *sigma,
+                   double log_lc_period, double *y, double *logPy);
+int orc_pt_accept(unsigned long long seed, unsigned id, unsigned iter, double temp, double logLx, double logLy,
+                  double logPx, double logPy);
+int orc_pt_swap_ensemble(unsigned long long seed, unsigned ens, unsigned iter, int n_temps, const double *temp,
+                         int *index, const double *logL);
+#ifdef __cplusplus
+}
+#endif

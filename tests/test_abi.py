@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols(header):
     src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(hb_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():
