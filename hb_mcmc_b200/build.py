@@ -73,7 +73,7 @@ def build_driver(force: bool = False) -> str | None:
     if not os.path.exists(src):
         return None
     if force or _stale(DRIVER, _glob(HOST_DIR, (".c", ".h")) + [LIB]):
-        cmd = ["gcc", "-O2", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", DRIVER, src, "-L", CSRC,
+        cmd = ["gcc", "-O2", "-std=gnu99", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", DRIVER, src, "-L", CSRC,
                "-lhb_b200", "-Wl,-rpath," + CSRC, "-lm"]
         subprocess.run(cmd, check=True, cwd=HOST_DIR)
     return DRIVER

@@ -1,0 +1,54 @@
+"""host/hb_mcmc: the reference's CLI and on-disk formats on the device sampler."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hb_mcmc_b200 import build
+from hb_mcmc_b200 import workload as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def test_driver_cli_and_file_formats(tmp_path, ctx):
+    build.build_lib()
+    exe = build.build_driver()
+    prefix = tmp_path / "data"
+    for d in ("chains", "logL", "log", "pars", "subpars", "magnitudes", "lightcurves/folded_lightcurves",
+              "lightcurves/mcmc_lightcurves"):
+        (prefix / d).mkdir(parents=True)
+    N = 375  # size of the reference's real folded light curves (163-763 points)
+    t = np.sort(np.random.default_rng(0).uniform(0, 10 ** wl.TRUTH_A[2], N))
+    flux = ctx.calc_light_curve(t, wl.TRUTH_A) + 3e-4 * np.random.default_rng(1).standard_normal(N)
+    with open(prefix / "lightcurves/folded_lightcurves/TIC42_new.txt", "w") as f:  # helpful_functions.py:197-203
+        f.write(f"{N}\n")
+        for a, b in zip(t, flux):
+            f.write(f"{a:.10f}\t{b:.10f}\t{3e-4:.10f}\n")
+    G = ctx.chain_info(wl.TRUTH_A[None], 100.0)[0, 4]
+    with open(prefix / "magnitudes/TIC42.txt", "w") as f:  # src/README.txt:21-27
+        f.write(f"100.0\n{G:.6f}\t0.05\n0.2\t0.1\n0.1\t0.1\n0.0\t0.1\n")
+    env = dict(os.environ, HB_DATA_PREFIX=str(prefix), HB_NTEMPS="12", HB_SEED="3")
+    r = subprocess.run([exe, "450", "TIC42", repr(float(wl.TRUTH_A[2])), "1"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Using color / GMAG information" in r.stdout and "PT steps/s" in r.stdout
+    sfx = "TIC42_gmag_B200_1"
+    chain = np.loadtxt(prefix / f"chains/chain.{sfx}.dat", ndmin=2)
+    assert chain.shape == (5, 23)  # logged after iterations 0,100,...,400: "iter/10 logL p0..p20"
+    assert chain[:, 0].tolist() == [0, 10, 20, 30, 40]
+    assert np.all(chain[:, 4] == wl.TRUTH_A[2])  # the period is pinned (mcmc_wrapper2.c:478)
+    logL = np.loadtxt(prefix / f"logL/logL.{sfx}.dat", ndmin=2)
+    assert logL.shape == (5, 13) and np.allclose(logL[:, 1], chain[:, 1])
+    with open(prefix / f"lightcurves/mcmc_lightcurves/{sfx}.out") as f:
+        assert int(f.readline()) == N
+        out = np.loadtxt(f)
+    assert out.shape == (N, 3) and np.allclose(out[:, 0], t, rtol=1e-5) and np.allclose(out[:, 1], flux, rtol=1e-5)
+    par = np.loadtxt(prefix / f"pars/par.{sfx}.dat")
+    sub = np.loadtxt(prefix / f"subpars/subpar.{sfx}.dat")
+    assert par.shape == (21,) and sub.shape == (21,)
+    # the sampler improves on its random start
+    assert chain[-1, 1] >= chain[0, 1]
+    # missing light-curve file: the reference prints and exits 0 (mcmc_wrapper2.c:279-283)
+    r = subprocess.run([exe, "10", "NOPE", "0.3", "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Lightcurve datafile not found" in r.stdout
