@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=0, help="override points per light curve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic)")
+    ap.add_argument("--pt-steps", type=int, default=40, help="PT-MCMC iterations timed for the steps/s figure (0 = skip)")
     return ap.parse_args()
 
 
@@ -317,6 +318,8 @@ def gpu_arm(args, cfg, rank, local_rank, world):
         e2e_s = float(tt.item())
     assert np.array_equal(out, logL_dev, equal_nan=True), "host-buffer and device-buffer paths disagree"
 
+    pt_info = pt_leg(args, ctx, cfg, rank, world, dist, stream) if args.pt_steps > 0 else None
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         pts_per_step = float(n) * N * world
@@ -342,6 +345,8 @@ def gpu_arm(args, cfg, rank, local_rank, world):
             },
             "nan_fraction": float(np.isnan(logL_dev).mean()),
         }
+        if pt_info is not None:
+            line["pt"] = pt_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg(cfg, t, flux, err, P, logL_dev)
         print(json.dumps(line), flush=True)
@@ -349,6 +354,52 @@ def gpu_arm(args, cfg, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def pt_leg(args, ctx, cfg, rank, world, dist, stream):
+    """Second half of BASELINE.json's metric: full PT-MCMC iterations per second on config C3's
+    per-GPU share (64 temperatures x 32 ensembles = 2048 walkers per GPU on the resident light curve;
+    256 ensembles over 8 GPUs).  Every iteration = propose + ONE likelihood per walker + accept +
+    64 swap proposals per ensemble + the all-gather of the cold-rung logL vector across ranks."""
+    import torch
+    from hb_mcmc_b200.pt import ShardedPT
+    n_temps, ens_per_gpu = 64, 32
+    sp = ShardedPT(ctx, n_temps, ens_per_gpu * world, float(cfg["truth_vec"][2]), seed=11)
+    sp.sampler.init_random()
+    for _ in range(3):
+        sp.step(1)
+        sp.gather_cold_logL_device()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
+    e0.record(stream)
+    for _ in range(args.pt_steps):
+        sp.step(1)
+        g = sp.gather_cold_logL_device()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    cnt = sp.sampler.counters()
+    info = {
+        "steps_per_sec": args.pt_steps / (ms * 1e-3), "ms_per_step": ms / args.pt_steps, "steps": args.pt_steps,
+        "n_temps": n_temps, "ensembles_per_gpu": ens_per_gpu, "walkers_per_gpu": n_temps * ens_per_gpu,
+        "n_points": cfg["n_points"], "likelihood_evals_per_walker_per_step": 1,
+        "model_points_per_sec": n_temps * ens_per_gpu * world * cfg["n_points"] * args.pt_steps / (ms * 1e-3),
+        "exchange": "all_gather of cold-rung logL (%d doubles per rank) per step, %s" % (ens_per_gpu, "NCCL" if world > 1 else "single rank"),
+        "acceptance": float(cnt["accepted"].sum() / max(1, cnt["proposed"].sum())),
+        "gpu_launches": int(ctx.launch_count - l0),
+        "gathered_finite": bool(torch.isfinite(g).any().item()),
+    }
+    sp.sampler.close()
+    return info
 
 
 def cpu_baseline_leg(cfg, t, flux, err, P, logL_gpu):

@@ -873,4 +873,16 @@ int hb_pt_get_counters(hb_pt* pt, unsigned long long* out)
 
 void* hb_pt_device_logL(hb_pt* pt) { return pt ? (void*)pt->logLx : nullptr; }
 
+int hb_pt_cold_logL_dev(hb_pt* pt, double* d_out)
+{
+    if (!pt || !d_out) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    const int E = pt->cfg.n_ens;
+    CK(launch_pt_gather_cold(pt->d_cfg, pt->index, pt->x, pt->logLx, pt->tmp, d_out, E, ctx->stream));
+    ctx->launches += 1;
+    return HB_OK;
+}
+
 }  // extern "C"

@@ -83,25 +83,62 @@ __global__ void k_pt_accept(const PtConfig* __restrict__ cfgp, unsigned iter, do
     for (int i = 0; i < kPtNpars; i++) h[i] = xl[i];
 }
 
-__global__ void k_pt_swap(const PtConfig* __restrict__ cfgp, unsigned iter, int* __restrict__ index,
-                          const double* __restrict__ logLx, const double* __restrict__ x,
-                          unsigned long long* __restrict__ counters, double* __restrict__ xmap,
-                          double* __restrict__ logLmap, int E)
+// One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
+// (swap s consumes exactly block s of the ensemble's Philox stream), lane 0 then applies them in
+// order -- each decision depends on the permutation left by the previous one (mcmc_wrapper2.c:554-563).
+__global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfgp, unsigned iter, int* __restrict__ index,
+                                                const double* __restrict__ logLx, const double* __restrict__ x,
+                                                unsigned long long* __restrict__ counters, double* __restrict__ xmap,
+                                                double* __restrict__ logLmap, int E)
 {
-    const int ens = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ens = blockIdx.x, lane = threadIdx.x;
     if (ens >= E) return;
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps;
-    const int nacc = pt_swap_ensemble(cfg, (uint32_t)ens, iter, index + (size_t)ens * T, logLx + (size_t)ens * T);
-    unsigned long long* cnt = counters + (size_t)ens * 8;
-    cnt[5] += (unsigned long long)nacc;
-    cnt[6] += (unsigned long long)T;
-    cnt[7] += 1ull;
+    __shared__ int s_b[kPtMaxTemps];
+    __shared__ double s_beta[kPtMaxTemps];
+    __shared__ int s_idx[kPtMaxTemps];
+    __shared__ double s_logL[kPtMaxTemps];
+    for (int s = lane; s < T; s += 32) {
+        U4 c; c.x = 0x80000000u | (uint32_t)ens; c.y = iter; c.z = 2u; c.w = (uint32_t)s;
+        const U4 r = philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+        const double u0 = ((double)(((uint64_t)r.x << 21) | (r.y >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u1 = ((double)(((uint64_t)r.z << 21) | (r.w >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        int b = (int)(u0 * (double)(T - 1));
+        if (b > T - 2) b = T - 2;
+        s_b[s] = b;
+        s_beta[s] = u1;
+        s_idx[s] = index[(size_t)ens * T + s];
+        s_logL[s] = logLx[(size_t)ens * T + s];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int nacc = 0;
+        for (int s = 0; s < T && T > 1; s++) {
+            const int b = s_b[s], a = b + 1;
+            const int olda = s_idx[a], oldb = s_idx[b];
+            const double heat1 = cfg.temp[a], heat2 = cfg.temp[b];
+            const double alpha = exp((s_logL[oldb] - s_logL[olda]) * ((heat2 - heat1) / (heat2 * heat1)));
+            if (alpha >= s_beta[s]) {
+                s_idx[a] = oldb;
+                s_idx[b] = olda;
+                nacc++;
+            }
+        }
+        unsigned long long* cnt = counters + (size_t)ens * 8;
+        cnt[5] += (unsigned long long)nacc;
+        cnt[6] += (unsigned long long)T;
+        cnt[7] += 1ull;
+    }
+    __syncwarp();
+    for (int s = lane; s < T; s += 32) index[(size_t)ens * T + s] = s_idx[s];
     // MAP of the cold rung (mcmc_wrapper2.c:565-572)
-    const int c0 = ens * T + index[(size_t)ens * T];
-    if (logLx[c0] > logLmap[ens]) {
-        logLmap[ens] = logLx[c0];
-        for (int i = 0; i < kPtNpars; i++) xmap[(size_t)ens * kPtNpars + i] = x[(size_t)c0 * kPtNpars + i];
+    const int c0 = ens * T + s_idx[0];
+    const bool better = logLx[c0] > logLmap[ens];
+    __syncwarp();
+    if (better) {
+        if (lane < kPtNpars) xmap[(size_t)ens * kPtNpars + lane] = x[(size_t)c0 * kPtNpars + lane];
+        if (lane == 0) logLmap[ens] = logLx[c0];
     }
 }
 
@@ -149,7 +186,8 @@ cudaError_t launch_pt_accept(const PtConfig* cfg, unsigned iter, double* x, cons
 cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned iter, int* index, const double* logLx, const double* x,
                            unsigned long long* counters, double* xmap, double* logLmap, int E, cudaStream_t s)
 {
-    LAUNCH1D(k_pt_swap, E, s, cfg, iter, index, logLx, x, counters, xmap, logLmap, E);
+    if (E > 0) k_pt_swap<<<E, 32, 0, s>>>(cfg, iter, index, logLx, x, counters, xmap, logLmap, E);
+    return cudaGetLastError();
 }
 cudaError_t launch_pt_gather_cold(const PtConfig* cfg, const int* index, const double* x, const double* logLx,
                                   double* out_x, double* out_logL, int E, cudaStream_t s)

@@ -142,6 +142,19 @@ HB_HD void pt_enforce_bounds(double* y, const PtConfig& cfg)
     for (int i = 0; i < kPtNpars; i++) {
         const double lo = cfg.lo[i], hi = cfg.hi[i];
         const bool rl = cfg.mode_lo[i] == 1, rh = cfg.mode_hi[i] == 1;
+        // Hot rungs (sqrt(T) up to 4e4) and the "as compiled" DE jumps overshoot the box by thousands
+        // of widths; the reference bounces them back one reflection at a time.  Two reflections are a
+        // translation by 2 (hi - lo) and one periodic wrap a translation by (hi - lo), so whole
+        // multiples are removed in one step and the loops below only finish the last bounce.
+        {
+            const double R = hi - lo;
+            const bool per = (cfg.mode_lo[i] == 2) && (cfg.mode_hi[i] == 2);
+            const double period = (rl && rh) ? 2.0 * R : (per ? R : 0.0);
+            if (period > 0.0 && fabs(y[i]) < 1e300) {
+                if (y[i] > hi + period) y[i] -= period * floor((y[i] - hi) / period);
+                else if (y[i] < lo - period) y[i] += period * floor((lo - y[i]) / period);
+            }
+        }
         int guard = 0;
         while (((rl && (y[i] < lo)) || (rh && (y[i] > hi))) && guard < 200000) {
             if (y[i] < lo) y[i] = 2.0 * lo - y[i];

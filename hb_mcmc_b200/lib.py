@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count",
     "hb_pt_create", "hb_pt_destroy", "hb_pt_init_random", "hb_pt_set_state", "hb_pt_step", "hb_pt_iteration",
     "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
-    "hb_pt_get_counters", "hb_pt_device_logL",
+    "hb_pt_get_counters", "hb_pt_device_logL", "hb_pt_cold_logL_dev",
 )
 
 _lib = None
@@ -96,6 +96,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_pt_get_counters.argtypes = [vp, C.POINTER(ull)]
     L.hb_pt_device_logL.argtypes = [vp]
     L.hb_pt_device_logL.restype = vp
+    L.hb_pt_cold_logL_dev.argtypes = [vp, vp]
     if path == _build.LIB:
         _lib = L
     return L

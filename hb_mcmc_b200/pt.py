@@ -112,6 +112,10 @@ class PTSampler:
         self._ck(self._L.hb_pt_get_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
         return {k: out[:, i].copy() for i, k in enumerate(COUNTER_NAMES)}
 
+    def cold_logL_into(self, device_ptr: int) -> None:
+        """Cold-rung logL[n_ens] into a device buffer (async on the context's stream)."""
+        self._ck(self._L.hb_pt_cold_logL_dev(self._h, C.c_void_p(device_ptr)))
+
     def device_logL_ptr(self) -> int:
         return int(self._L.hb_pt_device_logL(self._h) or 0)
 
@@ -149,6 +153,22 @@ class ShardedPT:
 
     def step(self, n_iters: int = 1):
         self.sampler.step(n_iters)
+
+    def gather_cold_logL_device(self):
+        """Device-side variant: the gather kernel writes straight into the NCCL send buffer; returns
+        the gathered [world, max_count] tensor (padding is NaN) without a host round trip."""
+        import torch
+        counts = [shard_ensembles(self.n_ens_total, self.world, r)[1] for r in range(self.world)]
+        mx = max(counts)
+        if getattr(self, "_send", None) is None:
+            self._send = torch.full((mx,), float("nan"), dtype=torch.float64, device="cuda")
+            self._recv = torch.empty((self.world, mx), dtype=torch.float64, device="cuda")
+        self.sampler.cold_logL_into(self._send.data_ptr())
+        if self.world == 1:
+            self._recv.copy_(self._send[None])
+        else:
+            self.dist.all_gather_into_tensor(self._recv, self._send)
+        return self._recv
 
     def gather_cold_logL(self, device=None) -> np.ndarray:
         """All-gather of the cold-rung logL vector (the only per-step exchange)."""

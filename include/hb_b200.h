@@ -122,6 +122,9 @@ int hb_pt_get_map(hb_pt* pt, double* xmap, double* logLmap);               /* [n
 int hb_pt_get_counters(hb_pt* pt, unsigned long long* out);
 /* device pointer of logL[n_ens*n_temps] (for an NCCL all-gather by the caller) */
 void* hb_pt_device_logL(hb_pt* pt);
+/* cold-rung logL of every ensemble into a DEVICE buffer d_out[n_ens], asynchronous on the context's
+ * stream: the send buffer of the per-step NCCL all-gather */
+int hb_pt_cold_logL_dev(hb_pt* pt, double* d_out);
 
 /* ---- measurement ----------------------------------------------------------------------- */
 /* DFMA throughput of the device in TFLOP/s (2 flop per FMA), the FP64 roofline denominator. */

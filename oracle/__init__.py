@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -35,9 +36,9 @@ def _f64(a):
 
 def build(ref: bool = True) -> None:
     """Compile the restatement and, when /root/reference is present, the reference."""
-    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True, stdout=sys.stderr)
     if ref:
-        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True, stdout=sys.stderr)
 
 
 def have_reference() -> bool:

@@ -67,12 +67,13 @@ def test_step_matches_oracle(ctx, orc, setup, quirks):
                 jt = L.orc_pt_propose(seed, r, it, temps[j], npast, int(quirks), p(xc), p(hr), p(lo), p(hi), p(ml), p(mh),
                                       gauss.ctypes.data_as(ip), p(sigma), logP, p(y), C.byref(lp))
                 n_de += jt == 2
-                # DE jumps "as compiled" are ~4000 x a history difference, folded back by thousands of
-                # reflections: the absolute rounding error of the big jump survives the folding
-                atol = 1e-13 if jt == 1 else 1e-9
+                # DE jumps "as compiled" are ~4000 x a history difference.  The reference (and the oracle)
+                # bounce them back one reflection at a time, each with its own rounding; the device removes
+                # whole multiples of the box in one step, so the two agree to ~n_bounces x ulp(jump)
+                atol = 1e-13 if jt == 1 else 1e-7
                 ok = np.isclose(y_gpu[c], y, rtol=1e-11, atol=atol, equal_nan=True)
                 assert ok.all(), (it, r, jt, y_gpu[c][~ok], y[~ok])
-                assert np.isclose(logPy[c], lp.value, rtol=1e-11 if jt == 1 else 1e-6) or (np.isnan(logPy[c]) and np.isnan(lp.value))
+                assert np.isclose(logPy[c], lp.value, rtol=1e-11 if jt == 1 else 1e-5) or (np.isnan(logPy[c]) and np.isnan(lp.value))
                 # accept decision with the GPU's own likelihood values
                 acc = L.orc_pt_accept(seed, r, it, temps[j], logL[c], logLy[c], orc.get_logP(xc, gauss), logPy[c])
                 n_acc += acc
