@@ -315,8 +315,13 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
 
 #ifndef HB_HOST_EMUL
 // true when the predicate holds on every lane that is executing this call together
-__device__ __forceinline__ bool warp_all(bool p) { return __all_sync(__activemask(), p); }
+template <bool kFullWarp>
+__device__ __forceinline__ bool warp_all(bool p)
+{
+    return kFullWarp ? __all_sync(0xffffffffu, p) : __all_sync(__activemask(), p);
+}
 #else
+template <bool kFullWarp>
 static inline bool warp_all(bool p) { return p; }
 #endif
 
@@ -341,15 +346,29 @@ __device__ __forceinline__ double rcp_fast(double x)
     return fma(y, e, y);
 }
 
-// a/b to ~1 ulp: one Newton step on the seed, then a residual correction of the quotient
-__device__ __forceinline__ double div_fast(double a, double b)
+// a/b for the Newton step of Kepler's equation: one Newton step on the MUFU seed gives y ~ 1/b to
+// 2^-46 and the quotient a*y to 1.5e-14 relative.  That is below the rounding noise of the
+// numerator itself (E - e sin E - M cancels to ~1e-16 absolute, i.e. >= 1e-14 relative to a step
+// of 0.01) -- measured: logL moves by 1e-15 relative against the 1-ulp division (HB_DIV_EXACT).
+// y is handed back: it seeds 1/den of the next, nearly identical, denominator.
+__device__ __forceinline__ double div_fast(double a, double b, double& y_out)
 {
     double y = rcp_seed(b);
     const double e = fma(-b, y, 1.0);
     y = fma(y, e, y);
+    y_out = y;
     const double q = a * y;
+#ifndef HB_DIV_EXACT
+    return q;
+#else
     const double r = fma(-b, q, a);
     return fma(r, y, q);
+#endif
+}
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    double y;
+    return div_fast(a, b, y);
 }
 
 // fdlibm __kernel_sin / __kernel_cos minimax coefficients on [-pi/4, pi/4]
@@ -368,14 +387,17 @@ __constant__ double kRed[5] = {1.57079632679489655800e+00, 6.1232339957367660358
 
 static __device__ __noinline__ void sincos_library(double x, double* s, double* c) { sincos(x, s, c); }
 
-// sin and cos, ~1 ulp, for |x| <= 1e5 (Kepler iterates are O(10)); the library handles the rest.
+// sin and cos, ~1 ulp, for |x| <= 1e5 (Kepler iterates are O(10)).  No range check here: the
+// caller accumulates the largest exponent word it passed in (`hi_max`) and, in the rare case it
+// exceeds kSincosHiLimit (wild Newton iterates at e -> 1, inf, NaN), redoes the sample with the
+// library functions (kepler_point_careful).
+constexpr int kSincosHiLimit = 0x40f86a00;  // high word of 1e5
 template <int V>
-__device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out)[V], double (&c_out)[V])
+__device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out)[V], double (&c_out)[V], int& hi_max)
 {
-    bool cold = false;
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        cold |= (__double2hiint(x[j]) & 0x7fffffff) > 0x40f86a00;  // |x| > ~1e5, inf, NaN
+        hi_max = max(hi_max, __double2hiint(x[j]) & 0x7fffffff);
         const double t = fma(x[j], kRed[3], kRed[4]);
         const int k = __double2loint(t);  // nearest integer to x * 2/pi sits in the low word
         const double kd = t - kRed[4];
@@ -404,16 +426,6 @@ __device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out
         s_out[j] = __hiloint2double(__double2hiint(sa) ^ ssign, __double2loint(sa));
         c_out[j] = __hiloint2double(__double2hiint(ca) ^ csign, __double2loint(ca));
     }
-    if (cold) {  // wild Newton iterates at e -> 1, inf, NaN
-#pragma unroll
-        for (int j = 0; j < V; j++)
-            if ((__double2hiint(x[j]) & 0x7fffffff) > 0x40f86a00) {
-                double s, c;
-                sincos_library(x[j], &s, &c);
-                s_out[j] = s;
-                c_out[j] = c;
-            }
-    }
 }
 
 static __device__ __noinline__ double fmod_library(double a, double b) { return fmod(a, b); }
@@ -435,28 +447,60 @@ __device__ __forceinline__ double fmod_twopi(double M)
     return copysign(r, M);
 }
 
-// likelihood3.c:149-160.  tsec = t * 86400 exactly as the reference forms it.  The mean anomaly
-// is bit-identical with the reference's 2 pi (t - T0) / P: the two products are explicitly
-// rounded and the division is the correctly rounded Markstein sequence on rP = RN(1/P).
-// Starter E0 = M + 0.85 e sign(sin M), exactly five Newton steps.  Outputs cos E, sin E and
-// den = 1 - e cos E.
-template <int V>
-__device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
-                                              const double rPs, double (&cE)[V], double (&sE)[V], double (&den)[V])
+// Mean anomaly of likelihood3.c:149-153, bit-identical with the reference's 2 pi (t - T0) / P:
+// the two products are explicitly rounded and the division is the correctly rounded Markstein
+// sequence on rP = RN(1/P).  tsec = t * 86400 exactly as the reference forms it.
+__device__ __forceinline__ double mean_anomaly(double tsec, double T0s, double Ps, double rPs)
 {
-    double M[V], E[V], dE[V];
+    const double x = __dmul_rn(kTwoPi, __dsub_rn(tsec, T0s));
+    const double q0 = __dmul_rn(x, rPs);
+    return fmod_twopi(fma(fma(-Ps, q0, x), rPs, q0));
+}
+
+// Starter of likelihood3.c:154-157: E0 = M + 0.85 e sign(sin M) (E0 = M when sin M == 0).
+// For |M| < fl(2 pi), sin M > 0 on (0, fl(pi)] and < 0 above (sin(fl(pi)) = 1.2e-16 > 0), so the
+// sign is read off M: sign(M) flipped when |M| > fl(pi), and no offset when M == 0.
+__device__ __forceinline__ double kepler_starter(double m, double e)
+{
+    const int hi = __double2hiint(m), lo = __double2loint(m);
+    const int ahi = hi & 0x7fffffff;
+    const bool above_pi = (ahi > 0x400921fb) | ((ahi == 0x400921fb) & ((unsigned)lo > 0x54442d18u));
+    const bool zero = (ahi | lo) == 0;
+    const double off = 0.85 * e;
+    int ohi = __double2hiint(off) ^ (hi & 0x80000000) ^ (above_pi ? 0x80000000 : 0);
+    const double so = zero ? 0.0 : __hiloint2double(ohi, __double2loint(off));
+    return m + so;
+}
+
+// Library-function version of the solve for one sample (cold path; exactly five steps).
+static __device__ __noinline__ void kepler_point_careful(double m, double e, double* cE, double* sE)
+{
+    const double am = fabs(m);
+    double sg = (am <= kPi) ? 1.0 : -1.0;
+    sg = (m < 0.0) ? -sg : sg;
+    sg = (am == 0.0) ? 0.0 : sg;
+    double E = fma(0.85 * e, sg, m), s, c;
+    for (int k = 0; k < 5; k++) {
+        sincos(E, &s, &c);
+        E -= (fma(-e, s, E) - m) / fma(-e, c, 1.0);
+    }
+    sincos(E, &s, &c);
+    *cE = c;
+    *sE = s;
+}
+
+// likelihood3.c:149-160 for V samples: outputs cos E, sin E, den = 1 - e cos E and beta = 1/den.
+// kFullWarp: all 32 lanes of the warp execute this call together (true in the model pass).
+template <int V, bool kFullWarp>
+__device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
+                                              const double rPs, double (&cE)[V], double (&sE)[V], double (&den)[V],
+                                              double (&beta)[V])
+{
+    double M[V], E[V], dE[V], yr[V];
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        const double x = __dmul_rn(kTwoPi, __dsub_rn(tsec[j], T0s));
-        const double q0 = __dmul_rn(x, rPs);
-        const double m = fmod_twopi(fma(fma(-Ps, q0, x), rPs, q0));
-        // sign(sin M) for |M| < fl(2 pi): positive on (0, fl(pi)], negative above (sin(fl(pi)) > 0)
-        const double am = fabs(m);
-        double sg = (am <= kPi) ? 1.0 : -1.0;
-        sg = (m < 0.0) ? -sg : sg;
-        sg = (am == 0.0) ? 0.0 : sg;
-        M[j] = m;
-        E[j] = fma(0.85 * e, sg, m);
+        M[j] = mean_anomaly(tsec[j], T0s, Ps, rPs);
+        E[j] = kepler_starter(M[j], e);
     }
     // The reference always takes five Newton steps.  Once a step is below 2^-27 the next iterate
     // is the root to rounding (quadratic convergence: the following step is ~C step^2 < 1e-16) and
@@ -465,35 +509,50 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
     // have such a step (warp-uniform, no divergence); lanes that never converge (the e -> 1 tail
     // near periastron) run all five steps exactly like the reference.
     bool tiny = false;
+    int hi_max = 0;
 #pragma unroll kNewtonUnroll
     for (int k = 0; k < 5; k++) {
-        sincos_lean<V>(E, sE, cE);
+        sincos_lean<V>(E, sE, cE, hi_max);
         tiny = true;
 #pragma unroll
         for (int j = 0; j < V; j++) {
             const double num = fma(-e, sE[j], E[j]) - M[j];
             const double dn = fma(-e, cE[j], 1.0);
-            const double En = E[j] - div_fast(num, dn);
+            const double En = E[j] - div_fast(num, dn, yr[j]);
             dE[j] = E[j] - En;  // the step actually applied (exact difference of neighbours)
             E[j] = En;
             tiny &= (__double2hiint(dE[j]) & 0x7fffffff) < 0x3e400000;  // |dE| < 2^-27
         }
-        tiny = warp_all(tiny);
+        tiny = warp_all<kFullWarp>(tiny);
         if (tiny) break;
     }
     if (tiny) {
-        // sin/cos(E_prev - dE) to first order: the neglected dE^2/2 < 3e-17 is relative
+        // sin/cos(E_prev - dE) to first order (the neglected dE^2/2 < 3e-17 is relative), and
+        // 1/den from the last reciprocal: den moved by < 1e-8 relative, one Newton step restores 1 ulp
 #pragma unroll
         for (int j = 0; j < V; j++) {
             const double c0 = cE[j], s0 = sE[j];
             cE[j] = fma(s0, dE[j], c0);
             sE[j] = fma(-c0, dE[j], s0);
+            den[j] = fma(-e, cE[j], 1.0);
+            beta[j] = fma(yr[j], fma(-den[j], yr[j], 1.0), yr[j]);
         }
     } else {
-        sincos_lean<V>(E, sE, cE);
-    }
+        sincos_lean<V>(E, sE, cE, hi_max);
 #pragma unroll
-    for (int j = 0; j < V; j++) den[j] = fma(-e, cE[j], 1.0);
+        for (int j = 0; j < V; j++) {
+            den[j] = fma(-e, cE[j], 1.0);
+            beta[j] = rcp_fast(den[j]);
+        }
+    }
+    if (hi_max > kSincosHiLimit) {  // some iterate left the range of the lean sincos: redo with the library
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            kepler_point_careful(M[j], e, &cE[j], &sE[j]);
+            den[j] = fma(-e, cE[j], 1.0);
+            beta[j] = 1.0 / den[j];
+        }
+    }
 }
 
 // likelihood3.c:353-389 with R1 >= R2 already sorted and d already in Rsun.  Written with
@@ -528,14 +587,14 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 
 // Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
-template <int V>
+template <int V, bool kFullWarp>
 __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double (&tsec)[V], double (&u)[V])
 {
-    double cE[V], sE[V], den[V];
-    kepler_points<V>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, cE, sE, den);
+    double cE[V], sE[V], den[V], bet[V];
+    kepler_points<V, kFullWarp>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, cE, sE, den, bet);
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        const double beta = rcp_fast(den[j]);  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
+        const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
         const double cnu = (cE[j] - cc.e) * beta;
         const double snu = cc.sq1me2 * sE[j] * beta;
         const double c = cc.cw * cnu - cc.sw * snu;  // cos(omega0 + nu)
@@ -570,11 +629,12 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double (&ts
     }
 }
 
+template <bool kFullWarp>
 __device__ __forceinline__ double raw_flux1(const ChainConst& cc, double tsec)
 {
     const double t[1] = {tsec};
     double u[1];
-    raw_flux<1>(cc, t, u);
+    raw_flux<1, kFullWarp>(cc, t, u);
     return u[0];
 }
 

@@ -122,7 +122,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         double lo = -INFINITY, hi = INFINITY;
         if (bracketed) {
             const uint32_t seed = (uint32_t)cc.seed;
-            const double us = raw_flux1(cc, tsec[sample_index(tid, kThreads, N, seed)]);
+            const double us = raw_flux1<true>(cc, tsec[sample_index(tid, kThreads, N, seed)]);
             // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
             const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
             int r_lo, r_hi, r_mid;
@@ -165,7 +165,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 idx[j] = base + j * kThreads + tid;
                 ts[j] = tsec[idx[j] < N ? idx[j] : N - 1];
             }
-            raw_flux<V>(cc, ts, u);
+            raw_flux<V, true>(cc, ts, u);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -305,8 +305,8 @@ __global__ void k_traj(const double* __restrict__ times, int Nt, const double* _
     const double Mtot = Ma + Mb;
     const double a = pow(kG * Mtot * sq(P) / sq(2 * kPi), 1. / 3.);
     const double ts[1] = {__dmul_rn(times[i], kSecDay)};
-    double cE[1], sE[1], den[1];
-    kepler_points<1>(ts, e, T0, P, __drcp_rn(P), cE, sE, den);
+    double cE[1], sE[1], den[1], bet[1];
+    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), cE, sE, den, bet);
     const double r = a * den[0];
     const double sq1 = sqrt(1 - e * e);
     const double nu = atan2(sq1 * sE[0], cE[0] - e);

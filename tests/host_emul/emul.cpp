@@ -24,6 +24,7 @@ static inline int __double2loint(double x) { return (int)(__double_as_longlong(x
 static inline double __hiloint2double(int hi, int lo) { return __longlong_as_double(((long long)hi << 32) | (unsigned int)lo); }
 static inline double __int2double_rn(int x) { return (double)x; }
 static inline int __double2int_rn(double x) { return (int)nearbyint(x); }
+static inline int max(int a, int b) { return a > b ? a : b; }
 #define HB_HOST_EMUL 1
 #define __constant__ static const
 #include "hb_device_host.cuh"
@@ -58,11 +59,11 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out)
     for (; i + 2 <= n; i += 2) {  // the two-wide path the kernel uses
         const double ts[2] = {__dmul_rn(t[i], kSecDay), __dmul_rn(t[i + 1], kSecDay)};
         double u[2];
-        raw_flux<2>(cc, ts, u);
+        raw_flux<2, true>(cc, ts, u);
         out[i] = u[0];
         out[i + 1] = u[1];
     }
-    for (; i < n; i++) out[i] = raw_flux1(cc, __dmul_rn(t[i], kSecDay));
+    for (; i < n; i++) out[i] = raw_flux1<false>(cc, __dmul_rn(t[i], kSecDay));
 }
 
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
@@ -77,7 +78,9 @@ extern "C" void emul_sincos(const double* x, long n, double* s, double* c)
     for (long i = 0; i < n; i++) {
         const double xv[1] = {x[i]};
         double sv[1], cv[1];
-        sincos_lean<1>(xv, sv, cv);
+        int hm = 0;
+        sincos_lean<1>(xv, sv, cv, hm);
+        if (hm > kSincosHiLimit) { sv[0] = sin(x[i]); cv[0] = cos(x[i]); }
         s[i] = sv[0];
         c[i] = cv[0];
     }
