@@ -315,10 +315,16 @@ int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* 
     cudaFree(ctx->d_t); cudaFree(ctx->d_flux); cudaFree(ctx->d_w);
     ctx->d_t = ctx->d_flux = ctx->d_w = nullptr;
     ctx->has_data = false;
-    size_t alloc = (size_t)std::max(n, 1L) * sizeof(double);
+    // padded to whole TMA tiles (k_chain_eval copies full tiles); the padding is finite and never used
+    const size_t tile = (size_t)eval_tile();
+    const size_t padded = ((size_t)std::max(n, 1L) + tile - 1) / tile * tile;
+    size_t alloc = padded * sizeof(double);
     CK(cudaMalloc((void**)&ctx->d_t, alloc));
     CK(cudaMalloc((void**)&ctx->d_flux, alloc));
     CK(cudaMalloc((void**)&ctx->d_w, alloc));
+    CK(cudaMemsetAsync(ctx->d_t, 0, alloc, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_flux, 0, alloc, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_w, 0, alloc, ctx->stream));
     // weights 1/max(sigma, 1e-5): the clamp of likelihood3.c:824-827 applied once at upload
     std::vector<double> w((size_t)n);
     for (long i = 0; i < n; i++) w[i] = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
@@ -413,8 +419,11 @@ static int stage_times(hb_ctx* ctx, const double* times, long nt)
         if (ctx->d_times2) cudaFree(ctx->d_times2);
         ctx->d_times2 = nullptr;
         ctx->cap_times2 = 0;
-        CK(cudaMalloc((void**)&ctx->d_times2, (size_t)nt * sizeof(double)));
-        ctx->cap_times2 = nt;
+        const size_t tile = (size_t)eval_tile();
+        const size_t padded = ((size_t)nt + tile - 1) / tile * tile;  // whole TMA tiles
+        CK(cudaMalloc((void**)&ctx->d_times2, padded * sizeof(double)));
+        CK(cudaMemsetAsync(ctx->d_times2, 0, padded * sizeof(double), ctx->stream));
+        ctx->cap_times2 = (long)padded;
     }
     return upload(ctx, ctx->d_times2, times, (size_t)nt);
 }

@@ -41,7 +41,65 @@ __device__ __forceinline__ double block_sum_double(double v, double* red)
     return t;
 }
 
+// ---- staging of the data stream ---------------------------------------------------------------
+// The observed light curve (t, flux, 1/sigma: 24 B per sample) is read by every chain and stays
+// L2-resident.  Two ways to bring it to the math were built and measured on B200 (C2, 4096 x 20k):
+//   HB_TMA_STAGING = 0 (default)  coalesced LDG, software-pipelined one iteration ahead in registers:
+//                                 1.490 ms
+//   HB_TMA_STAGING = 1            TMA bulk copies (cp.async.bulk -> SASS UBLKCP) of whole 256-sample
+//                                 tiles into a 2-stage shared-memory ring, completion by mbarrier
+//                                 expect_tx/complete_tx, stage reuse by a second mbarrier the warps
+//                                 arrive on: 1.570 ms (the ring couples the warps to within one
+//                                 iteration of each other); a per-warp variant with 256-byte slices
+//                                 was 1.733 ms.
+// At ~2000 cycles of FP64 work per 24 bytes the stream is far from any bandwidth limit, so the
+// variant with the least synchronisation wins; the TMA path is kept selectable.
+#ifndef HB_TMA_STAGING
+#define HB_TMA_STAGING 0
+#endif
+constexpr int kTile = kPointsPerThread * kEvalThreads;  // samples per loop iteration of a CTA
+constexpr int kStages = 2;
+
+struct TileStage {
+    double ts[kTile], fl[kTile], wv[kTile];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 struct EvalShared {
+#if HB_TMA_STAGING
+    alignas(16) TileStage stage[kStages];
+    uint64_t full_bar[kStages], empty_bar[kStages];
+#endif
     ChainConst cc;
     SelectCtl<kEvalThreads> ctl;
     double red[3 * 32];
@@ -51,6 +109,7 @@ struct EvalShared {
 };
 
 size_t eval_smem_bytes() { return sizeof(EvalShared); }
+int eval_tile() { return kTile; }
 
 // Median rank of likelihood3.c:97-101 (quirk Q3): even N -> N/2, odd N -> N/2 + 1.  N == 1
 // would read one past the end in the reference; the only element is used instead.
@@ -88,6 +147,19 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     __shared__ int s_chain;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int krank = median_rank(N);
+    const int n_tiles = (N + kTile - 1) / kTile;
+#if HB_TMA_STAGING
+    if (tid == 0) {
+        for (int st = 0; st < kStages; st++) {
+            mbar_init(&sm.full_bar[st], 1);
+            mbar_init(&sm.empty_bar[st], kThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t git = 0;  // tiles consumed so far by this CTA (all chains): stage = git % 2, phase = git / 2
+    const uint32_t tile_bytes = kTile * sizeof(double);
+#endif
 
     for (;;) {
         // dynamic chain scheduler: chains differ in cost (eclipse fraction, Roche early-out)
@@ -157,14 +229,59 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         int nanflag = 0, c_lt = 0;
         double S0 = 0., S1 = 0., S2 = 0.;
         constexpr int V = kPointsPerThread;
-        for (int base = 0; base < N; base += V * kThreads) {
+#if HB_TMA_STAGING
+        // the data arrays are padded to whole tiles by the host side, so every copy is a full tile
+        auto issue_tile = [&](int tile, uint32_t g) {
+            const int st = g % kStages;
+            const size_t off = (size_t)tile * kTile;
+            mbar_expect_tx(&sm.full_bar[st], flux != nullptr ? 3 * tile_bytes : tile_bytes);
+            bulk_g2s(sm.stage[st].ts, tsec + off, tile_bytes, &sm.full_bar[st]);
+            if (flux != nullptr) {
+                bulk_g2s(sm.stage[st].fl, flux + off, tile_bytes, &sm.full_bar[st]);
+                bulk_g2s(sm.stage[st].wv, w + off, tile_bytes, &sm.full_bar[st]);
+            }
+        };
+        if (tid == 0) issue_tile(0, git);  // every stage is free here: the chain-level barriers drained the pipe
+        for (int tile = 0; tile < n_tiles; tile++, git++) {
+            const int base = tile * kTile;
+            const int st = git % kStages;
+            if (tid == 0 && tile + 1 < n_tiles) {
+                // next tile into the other stage, once every warp has taken the previous tile out of it
+                if (tile >= 1) mbar_wait(&sm.empty_bar[(git + 1) % kStages], ((git - 1) / kStages) & 1);
+                issue_tile(tile + 1, git + 1);
+            }
+            mbar_wait(&sm.full_bar[st], (git / kStages) & 1);
             int idx[V];
-            double ts[V], u[V];
+            double ts[V], u[V], fl[V], wv[V];
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 idx[j] = base + j * kThreads + tid;
-                ts[j] = tsec[idx[j] < N ? idx[j] : N - 1];
+                ts[j] = sm.stage[st].ts[j * kThreads + tid];
+                fl[j] = sm.stage[st].fl[j * kThreads + tid];
+                wv[j] = sm.stage[st].wv[j * kThreads + tid];
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty_bar[st]);
+#else
+        // software pipeline: the next iteration's time samples and this iteration's (flux, weight)
+        // are requested from L2 before the ~2000-cycle model evaluation that hides their latency
+        // (the arrays are padded to whole tiles, so no index clamp is needed)
+        double ts_next[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) ts_next[j] = tsec[j * kThreads + tid];
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int base = tile * kTile;
+            int idx[V];
+            double ts[V], u[V], fl[V], wv[V];
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                idx[j] = base + j * kThreads + tid;
+                ts[j] = ts_next[j];
+                if (tile + 1 < n_tiles) ts_next[j] = tsec[idx[j] + kTile];
+                fl[j] = (flux != nullptr) ? flux[idx[j]] : 0.0;
+                wv[j] = (flux != nullptr) ? w[idx[j]] : 0.0;
+            }
+#endif
             raw_flux<V, true>(cc, ts, u);
 #pragma unroll
             for (int j = 0; j < V; j++) {
@@ -187,8 +304,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                     }
                 }
                 if (flux != nullptr && valid) {
-                    const double wi = w[i];
-                    const double a = fma(A, uj - u0, ft - flux[i]);
+                    const double wi = wv[j];
+                    const double a = fma(A, uj - u0, ft - fl[j]);
                     const double r = a * wi;
                     S0 = fma(r, r, S0);
                     S1 = fma(r, wi, S1);

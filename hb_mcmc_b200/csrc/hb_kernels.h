@@ -32,6 +32,7 @@ constexpr int kCandA = HB_CAND_A;              // shared-memory survivor buffers
 constexpr int kCandB = HB_CAND_B;
 
 size_t eval_smem_bytes();
+int eval_tile();  // samples per TMA tile: device time / flux / weight arrays are padded to a multiple of it
 cudaError_t configure_eval();
 cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, cudaStream_t s);
 cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double* flux, const double* w,
