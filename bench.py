@@ -227,6 +227,11 @@ def gpu_arm(args, cfg, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hb_mcmc_b200 path has no CPU fallback")
+    # stdout carries exactly one JSON line: anything native libraries print (NCCL's version banner
+    # goes to fd 1) is sent to stderr until the result line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -350,7 +355,10 @@ def gpu_arm(args, cfg, rank, local_rank, world):
             line["pt"] = pt_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg(cfg, t, flux, err, P, logL_dev)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -2,10 +2,10 @@
 //
 //   k_prologue    one thread per chain: parameters -> ChainConst (hb_device.cuh)
 //   k_chain_eval  persistent CTAs, one chain at a time per CTA:
-//                   pass B  model at every time sample  -> template keys in scratch
-//                   select  exact order statistic (reference median rule, quirk Q3)
-//                   pass D  normalise + chi^2 against (flux, 1/sigma) -> logL
-//   k_traj / k_scalar / k_mags   device versions of the small likelihood3.h entry points
+//                   pre-sample  256 model values -> bracket of the median rank + chi^2 pivot
+//                   model pass  u at every sample; candidates in the bracket, chi^2 partial sums
+//                   select      exact order statistic (reference median rule, quirk Q3) -> logL
+//   k_order_stat / k_traj / k_scalar / k_gaia / k_chain_info   the small likelihood3.h entry points
 //   k_fp64_peak   DFMA throughput probe (the roofline denominator, measured on the box)
 //
 // Replaces likelihood3.c:809-873 (loglikelihood) and :530-686 (calc_light_curve).
@@ -25,22 +25,6 @@ __global__ void k_prologue(const double* __restrict__ params, int n, MagSetup ms
     out[c] = cc;
 }
 
-// ---------------------------------------------------------------------------
-template <int kThreads>
-__device__ __forceinline__ double block_sum_double(double v, double* red)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if (lane == 0) red[wid] = v;
-    __syncthreads();
-    double t = 0;
-#pragma unroll
-    for (int i = 0; i < kThreads / 32; i++) t += red[i];
-    return t;
-}
-
 // ---- staging of the data stream ---------------------------------------------------------------
 // The observed light curve (t, flux, 1/sigma: 24 B per sample) is read by every chain and stays
 // L2-resident.  Two ways to bring it to the math were built and measured on B200 (C2, 4096 x 20k):
@@ -58,7 +42,7 @@ __device__ __forceinline__ double block_sum_double(double v, double* red)
 #define HB_TMA_STAGING 0
 #endif
 constexpr int kTile = kPointsPerThread * kEvalThreads;  // samples per loop iteration of a CTA
-constexpr int kStages = 2;
+[[maybe_unused]] constexpr int kStages = 2;
 
 struct TileStage {
     double ts[kTile], fl[kTile], wv[kTile];

@@ -542,8 +542,8 @@ double orc_get_logP(const double *pars, const int *gauss)
 }
 
 /* Boundary handling + the post-proposal fix-ups of mcmc_wrapper2.c:440-481, applied in
- * place to a proposal y.  Keeps quirk Q5 (the "order the masses" block copies instead of
- * swapping, so y[0] == y[1] == min afterwards... precisely: y[1] = y[0]; y[0] = y[1]). */
+ * place to a proposal y.  Keeps quirk Q5: the "order the masses" block assigns y[1] = y[0] and
+ * then y[0] = y[1] (its tmp is never used), so both end up equal to the old y[0]. */
 void orc_enforce_bounds(double *y, const double *lo, const double *hi, const double *mode_lo,
                         const double *mode_hi, double log_lc_period, double lc_period)
 {
@@ -734,9 +734,7 @@ int orc_pt_propose(unsigned long long seed, unsigned id, unsigned iter, double t
     if (quirks) {
         orc_enforce_bounds(y, lo, hi, mode_lo, mode_hi, log_lc_period, pow(10., log_lc_period));
     } else {
-        double y0 = y[0], y1 = y[1];
-        (void)y0; (void)y1;
-        /* run the reference fix-ups on a copy with masses pre-swapped so that its copy is a no-op */
+        /* same boundary loops as orc_enforce_bounds, then a real swap of the masses */
         for (int i = 0; i < ORC_NPARS; i++) {
             while (((mode_lo[i] == 1) && (y[i] < lo[i])) || ((mode_hi[i] == 1) && (y[i] > hi[i]))) {
                 if (y[i] < lo[i]) y[i] = 2.0 * lo[i] - y[i];
