@@ -43,6 +43,19 @@ METRIC = "model_point_logL_evals_per_sec"
 UNIT = "points/s"
 FLOP_PER_POINT = 520.0  # 156 plain + 6 sincos x 40 + 8 div x 14 + 1 sqrt x 14
 NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
+BYTES_PER_POINT = 8.0       # algorithmic HBM bytes: the template key store (the data stream is shared by all chains)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_chain_eval launch on C2, ncu --set full
+# (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload
+NCU_TRAFFIC_C2_BYTES = 64.142592e6 + 668.577280e6
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md"
+
 
 
 def parse_args():
@@ -343,7 +356,10 @@ def gpu_arm(args, cfg, rank, local_rank, world):
             "clocks": sampler.summary(t_begin, t_end),
             "roofline": {
                 "bound": "fp64", "kernel": "k_chain_eval", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+                "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
+                "traffic": NCU_TRAFFIC_C2_BYTES if (args.workload == "C2" and not args.chains and not args.points) else None,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_chain_eval_ncu_summary.txt)",
+                "hbm": hbm_block(n, N, k_ms),
                 "flop_per_point": FLOP_PER_POINT, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "peak_source": "hb_fp64_peak DFMA probe on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
@@ -363,6 +379,15 @@ def gpu_arm(args, cfg, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def hbm_block(n, N, k_ms):
+    """Secondary roofline: the kernel's algorithmic HBM stream against the measured copy bandwidth
+    (it is not the bound: ~7 % of peak)."""
+    peak, src = measured_hbm_peak()
+    gbs = float(n) * N * BYTES_PER_POINT / (k_ms * 1e-3) * 1e-9
+    return {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bytes_per_point": BYTES_PER_POINT,
+            "peak_source": src}
 
 
 def pt_leg(args, ctx, cfg, rank, world, dist, stream):
