@@ -88,6 +88,7 @@ struct EvalShared {
     SelectCtl<kEvalThreads> ctl;
     double red[3 * 32];
     double pivot;  // chi^2 expansion point u0 (a template value near the median)
+    double ktab[kTableSize];  // the chain's E(M) starter table (hb_device.cuh)
     uint64_t candA[kCandA];
     uint64_t candB[kCandB];
 };
@@ -171,6 +172,15 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             continue;
         }
 
+        // ---- E(M) starter table for chains whose solve is path-independent (0 <= e <= 0.8) ----
+        const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= 4 * kTableSize);
+        const double* ktab = use_table ? sm.ktab : nullptr;
+        if (use_table) {
+            const double e = cc.e;
+            for (int j = tid; j < kTableSize; j += kThreads) sm.ktab[j] = kepler_table_node(j, e);
+            __syncthreads();
+        }
+
         // ---- pre-sample: bracket of the median rank + expansion point ----
         const bool bracketed = N > kThreads;
         uint64_t* cand = sm.candA;  // first-round survivors
@@ -178,7 +188,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         double lo = -INFINITY, hi = INFINITY;
         if (bracketed) {
             const uint32_t seed = (uint32_t)cc.seed;
-            const double us = raw_flux1<true>(cc, tsec[sample_index(tid, kThreads, N, seed)]);
+            const double us = raw_flux1<true>(cc, ktab, tsec[sample_index(tid, kThreads, N, seed)]);
             // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
             const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
             int r_lo, r_hi, r_mid;
@@ -266,7 +276,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 wv[j] = (flux != nullptr) ? w[idx[j]] : 0.0;
             }
 #endif
-            raw_flux<V, true>(cc, ts, u);
+            raw_flux<V, true>(cc, ktab, ts, u);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -407,7 +417,7 @@ __global__ void k_traj(const double* __restrict__ times, int Nt, const double* _
     const double a = pow(kG * Mtot * sq(P) / sq(2 * kPi), 1. / 3.);
     const double ts[1] = {__dmul_rn(times[i], kSecDay)};
     double cE[1], sE[1], den[1], bet[1];
-    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), cE, sE, den, bet);
+    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), nullptr, cE, sE, den, bet);
     const double r = a * den[0];
     const double sq1 = sqrt(1 - e * e);
     const double nu = atan2(sq1 * sE[0], cE[0] - e);

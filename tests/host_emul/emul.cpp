@@ -25,6 +25,8 @@ static inline double __hiloint2double(int hi, int lo) { return __longlong_as_dou
 static inline double __int2double_rn(int x) { return (double)x; }
 static inline int __double2int_rn(double x) { return (int)nearbyint(x); }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int __double2int_rd(double x) { return (int)floor(x); }
 #define HB_HOST_EMUL 1
 #define __constant__ static const
 #include "hb_device_host.cuh"
@@ -50,20 +52,27 @@ extern "C" void emul_prologue(const double* p, const double* md, const double* m
 }
 
 // raw (un-normalised) template, likelihood3.c:673
-extern "C" void emul_raw(const double* p, const double* t, long n, double* out)
+extern "C" void emul_raw(const double* p, const double* t, long n, double* out, int use_table)
 {
     const double md[5] = {1000, 1, 1, 1, 1}, me[4] = {1e15, 1e15, 1e15, 1e15};
     ChainConst cc;
     chain_prologue(p, default_mags(md, me, 1, 0), cc);
+    // the kernel's starter table for chains with 0 <= e <= kTableMaxE (use_table != 0)
+    static double tab[kTableSize];
+    const double* ktab = nullptr;
+    if (use_table && cc.e >= 0.0 && cc.e <= kTableMaxE) {
+        for (int j = 0; j < kTableSize; j++) tab[j] = kepler_table_node(j, cc.e);
+        ktab = tab;
+    }
     long i = 0;
     for (; i + 2 <= n; i += 2) {  // the two-wide path the kernel uses
         const double ts[2] = {__dmul_rn(t[i], kSecDay), __dmul_rn(t[i + 1], kSecDay)};
         double u[2];
-        raw_flux<2, true>(cc, ts, u);
+        raw_flux<2, true>(cc, ktab, ts, u);
         out[i] = u[0];
         out[i + 1] = u[1];
     }
-    for (; i < n; i++) out[i] = raw_flux1<false>(cc, __dmul_rn(t[i], kSecDay));
+    for (; i < n; i++) out[i] = raw_flux1<false>(cc, ktab, __dmul_rn(t[i], kSecDay));
 }
 
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)

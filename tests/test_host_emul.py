@@ -25,7 +25,7 @@ def emul():
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(EMUL, "emul.cpp")],
                    check=True, cwd=EMUL)
     L = C.CDLL(so)
-    L.emul_raw.argtypes = [dp, dp, C.c_long, dp]
+    L.emul_raw.argtypes = [dp, dp, C.c_long, dp, C.c_int]
     L.emul_finish.argtypes = [dp, C.c_long, C.c_double, C.c_double, C.c_double, dp]
     L.emul_fmod_twopi.restype = C.c_double
     L.emul_fmod_twopi.argtypes = [C.c_double]
@@ -68,11 +68,11 @@ def test_phase_division_is_ieee(emul):
     assert np.array_equal(out, x / P)
 
 
-def raw(L, p, t):
+def raw(L, p, t, use_table=1):
     p = np.ascontiguousarray(p, dtype=np.float64)
     t = np.ascontiguousarray(t, dtype=np.float64)
     out = np.empty(t.size)
-    L.emul_raw(p.ctypes.data_as(dp), t.ctypes.data_as(dp), t.size, out.ctypes.data_as(dp))
+    L.emul_raw(p.ctypes.data_as(dp), t.ctypes.data_as(dp), t.size, out.ctypes.data_as(dp), use_table)
     return out
 
 
@@ -106,6 +106,26 @@ def test_raw_template_random_draws(emul, orc):
             scale = np.maximum(np.abs(want), 1.0)
             worst = max(worst, np.nanmax(np.abs(got - want) / scale))
         assert worst < 1e-11, worst
+
+
+def test_table_starter_equals_reference_starter(emul, orc):
+    """Chains with e <= 0.8 start Newton from the E(M) table: same converged root, so the raw template
+    agrees with the reference-starter path (and hence the oracle) to rounding noise."""
+    t = wl.time_grid(4000) * 5.0 - 3.0
+    P = wl.draw_chains(96, wl.TRUTH_A, lambda P: np.array([orc.roche_overflow(p) for p in P]), seed=11, e_max=0.8)
+    for k, e in enumerate([0.0, 1e-9, 0.3, 0.5, 0.6, 0.7, 0.79, 0.8]):
+        q = P[k].copy()
+        q[3] = e
+        if not orc.roche_overflow(q):
+            P[k] = q
+    worst = 0.0
+    for p in P:
+        a, b = raw(emul, p, t, 1), raw(emul, p, t, 0)
+        scale = np.maximum(np.abs(b), 1.0)
+        worst = max(worst, np.nanmax(np.abs(a - b) / scale))
+        _, want = orc.calc_light_curve(t, p, raw=True)
+        assert np.nanmax(np.abs(a - want) / scale) < 1e-11
+    assert worst < 2e-13, worst
 
 
 def test_finish_matches_reference_order(emul, orc):
