@@ -54,7 +54,8 @@ struct ChainConst {
     double blend, ft;
     // per-chain additive chi^2 (Gaia magnitude / colour terms) and flags
     double chi2_extra;
-    double flag;  // bit 0: Roche overflow, bit 1: model is NaN by construction (e >= 1 or NaN e)
+    double flag;  // bit 0: Roche overflow, bit 1: model is NaN by construction (e >= 1 or NaN e),
+                  // bit 2: the projected separation never drops below R1 + R2 (no sample can be in eclipse)
     double seed;  // 32-bit hash of the parameter bits: sampling jitter of the select (a chain's
                   // result does not depend on where it sits in the batch)
     // diagnostics (hb_chain_info): R1 R2 T1 T2 G B-V V-G G-T
@@ -84,6 +85,28 @@ __device__ inline double interp_nodes(double m, const double* mn, const double* 
         }
     }
     return r;
+}
+
+// m = 10^logM is passed in by the prologue (one exp10 per star instead of three pow calls)
+__device__ inline double dev_getT_m(double m)
+{
+    const double mn[16] = {0.1, 0.26, 0.47, 0.59, 0.69, 0.87, 0.98, 1.085, 1.4, 1.65, 2.0, 2.5, 3.0, 4.4, 15., 40.};
+    const double tn[16] = {3.491, 3.531, 3.547, 3.584, 3.644, 3.712, 3.745, 3.774,
+                           3.823, 3.863, 3.913, 3.991, 4.057, 4.182, 4.477, 4.623};
+    return interp_nodes(m, mn, tn, 16);
+}
+
+__device__ inline double dev_getR_m(double m)
+{
+    const double mn[10] = {0.07, 0.2, 0.356, 0.655, 0.784, 0.787, 1.377, 4.4, 15., 40.};
+    const double rn[10] = {-0.953, -0.627, -0.423, -0.154, -0.082, -0.087, 0.295, 0.477, 0.792, 1.041};
+    return interp_nodes(m, mn, rn, 10);
+}
+
+__device__ inline double dev_envelope_radius_m(double m)
+{
+    const double n = 4.22, slope = 15.68, floor_ = 0.01, corner = 1.055, ceil_ = 0.17;
+    return 1 / (1 / ceil_ + 1 / (slope * pow((pow(m, n) + pow(corner, n)), (1 / n)) - (slope * corner - floor_)));
 }
 
 __device__ inline double dev_getT(double logM)
@@ -153,8 +176,8 @@ __device__ inline void two_bb_mags(double R1, double R2, double T1, double T2, d
 
 __device__ inline double eggleton_dev(double q)  // likelihood3.c:945-948
 {
-    double q23 = pow(q, 2. / 3);
-    return 0.49 * q23 / (0.6 * q23 + log(1 + pow(q, 1. / 3)));
+    const double q13 = cbrt(q), q23 = q13 * q13;
+    return 0.49 * q23 / (0.6 * q23 + log(1 + q13));
 }
 
 // ---------------------------------------------------------------------------
@@ -169,12 +192,18 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     const double aref[2] = {p[13], p[14]};
     const double blending = p[19], ft = p[20];
 
+    // Transcendentals are the latency of this kernel (one thread per chain).  Everything that feeds
+    // the orbit phase or the eclipse geometry (P, M, R, a) keeps the reference's pow() calls: CUDA's
+    // pow and glibc's agree to the last bit almost always, and an ulp there is amplified ~1e5 x by
+    // the ill-conditioned asin(h/R) of eclipse_area (measured: worst logL deviation 1.1e-11 with
+    // pow, 8.5e-11 with exp10/cbrt).  10^logM is formed once per star instead of four times, and
+    // the flux COEFFICIENTS (smooth, O(1e-3) terms) use cbrt instead of pow(x, k/3).
     const double M[2] = {pow(10., logM1), pow(10., logM2)};
     // radii / temperatures (likelihood3.c:693-717)
-    const double R[2] = {pow(10., dev_getR(logM1) + p[7] * dev_envelope_radius(logM1)),
-                         pow(10., dev_getR(logM2) + p[8] * dev_envelope_radius(logM2))};
-    const double Te[2] = {pow(10., dev_getT(logM1) + p[17] * dev_envelope_temp(logM1)),
-                          pow(10., dev_getT(logM2) + p[18] * dev_envelope_temp(logM2))};
+    const double R[2] = {pow(10., dev_getR_m(M[0]) + p[7] * dev_envelope_radius_m(M[0])),
+                         pow(10., dev_getR_m(M[1]) + p[8] * dev_envelope_radius_m(M[1]))};
+    const double Te[2] = {pow(10., dev_getT_m(M[0]) + p[17] * dev_envelope_temp(logM1)),
+                          pow(10., dev_getT_m(M[1]) + p[18] * dev_envelope_temp(logM2))};
     // luminosity fractions (likelihood3.c:612-614)
     const double L1 = sq(R[0]) * sq(sq(Te[0])), L2 = sq(R[1]) * sq(sq(Te[1]));
     const double Nrm[2] = {L1 / (L1 + L2), L2 / (L1 + L2)};
@@ -204,8 +233,8 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     }
 
     const double ppm = 1.e-6;
-    const double Pm13 = pow(Pd, -1. / 3), Pm43 = pow(Pd, -4. / 3), Pm83 = pow(Pd, -8. / 3), Pm103 = pow(Pd, -10. / 3);
-    const double Prot = Pd * pow(1 - e, 3. / 2);
+    const double Pm13 = 1.0 / cbrt(Pd), Pm43 = Pm13 / Pd, Pm83 = Pm43 * Pm43, Pm103 = Pm83 * Pm13 * Pm13;
+    const double Prot = Pd * ((1 - e) * sqrt(1 - e));
 
     double K0 = 0, K1 = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, c1 = 0, c3 = 0, d0 = 0, d2 = 0, d4 = 0;
 #pragma unroll
@@ -215,8 +244,10 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
         const double sgn = (k == 0) ? 1.0 : -1.0;  // star 2 sees omega0 + pi: odd harmonics flip
         const double N = Nrm[k];
         const double q = Mb / Ma;
+        const double Ma13 = cbrt(Ma), q13 = cbrt(1 + q);                 // Ma^(1/3), (1+q)^(1/3)
+        const double iMa23 = 1.0 / (Ma13 * Ma13), iq23 = 1.0 / (q13 * q13);  // ^(-2/3)
         // beaming, likelihood3.c:224-236 (pow(1+q, 2/3) == 1, quirk Q1)
-        const double B = -2830. * ab[k] * q * pow(Ma, 1. / 3) * Pm13 * si / cc.sq1me2 * ppm;
+        const double B = -2830. * ab[k] * q * Ma13 * Pm13 * si / cc.sq1me2 * ppm;
         // ellipsoidal coefficient set, likelihood3.c:258-264
         const double al11 = 15 * mu[k] * (2 + tau[k]) / (32 * (3 - mu[k]));
         const double al21 = 3 * (15 + mu[k]) * (1 + tau[k]) / (20 * (3 - mu[k]));
@@ -224,8 +255,8 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
         const double al01 = al21 / 9, al0b1 = 3 * al2b1 / 20, al31 = 5 * al11 / 3, al41 = 7 * al2b1 / 4;
         const double R3 = Rs * Rs * Rs, R4 = R3 * Rs, R5 = R4 * Rs;
         const double qq = q / (1 + q);
-        const double Mm53 = pow(Ma, -5. / 3) * q / pow(1 + q, 5. / 3) * Pm103;  // order-5 common factor
-        const double Mm43 = pow(Ma, -4. / 3) * q / pow(1 + q, 4. / 3) * Pm83;   // order-4 common factor
+        const double Mm53 = (iMa23 / Ma) * q * (iq23 / (1 + q)) * Pm103;        // Ma^-5/3 q (1+q)^-5/3 P^-10/3
+        const double Mm43 = (iMa23 * iMa23) * q * (iq23 * iq23) * Pm83;         // Ma^-4/3 q (1+q)^-4/3 P^-8/3
         const double AM1 = 13435. * 2 * al01 * (2 - 3 * si2) / Ma / sq(Prot) * R3 * ppm;
         const double AM2 = 13435. * 3 * al01 * (2 - 3 * si2) / Ma * qq / sq(Pd) * R3 * ppm;       // x beta^3
         const double C21 = 13435. * al21 * si2 / Ma * qq / sq(Pd) * R3 * ppm;                     // x beta^3 cos2x
@@ -235,7 +266,7 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
         const double S3 = 3194. * al31 * si3 * Mm43 * R4 * ppm;                                   // x beta^4 sin3x
         const double C4 = 759. * al41 * si4 * Mm53 * R5 * ppm;                                    // x beta^5 cos4x
         // reflection, likelihood3.c:322-337
-        const double Rf = 56514. * aref[k] * pow(1 + q, -2. / 3) * pow(Ma, -2. / 3) * Pm43 * sq(Ro) * ppm;  // x beta^2
+        const double Rf = 56514. * aref[k] * iq23 * iMa23 * Pm43 * sq(Ro) * ppm;  // x beta^2
 
         K0 += N * (1 + AM1);
         K1 += sgn * N * B;
@@ -281,14 +312,16 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     {
         const double M1 = M[0] * kMsun, M2 = M[1] * kMsun;
         const double q = M1 / M2;
-        const double sep = pow(kG * (M1 + M2) * sq(cc.Ps) / (4.0 * kPi * kPi), 1. / 3.);
+        const double sep = cbrt(kG * (M1 + M2) * sq(cc.Ps) / (4.0 * kPi * kPi));
         const double r1 = R[0] * kRsun / (sep * (1 - e));
         const double r2 = R[1] * kRsun / (sep * (1 - e));
         roche = ((eggleton_dev(q) < r1) || (eggleton_dev(1 / q) < r2)) ? 1 : 0;
     }
     // e >= 1 (reachable, quirk Q4) or NaN e: the reference's template is NaN at every sample
     const int nan_model = !(e < 1.0) ? 1 : 0;
-    cc.flag = (double)(roche | (nan_model << 1));
+    // d >= r_min |cos i| with r_min = a (1 - |e|): chains that can never eclipse skip the per-sample test
+    const int no_eclipse = (cc.ar * (1 - fabs(e)) * fabs(ci) >= (cc.Rb + cc.Rs) * (1.0 + 1e-9)) ? 1 : 0;
+    cc.flag = (double)(roche | (nan_model << 1) | (no_eclipse << 2));
     {
         uint32_t h = 0x811c9dc5u;
         for (int i = 0; i < NPARS; i++) {
@@ -645,6 +678,7 @@ template <int V, bool kFullWarp>
 __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab, const double (&tsec)[V],
                                          double (&u)[V])
 {
+    const bool may_eclipse = (((int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
     kepler_points<V, kFullWarp>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cE, sE, den, bet);
 #pragma unroll
@@ -671,7 +705,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
         const double rr = cc.ar * den[j];
         const double d2 = rr * rr * proj2;
         const double lim = cc.Rb + cc.Rs;
-        if (d2 < lim * lim * (1.0 + 1e-9)) {
+        if (may_eclipse && d2 < lim * lim * (1.0 + 1e-9)) {
             const double d = fabs(rr * sqrt(proj2));
             if (!(d >= lim)) {
                 const double area = eclipse_area_dev(cc.Rb, cc.Rs, d);
