@@ -410,6 +410,11 @@ __constant__ double kSinC[6] = {-1.66666666666666324348e-01, 8.33333333332248946
                                 2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
 __constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                 -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+// Scalar constants of the per-sample code as constant-bank operands (a literal double costs two
+// UMOV per use): 0 fl(2 pi)  1 1/fl(2 pi)  2 magic - 0.5  3 magic = 1.5 * 2^52  4 table nodes per
+// radian  5 -1/6  6 1/6  7 fl(pi)
+__constant__ double kMisc[8] = {6.283185307179586476925, 0.15915494309189534561, 6755399441055743.5, 6755399441055744.0,
+                                162.97466172610083, -1.0 / 6.0, 1.0 / 6.0, 3.14159265358979323846};
 // pi/2 split in three (Cody-Waite), 2/pi, and the round-to-integer magic number 1.5 * 2^52
 __constant__ double kRed[5] = {1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983880e-33,
                                6.36619772367581382433e-01, 6755399441055744.0};
@@ -462,22 +467,25 @@ __device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out
     }
 }
 
-static __device__ __noinline__ double fmod_library(double a, double b) { return fmod(a, b); }
-
-// Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153): a rounded quotient
-// from the magic-number trick, one exact FMA remainder, and a rare off-by-one repair.
-__device__ __forceinline__ double fmod_twopi(double M)
+// rare tail of fmod_twopi: quotient off by one (|M| within rounding of a multiple of 2 pi), or
+// huge / inf / NaN input
+static __device__ __noinline__ double fmod_twopi_fix(double q, double r, double am)
 {
     const double y = kTwoPi;
+    if (!(am < 1.0e15)) return fmod(am, y);
+    q += (r < 0.0) ? -1.0 : 1.0;
+    return fma(-q, y, am);  // exact: 0 <= r < y is representable
+}
+
+// Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153): a rounded quotient
+// from the magic-number trick and one exact FMA remainder; one range test catches both the
+// off-by-one quotient and non-finite input.
+__device__ __forceinline__ double fmod_twopi(double M)
+{
     const double am = fabs(M);
-    if (!(am < 1.0e15)) return fmod_library(M, y);  // huge / inf / NaN: library path
-    const double magic = 6755399441055744.0;
-    double q = fma(am, 1.0 / y, magic - 0.5) - magic;  // rint(am / y - 0.5) ~ floor
-    double r = fma(-q, y, am);
-    if (r < 0.0 || r >= y) {  // quotient off by one (am within rounding of a multiple of y)
-        q += (r < 0.0) ? -1.0 : 1.0;
-        r = fma(-q, y, am);   // exact: 0 <= r < y is representable
-    }
+    const double q = fma(am, kMisc[1], kMisc[2]) - kMisc[3];  // rint(am / y - 0.5) ~ floor
+    double r = fma(-q, kMisc[0], am);
+    if (!(r >= 0.0 && r < kMisc[0])) r = fmod_twopi_fix(q, r, am);
     return copysign(r, M);
 }
 
@@ -486,7 +494,7 @@ __device__ __forceinline__ double fmod_twopi(double M)
 // sequence on rP = RN(1/P).  tsec = t * 86400 exactly as the reference forms it.
 __device__ __forceinline__ double mean_anomaly(double tsec, double T0s, double Ps, double rPs)
 {
-    const double x = __dmul_rn(kTwoPi, __dsub_rn(tsec, T0s));
+    const double x = __dmul_rn(kMisc[0], __dsub_rn(tsec, T0s));
     const double q0 = __dmul_rn(x, rPs);
     return fmod_twopi(fma(fma(-Ps, q0, x), rPs, q0));
 }
@@ -529,43 +537,40 @@ static __device__ __noinline__ void kepler_point_careful(double m, double e, dou
 // 0.85; the un-converged tail only starts between 0.85 and 0.90).  The converged root does not
 // depend on the starter, so such chains may start Newton from anything convergent: a cubic
 // Lagrange interpolation in a shared-memory table of E on kTableN+1 uniform nodes of M in
-// [0, pi] (odd / mirror symmetries give the rest).  Interpolation error <= 5e-9 for e <= 0.6 and
+// [0, 2 pi] (the upper half is the mirror image E(2 pi - M) = 2 pi - E(M) of the solved lower
+// half, negative M uses E(-M) = -E(M)).  Interpolation error <= 5e-9 for e <= 0.6 and
 // <= 3.4e-7 at e = 0.8, so the warp-uniform exit of the Newton loop fires after ONE step
 // (two near periastron at the high end) instead of three to four from the reference starter.
-constexpr int kTableN = 512;               // intervals on [0, pi]
+constexpr int kTableN = 1024;              // intervals on [0, 2 pi]  (h = pi / 512)
 constexpr int kTableSize = kTableN + 3;    // nodes -1 .. kTableN+1
+constexpr int kTableSolved = kTableN / 2 + 2;  // entries 0 .. kTableN/2+1 are solved, the rest mirrored
 constexpr double kTableMaxE = 0.8;
 
-// E at table node j (M = (j - 1) pi / kTableN), solved with the reference starter and Newton steps
 __device__ __forceinline__ double kepler_table_node(int j, double e);
 
-// starter from the table: tab[j + 1] = E(j pi / kTableN)
+// starter from the table: tab[j + 1] = E(2 pi j / kTableN), |m| < 2 pi
 __device__ __forceinline__ double kepler_table_guess(const double* __restrict__ tab, double m)
 {
-    const double am = fabs(m);
-    const bool upper = am > kPi;                        // E(2 pi - M) = 2 pi - E(M)
-    const double a2 = upper ? (kTwoPiExact - am) : am;  // in [0, pi]
-    const double x = a2 * ((double)kTableN / kPi);
+    const double x = fabs(m) * kMisc[4];
     int j = __double2int_rd(x);
-    j = min(max(j, 0), kTableN - 1);
-    const double t = x - (double)j;                     // in [0, 1]
+    j = min(j, kTableN - 1);
+    const double t = x - (double)j;  // in [0, 1]
     const double a = t + 1.0, b = t - 1.0, c = t - 2.0;
     const double tb = t * b, at = a * t;
-    const double w0 = tb * c * (-1.0 / 6.0);
+    const double w0 = tb * c * kMisc[5];
     const double w1 = a * b * c * 0.5;
     const double w2 = at * c * (-0.5);
-    const double w3 = at * b * (1.0 / 6.0);
+    const double w3 = at * b * kMisc[6];
     double E = w0 * tab[j];
     E = fma(w1, tab[j + 1], E);
     E = fma(w2, tab[j + 2], E);
     E = fma(w3, tab[j + 3], E);
-    E = upper ? (kTwoPiExact - E) : E;
     return copysign(E, m);
 }
 
 __device__ __forceinline__ double kepler_table_node(int j, double e)
 {
-    const double m = (double)(j - 1) * (kPi / (double)kTableN);
+    const double m = (double)(j - 1) * (kTwoPi / (double)kTableN);
     double E[1] = {kepler_starter(m, e)}, s[1], c[1];
     int hi = 0;
     for (int k = 0; k < 6; k++) {  // quadratic convergence: a starter only needs ~1e-10

@@ -61,7 +61,8 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out, 
     static double tab[kTableSize];
     const double* ktab = nullptr;
     if (use_table && cc.e >= 0.0 && cc.e <= kTableMaxE) {
-        for (int j = 0; j < kTableSize; j++) tab[j] = kepler_table_node(j, cc.e);
+        for (int j = 0; j < kTableSolved; j++) tab[j] = kepler_table_node(j, cc.e);
+        for (int j = kTableSolved; j < kTableSize; j++) tab[j] = kTwoPi - tab[kTableN + 2 - j];
         ktab = tab;
     }
     long i = 0;
