@@ -70,6 +70,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic)")
     ap.add_argument("--pt-steps", type=int, default=40, help="PT-MCMC iterations timed for the steps/s figure (0 = skip)")
+    ap.add_argument("--no-pt-reference", action="store_true",
+                    help="skip the reference-size PT comparison (50 rungs x 375 real points, GPU vs the reference driver binary)")
     return ap.parse_args()
 
 
@@ -339,6 +341,9 @@ def gpu_arm(args, cfg, rank, local_rank, world):
 
     pt_info = pt_leg(args, ctx, cfg, rank, world, dist, stream) if args.pt_steps > 0 else None
 
+    if pt_info is not None and rank == 0 and world == 1 and not args.no_pt_reference and not args.no_cpu_baseline:
+        pt_info["reference_size"] = pt_reference_size_leg(ctx)
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         pts_per_step = float(n) * N * world
@@ -434,6 +439,48 @@ def pt_leg(args, ctx, cfg, rank, world, dist, stream):
     }
     sp.sampler.close()
     return info
+
+
+def pt_reference_size_leg(ctx):
+    """The reference's own use case: ONE ladder of 50 rungs on a real folded light curve (TIC 102289966,
+    375 points, tests/golden/).  GPU: hb_pt_step.  CPU: the unmodified reference driver binary
+    (oracle/_ref/hb_mcmc_ref, built from mcmc_wrapper2.c with only its /scratch prefix and thread count
+    patched) for 2000 iterations on the host cores -- it evaluates 2 likelihoods per rung per step."""
+    import re
+    import shutil
+    import numpy as np
+    from hb_mcmc_b200.pt import PTSampler
+    gold = os.path.join(ROOT, "tests", "golden")
+    with open(os.path.join(gold, "lc_102289966_new.txt")) as f:
+        n = int(f.readline())
+        d = np.loadtxt(f)
+    logp = 0.7960497
+    ctx.set_data(d[:, 0], d[:, 1], d[:, 2])
+    ctx.set_mags([1000, 1, 1, 1, 1], [1e15] * 4, 1, 0)
+    s = PTSampler(ctx, 50, 1, logp, seed=3)
+    s.init_random()
+    s.step(200)
+    ctx.sync()
+    t0 = time.perf_counter()
+    iters = 3000
+    s.step(iters)
+    ctx.sync()
+    gpu_rate = iters / (time.perf_counter() - t0)
+    s.close()
+    out = {"n_temps": 50, "n_ens": 1, "n_points": n, "gpu_steps_per_sec": gpu_rate, "gpu_iterations": iters}
+    exe = os.path.join(ROOT, "oracle", "_ref", "hb_mcmc_ref")
+    scr = os.path.join(ROOT, "oracle", "_ref", "scratch")
+    if os.path.exists(exe) and os.path.isdir(scr):
+        shutil.copy(os.path.join(gold, "lc_102289966_new.txt"),
+                    os.path.join(scr, "data", "lightcurves", "folded_lightcurves", "102289966_new.txt"))
+        ref_iters = 1500
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, str(ref_iters), "102289966", repr(logp), "9"], capture_output=True, text=True, cwd=scr)
+        dt = time.perf_counter() - t0
+        if r.returncode == 0 and re.search(r"Begining main mcmc loop", r.stdout):
+            out.update({"cpu_steps_per_sec": ref_iters / dt, "cpu_iterations": ref_iters, "cpu_kind": "reference",
+                        "cpu_threads": 8, "cpu_note": "unmodified mcmc_wrapper2.c driver, 2 likelihood evaluations per rung per step"})
+    return out
 
 
 def cpu_baseline_leg(cfg, t, flux, err, P, logL_gpu):
