@@ -28,59 +28,129 @@ __global__ void k_pt_init_random(const PtConfig* __restrict__ cfgp, double* __re
     xw[6] = fmod(xw[6], cfg.lc_period);
 }
 
-__global__ void k_pt_propose(const PtConfig* __restrict__ cfgp, unsigned iter, const double* __restrict__ x,
-                             const int* __restrict__ index, const double* __restrict__ history, double* __restrict__ y,
-                             double* __restrict__ logPy, int* __restrict__ jump, int W)
+// ---- warp-per-walker step kernels --------------------------------------------------------
+// At the reference's own size (50 rungs, a few hundred samples) the step is latency-bound, so the
+// per-walker work is spread over a warp: lane n owns parameter n (21 of 32 lanes), every lane
+// evaluates its own Philox draws by index (pt_draw) and its own bound / prior term; sums that the
+// sequential formulation takes in parameter order are taken in that order by lane 0, so the values
+// are those of pt_propose / pt_accept in hb_pt.cuh bit for bit.
+__device__ __forceinline__ double warp_ordered_sum(double term, int count)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;  // global rung id = ens * T + j
+    double acc = 0.;
+    for (int n = 0; n < count; n++) acc += __shfl_sync(0xffffffffu, term, n);
+    return acc;  // identical on every lane
+}
+
+__global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__ cfgp, unsigned iter,
+                                                    const double* __restrict__ x, const int* __restrict__ index,
+                                                    const double* __restrict__ history, double* __restrict__ y,
+                                                    double* __restrict__ logPy, int* __restrict__ jump, int W)
+{
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global rung id = ens * T + j
+    const int lane = threadIdx.x & 31;
     if (r >= W) return;
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
     const int c = ens * T + index[r];
-    double xl[kPtNpars], yl[kPtNpars], lp;
-    for (int i = 0; i < kPtNpars; i++) xl[i] = x[(size_t)c * kPtNpars + i];
-    const int jt = pt_propose(cfg, (uint32_t)r, iter, cfg.temp[j], xl, history + (size_t)r * cfg.npast * kPtNpars, yl, &lp);
-    for (int i = 0; i < kPtNpars; i++) y[(size_t)c * kPtNpars + i] = yl[i];
-    logPy[c] = lp;
-    jump[c] = jt;
+    const int n = lane < kPtNpars ? lane : kPtNpars - 1;  // idle lanes shadow the last parameter
+    const unsigned long long seed = cfg.seed;
+    const uint32_t id = (uint32_t)r;
+    const double temp = cfg.temp[j];
+    const double xn = x[(size_t)c * kPtNpars + n];
+    const double* hist = history + (size_t)r * cfg.npast * kPtNpars;
+
+    const double alpha = pt_draw(seed, id, iter, 0u, 0u);
+    const double jscale = pow(10., -6. + 6. * alpha);
+    const bool de = (pt_draw(seed, id, iter, 0u, 1u) < 0.5) && ((long long)iter > (long long)cfg.npast);
+    const double sqtemp = sqrt(temp);
+    double yn;
+    int jump_type = 1;
+    if (!de) {
+        yn = xn + pt_normal(seed, id, iter, 0u, 2u, n) * cfg.sigma[n] * sqtemp * jscale;
+    } else {
+        uint32_t d = 2u;
+        int a = 0, b;
+        if (!cfg.quirks) a = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast);
+        do { b = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast); } while (b == a);
+        const bool scaled = pt_draw(seed, id, iter, 0u, d++) < 0.9;
+        const double eps_fac = cfg.quirks ? (pt_gaussian(0., 0., 1.e-4) - 0.5) : 0.0;
+        double dx = hist[b * kPtNpars + n] - hist[a * kPtNpars + n];
+        const double eps = dx * eps_fac;
+        if (scaled) dx *= pt_normal(seed, id, iter, 0u, d, n) * cfg.gamma;
+        dx += eps;
+        yn = xn + dx;
+        const double dx_mag = warp_ordered_sum((xn - yn) * (xn - yn), kPtNpars);
+        jump_type = 2;
+        if (dx_mag < 1e-6) {  // mcmc_wrapper2.c:432-436; the Gaussian draws continue the stream
+            const uint32_t d2 = d + (scaled ? 22u : 0u);
+            yn = xn + pt_normal(seed, id, iter, 0u, d2, n) * cfg.sigma[n] * sqtemp * jscale;
+            jump_type = 1;
+        }
+    }
+    yn = pt_bound_one(yn, n, cfg);
+    // mass ordering (quirk Q5), pinned period, T0 mod P (mcmc_wrapper2.c:470-481)
+    const double y0 = __shfl_sync(0xffffffffu, yn, 0), y1 = __shfl_sync(0xffffffffu, yn, 1);
+    if (y1 > y0) {
+        if (cfg.quirks) { if (lane == 1) yn = y0; }
+        else { if (lane == 0) yn = y1; else if (lane == 1) yn = y0; }
+    }
+    if (lane == 2) yn = cfg.log_lc_period;
+    if (lane == 6) yn = fmod(yn, cfg.lc_period);
+    // Gaussian priors (mcmc_wrapper2.c:703-765), summed in parameter order
+    double mean, sig;
+    pt_prior_of(n, mean, sig);
+    const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(yn, mean, sig)) : 0.0;
+    const double lp = warp_ordered_sum(term, kPtNpars);
+    if (lane < kPtNpars) y[(size_t)c * kPtNpars + lane] = yn;
+    if (lane == 0) {
+        logPy[c] = lp;
+        jump[c] = jump_type;
+    }
 }
 
 // counters per ensemble: 0 acc (chain slot 0 accepted, the reference's `acc`), 1 DE trials of slot 0,
 // 2 DE accepted of slot 0, 3 accepted over all rungs, 4 proposals over all rungs, 5 swaps accepted,
 // 6 swaps proposed, 7 iterations
-__global__ void k_pt_accept(const PtConfig* __restrict__ cfgp, unsigned iter, double* __restrict__ x,
-                            const double* __restrict__ y, double* __restrict__ logLx, const double* __restrict__ logLy,
-                            const double* __restrict__ logPy, const int* __restrict__ jump, const int* __restrict__ index,
-                            double* __restrict__ history, unsigned long long* __restrict__ counters, int W)
+__global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ cfgp, unsigned iter, double* __restrict__ x,
+                                                   const double* __restrict__ y, double* __restrict__ logLx,
+                                                   const double* __restrict__ logLy, const double* __restrict__ logPy,
+                                                   const int* __restrict__ jump, const int* __restrict__ index,
+                                                   double* __restrict__ history, unsigned long long* __restrict__ counters,
+                                                   int W)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= W) return;
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
     const int slot = index[r], c = ens * T + slot;
-    double xl[kPtNpars];
-    for (int i = 0; i < kPtNpars; i++) xl[i] = x[(size_t)c * kPtNpars + i];
-    const double logPx = pt_log_prior(xl, cfg.gauss);
+    const int n = lane < kPtNpars ? lane : kPtNpars - 1;
+    double xn = x[(size_t)c * kPtNpars + n];
+    double mean, sig;
+    pt_prior_of(n, mean, sig);
+    const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(xn, mean, sig)) : 0.0;
+    const double logPx = warp_ordered_sum(term, kPtNpars);
     const bool acc = pt_accept(cfg, (uint32_t)r, iter, cfg.temp[j], logLx[c], logLy[c], logPx, logPy[c]);
-    unsigned long long* cnt = counters + (size_t)ens * 8;
     const int jt = jump[c];
-    if (slot == 0 && jt == 2) atomicAdd(&cnt[1], 1ull);
-    atomicAdd(&cnt[4], 1ull);
     if (acc) {
-        for (int i = 0; i < kPtNpars; i++) {
-            xl[i] = y[(size_t)c * kPtNpars + i];
-            x[(size_t)c * kPtNpars + i] = xl[i];
-        }
-        logLx[c] = logLy[c];
-        atomicAdd(&cnt[3], 1ull);
-        if (slot == 0) {
-            atomicAdd(&cnt[0], 1ull);
-            if (jt == 2) atomicAdd(&cnt[2], 1ull);
+        xn = y[(size_t)c * kPtNpars + n];
+        if (lane < kPtNpars) x[(size_t)c * kPtNpars + lane] = xn;
+    }
+    if (lane == 0) {
+        unsigned long long* cnt = counters + (size_t)ens * 8;
+        if (slot == 0 && jt == 2) atomicAdd(&cnt[1], 1ull);
+        atomicAdd(&cnt[4], 1ull);
+        if (acc) {
+            logLx[c] = logLy[c];
+            atomicAdd(&cnt[3], 1ull);
+            if (slot == 0) {
+                atomicAdd(&cnt[0], 1ull);
+                if (jt == 2) atomicAdd(&cnt[2], 1ull);
+            }
         }
     }
     // history[j][iter % NPAST] = x[chain_id]  (mcmc_wrapper2.c:381,543-546)
-    double* h = history + ((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars;
-    for (int i = 0; i < kPtNpars; i++) h[i] = xl[i];
+    if (lane < kPtNpars) history[((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars + lane] = xn;
 }
 
 // One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
@@ -175,13 +245,15 @@ cudaError_t launch_pt_init_random(const PtConfig* cfg, double* x, int W, cudaStr
 cudaError_t launch_pt_propose(const PtConfig* cfg, unsigned iter, const double* x, const int* index, const double* history,
                               double* y, double* logPy, int* jump, int W, cudaStream_t s)
 {
-    LAUNCH1D(k_pt_propose, W, s, cfg, iter, x, index, history, y, logPy, jump, W);
+    if (W > 0) k_pt_propose<<<(W + 3) / 4, 128, 0, s>>>(cfg, iter, x, index, history, y, logPy, jump, W);
+    return cudaGetLastError();
 }
 cudaError_t launch_pt_accept(const PtConfig* cfg, unsigned iter, double* x, const double* y, double* logLx,
                              const double* logLy, const double* logPy, const int* jump, const int* index, double* history,
                              unsigned long long* counters, int W, cudaStream_t s)
 {
-    LAUNCH1D(k_pt_accept, W, s, cfg, iter, x, y, logLx, logLy, logPy, jump, index, history, counters, W);
+    if (W > 0) k_pt_accept<<<(W + 3) / 4, 128, 0, s>>>(cfg, iter, x, y, logLx, logLy, logPy, jump, index, history, counters, W);
+    return cudaGetLastError();
 }
 cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned iter, int* index, const double* logLx, const double* x,
                            unsigned long long* counters, double* xmap, double* logLmap, int E, cudaStream_t s)

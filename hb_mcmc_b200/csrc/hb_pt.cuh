@@ -1,5 +1,5 @@
-// hb_pt.cuh -- parallel-tempering step of mcmc_wrapper2.c as device code (shared with the host
-// emulation used by the CPU tests).  One thread per rung (walker):
+// hb_pt.cuh -- building blocks of the parallel-tempering step of mcmc_wrapper2.c as device code.
+// The kernels (hb_pt.cu) give every walker a warp, one lane per parameter:
 //   propose  mcmc_wrapper2.c:390-481  jump scale, Gaussian (:1062-1088) or differential-evolution
 //            (:1091-1140) proposal, reflect / periodic bounds (:440-467), mass ordering, pinned
 //            period, T0 mod P, Gaussian priors get_logP (:703-765)
@@ -106,121 +106,70 @@ struct PtRng {
     }
 };
 
+// Draw number d (0-based) of stream (id, iter, stage) without walking the stream: draws 2n and
+// 2n+1 are the two halves of Philox block n.  PtRng::next() returns exactly this sequence, so a
+// warp can evaluate all draws of one walker in parallel.
+HB_HD double pt_draw(unsigned long long seed, uint32_t id, uint32_t iter, uint32_t stage, uint32_t d)
+{
+    U4 c; c.x = id; c.y = iter; c.z = stage; c.w = d >> 1;
+    const U4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t v = (d & 1u) ? (((uint64_t)r.z << 21) | (r.w >> 11)) : (((uint64_t)r.x << 21) | (r.y >> 11));
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// normal number n of a run of Box-Muller pairs whose first uniform is draw d0 (PtRng::normal2 order)
+HB_HD double pt_normal(unsigned long long seed, uint32_t id, uint32_t iter, uint32_t stage, uint32_t d0, int n)
+{
+    const uint32_t d = d0 + 2u * (uint32_t)(n >> 1);
+    const double u1 = pt_draw(seed, id, iter, stage, d), u2 = pt_draw(seed, id, iter, stage, d + 1u);
+    const double r = sqrt(-2.0 * log(u1));
+    const double a = 6.283185307179586 * u2;
+    return (n & 1) ? r * sin(a) : r * cos(a);
+}
+
+// prior mean / sigma of parameter i (mcmc_wrapper2.c:710-757)
+HB_HD void pt_prior_of(int i, double& mean, double& sig)
+{
+    mean = 0.; sig = 1e15;
+    if (i == 7 || i == 8 || i == 17 || i == 18) sig = 1.;
+    else if (i == 9 || i == 11) { mean = 0.16; sig = 0.04; }
+    else if (i == 10 || i == 12) { mean = 0.34; sig = 0.04; }
+    else if (i == 13 || i == 14) { mean = 1.; sig = 0.2; }
+    else if (i == 15 || i == 16) sig = 0.1;
+}
+
 // mcmc_wrapper2.c:1175-1178 with SQRT_2PI of mcmc_wrapper2.h:10
 HB_HD double pt_gaussian(double x, double mean, double sigma)
 {
     return (1 / sigma / 2.5066282746) * exp(-pow((x - mean) / sigma, 2.) / 2.);
 }
 
-// mcmc_wrapper2.c:703-765
-HB_HD double pt_log_prior(const double* p, const int* gauss)
+// Boundary handling of parameter i (mcmc_wrapper2.c:440-467): reflect at sides with mode 1, wrap
+// when both sides have mode 2.  Hot rungs (sqrt(T) up to 4e4) and the "as compiled" DE jumps
+// overshoot the box by thousands of widths; the reference bounces them back one reflection at a
+// time.  Two reflections are a translation by 2 (hi - lo) and one wrap a translation by (hi - lo),
+// so whole multiples are removed in one step and the loops only finish the last bounce.
+HB_HD double pt_bound_one(double y, int i, const PtConfig& cfg)
 {
-    const double mean[kPtNpars] = {0, 0, 0, 0, 0, 0, 0, 0., 0., 0.16, 0.34, 0.16, 0.34, 1., 1., 0., 0., 0., 0., 0, 0};
-    const double sig[kPtNpars] = {1e15, 1e15, 1e15, 1e15, 1e15, 1e15, 1e15, 1., 1., 0.04, 0.04, 0.04, 0.04, 0.2, 0.2,
-                                  0.1, 0.1, 1., 1., 1e15, 1e15};
-    double logP = 0.;
-    for (int i = 0; i < kPtNpars; i++)
-        if (gauss[i] == 1) logP += log(pt_gaussian(p[i], mean[i], sig[i]));
-    return logP;
-}
-
-// 21 Gaussian jumps of mcmc_wrapper2.c:1062-1088
-HB_HD void pt_gaussian_proposal(const double* x, const double* sigma, double scale, double temp, PtRng& g, double* y)
-{
-    const double sqtemp = sqrt(temp);
-    for (int n = 0; n < kPtNpars; n += 2) {
-        double z0, z1;
-        g.normal2(z0, z1);
-        y[n] = x[n] + z0 * sigma[n] * sqtemp * scale;
-        if (n + 1 < kPtNpars) y[n + 1] = x[n + 1] + z1 * sigma[n + 1] * sqtemp * scale;
+    const double lo = cfg.lo[i], hi = cfg.hi[i];
+    const bool rl = cfg.mode_lo[i] == 1, rh = cfg.mode_hi[i] == 1;
+    const bool pl = cfg.mode_lo[i] == 2, ph = cfg.mode_hi[i] == 2;
+    const double period = (rl && rh) ? 2.0 * (hi - lo) : ((pl && ph) ? (hi - lo) : 0.0);
+    if (period > 0.0 && fabs(y) < 1e300) {
+        if (y > hi + period) y -= period * floor((y - hi) / period);
+        else if (y < lo - period) y += period * floor((lo - y) / period);
     }
-}
-
-// Boundary handling + fix-ups of mcmc_wrapper2.c:440-481, in place.
-HB_HD void pt_enforce_bounds(double* y, const PtConfig& cfg)
-{
-    for (int i = 0; i < kPtNpars; i++) {
-        const double lo = cfg.lo[i], hi = cfg.hi[i];
-        const bool rl = cfg.mode_lo[i] == 1, rh = cfg.mode_hi[i] == 1;
-        // Hot rungs (sqrt(T) up to 4e4) and the "as compiled" DE jumps overshoot the box by thousands
-        // of widths; the reference bounces them back one reflection at a time.  Two reflections are a
-        // translation by 2 (hi - lo) and one periodic wrap a translation by (hi - lo), so whole
-        // multiples are removed in one step and the loops below only finish the last bounce.
-        {
-            const double R = hi - lo;
-            const bool per = (cfg.mode_lo[i] == 2) && (cfg.mode_hi[i] == 2);
-            const double period = (rl && rh) ? 2.0 * R : (per ? R : 0.0);
-            if (period > 0.0 && fabs(y[i]) < 1e300) {
-                if (y[i] > hi + period) y[i] -= period * floor((y[i] - hi) / period);
-                else if (y[i] < lo - period) y[i] += period * floor((lo - y[i]) / period);
-            }
-        }
-        int guard = 0;
-        while (((rl && (y[i] < lo)) || (rh && (y[i] > hi))) && guard < 200000) {
-            if (y[i] < lo) y[i] = 2.0 * lo - y[i];
-            else y[i] = 2.0 * hi - y[i];
-            if (!(fabs(y[i]) < 1e300)) { y[i] = NAN; break; }  // +-inf would bounce forever
-            guard++;
-        }
-        if (guard >= 200000) y[i] = NAN;  // the reference would still be looping; the proposal is rejected
-        guard = 0;
-        while ((cfg.mode_lo[i] == 2) && (y[i] < lo) && guard++ < 200000) y[i] = hi + (y[i] - lo);
-        while ((cfg.mode_hi[i] == 2) && (y[i] > hi) && guard++ < 200000) y[i] = lo + (y[i] - hi);
+    int guard = 0;
+    while (((rl && (y < lo)) || (rh && (y > hi))) && guard < 200000) {
+        y = (y < lo) ? 2.0 * lo - y : 2.0 * hi - y;
+        if (!(fabs(y) < 1e300)) return NAN;  // +-inf would bounce forever; NaN rejects the proposal
+        guard++;
     }
-    if (y[1] > y[0]) {
-        if (cfg.quirks) {  // Q5: tmp is never used in the reference
-            y[1] = y[0];
-        } else {
-            const double t = y[1]; y[1] = y[0]; y[0] = t;
-        }
-    }
-    y[2] = cfg.log_lc_period;
-    y[6] = fmod(y[6], cfg.lc_period);
-}
-
-// One proposal for rung `rung_id` (global id = ens * n_temps + j) at iteration `iter`.
-// history = this rung's ring buffer [npast][21].  Returns jump type (1 Gaussian, 2 DE) and fills
-// y[21], *logPy.
-HB_HD int pt_propose(const PtConfig& cfg, uint32_t rung_id, uint32_t iter, double temp, const double* x,
-                     const double* history, double* y, double* logPy)
-{
-    PtRng g;
-    g.init(cfg.seed, rung_id, iter, 0u);
-    const double alpha = g.next();
-    const double jscale = pow(10., -6. + 6. * alpha);
-    int jump_type = 1;
-    const bool de = (g.next() < 0.5) && ((long long)iter > (long long)cfg.npast);
-    if (!de) {
-        pt_gaussian_proposal(x, cfg.sigma, jscale, temp, g, y);
-    } else {
-        int a = 0, b;
-        if (!cfg.quirks) a = (int)(g.next() * cfg.npast);
-        do { b = (int)(g.next() * cfg.npast); } while (b == a);
-        const bool scaled = g.next() < 0.9;
-        // Q6 "as compiled": epsilon = dx (gaussian(0, 0, 1e-4) - 0.5)
-        const double eps_fac = cfg.quirks ? (pt_gaussian(0., 0., 1.e-4) - 0.5) : 0.0;
-        double dx_mag = 0.;
-        for (int n = 0; n < kPtNpars; n += 2) {
-            double z0 = 1. / cfg.gamma, z1 = 1. / cfg.gamma;
-            if (scaled) g.normal2(z0, z1);
-            for (int m = n; m < n + 2 && m < kPtNpars; m++) {
-                double dx = history[b * kPtNpars + m] - history[a * kPtNpars + m];
-                const double eps = dx * eps_fac;
-                if (scaled) dx *= (m == n ? z0 : z1) * cfg.gamma;
-                dx += eps;
-                y[m] = x[m] + dx;
-                dx_mag += (x[m] - y[m]) * (x[m] - y[m]);
-            }
-        }
-        jump_type = 2;
-        if (dx_mag < 1e-6) {  // mcmc_wrapper2.c:432-436
-            pt_gaussian_proposal(x, cfg.sigma, jscale, temp, g, y);
-            jump_type = 1;
-        }
-    }
-    pt_enforce_bounds(y, cfg);
-    *logPy = pt_log_prior(y, cfg.gauss);
-    return jump_type;
+    if (guard >= 200000) return NAN;  // the reference would still be looping
+    guard = 0;
+    while (pl && (y < lo) && guard++ < 200000) y = hi + (y - lo);
+    while (ph && (y > hi) && guard++ < 200000) y = lo + (y - hi);
+    return y;
 }
 
 // Metropolis-Hastings decision of mcmc_wrapper2.c:492-505 (NaN H rejects)
@@ -232,33 +181,6 @@ HB_HD bool pt_accept(const PtConfig& cfg, uint32_t rung_id, uint32_t iter, doubl
     const double alpha = g.next();
     const double H = exp((logLy - logLx) / temp + (logPy - logPx));
     return alpha <= H;
-}
-
-// n_temps swap proposals for one ensemble (mcmc_wrapper2.c:554-563, 796-816).  index[] maps
-// rung -> chain slot within the ensemble; logL is indexed by chain slot.  Returns accepted count.
-HB_HD int pt_swap_ensemble(const PtConfig& cfg, uint32_t ens, uint32_t iter, int* index, const double* logL)
-{
-    PtRng g;
-    g.init(cfg.seed, 0x80000000u | ens, iter, 2u);
-    int accepted = 0;
-    if (cfg.n_temps < 2) return 0;
-    for (int s = 0; s < cfg.n_temps; s++) {
-        int b = (int)(g.next() * (double)(cfg.n_temps - 1));
-        if (b > cfg.n_temps - 2) b = cfg.n_temps - 2;
-        const int a = b + 1;
-        const int olda = index[a], oldb = index[b];
-        const double heat1 = cfg.temp[a], heat2 = cfg.temp[b];
-        const double dlogL = logL[oldb] - logL[olda];
-        const double H = (heat2 - heat1) / (heat2 * heat1);
-        const double alpha = exp(dlogL * H);
-        const double beta = g.next();
-        if (alpha >= beta) {
-            index[a] = oldb;
-            index[b] = olda;
-            accepted++;
-        }
-    }
-    return accepted;
 }
 
 }  // namespace hb
