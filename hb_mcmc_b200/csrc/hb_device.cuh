@@ -183,58 +183,203 @@ __device__ inline double eggleton_dev(double q)  // likelihood3.c:945-948
 // ---------------------------------------------------------------------------
 // chain prologue: everything that does not depend on the time sample
 // ---------------------------------------------------------------------------
-__device__ inline void chain_prologue(const double* __restrict__ p, const MagSetup& ms, ChainConst& cc)
+// Every transcendental value the prologue needs.  The sequential path (one thread per chain) and
+// the warp path (one warp per chain, all lanes calling the same libm routine on different arguments)
+// fill this struct with the same calls on the same arguments; prologue_assemble() is pure arithmetic.
+//
+// Everything that feeds the orbit phase or the eclipse geometry (P, M, R, a) keeps the reference's
+// pow() calls: CUDA's pow and glibc's agree to the last bit almost always, and an ulp there is
+// amplified ~1e5 x by the ill-conditioned asin(h/R) of eclipse_area (measured: worst logL
+// deviation 1.1e-11 with pow, 8.5e-11 with exp10/cbrt).  10^logM is formed once per star, and
+// the flux COEFFICIENTS (smooth, O(1e-3) terms) use cbrt instead of pow(x, k/3).
+struct PrologueT {
+    double M[2], Pd, xb[2], si, ci, sw, cw;  // 10^logM, 10^logP, exp(p15|16), sin/cos inc, sin/cos omega0
+    double sq1me2, sq1me;                    // sqrt(1 - e^2), sqrt(1 - e)
+    double pm[2], cn, envroot[2];            // M^4.22, 1.055^4.22, (pm + cn)^(1/4.22)   (envelope_Radius)
+    double Te[2], R[2], lTe[2];              // Teff, radius [Rsun], log10 Teff
+    double cM[2], cq[2], cP;                 // cbrt(M_k), cbrt(1 + q_k), cbrt(Pd)
+    double a, sep, eq[2], elog[2];           // a [cm] (traj), Roche separation, cbrt(q), cbrt(1/q), log(1 + .)
+    double ex[2][4], lf[4];                  // exp(h nu_j / k T_s), log10 f_nu_j
+};
+
+constexpr double kEnvN = 4.22, kEnvCorner = 1.055;  // envelope_Radius, likelihood3.c:497-501
+__device__ __forceinline__ double env_from_root(double root)
 {
-    const double logM1 = p[0], logM2 = p[1];
-    const double Pd = pow(10., p[2]);
-    const double e = p[3], inc = p[4], omega0 = p[5], T0 = p[6];
+    const double slope = 15.68, floor_ = 0.01, ceil_ = 0.17;
+    return 1 / (1 / ceil_ + 1 / (slope * root - (slope * kEnvCorner - floor_)));
+}
+__device__ __forceinline__ double te_arg(const double* p, int k, double m) { return dev_getT_m(m) + p[17 + k] * 0.0224; }
+__device__ __forceinline__ double r_arg(const double* p, int k, double m, double root)
+{
+    return dev_getR_m(m) + p[7 + k] * env_from_root(root);
+}
+__device__ __forceinline__ double a_arg(const double* M, double Ps)  // likelihood3.c:141-142
+{
+    const double Mtot = M[0] * kMsun + M[1] * kMsun;
+    return kG * Mtot * sq(Ps) / sq(2 * kPi);
+}
+__device__ __forceinline__ double sep_arg(const double* M, double Ps)  // likelihood3.c:962
+{
+    return kG * (M[0] * kMsun + M[1] * kMsun) * sq(Ps) / (4.0 * kPi * kPi);
+}
+// blackbody pieces of calc_mags (likelihood3.c:760-789)
+__device__ __forceinline__ double bb_nu(int j)
+{
+    const double lam[4] = {442, 540, 673, 750};
+    return kC / (lam[j] * 1e-7);
+}
+__device__ __forceinline__ double bb_exp_arg(int j, double T) { return 6.626e-27 * bb_nu(j) / (1.38e-16 * T); }
+__device__ __forceinline__ double bb_flux(int j, double R1, double R2, double e1, double e2, double D, double blending)
+{
+    const double h = 6.626e-27, pc = 3.086e18, nu = bb_nu(j);
+    const double pl = 2. * h * (nu * nu * nu) / sq(kC);
+    R1 *= kRsun;
+    R2 *= kRsun;
+    const double f = kPi * (R1 * R1 * (pl / (e1 - 1.)) + R2 * R2 * (pl / (e2 - 1.))) / (sq(D) * sq(pc));
+    return f / (1 - blending);
+}
+
+// sequential fill: one thread evaluates the ~50 calls one after the other
+__device__ inline void prologue_trans_seq(const double* __restrict__ p, const MagSetup& ms, PrologueT& T)
+{
+    const double e = p[3];
+    T.M[0] = pow(10., p[0]);
+    T.M[1] = pow(10., p[1]);
+    T.Pd = pow(10., p[2]);
+    T.xb[0] = exp(p[15]);
+    T.xb[1] = exp(p[16]);
+    sincos(p[4], &T.si, &T.ci);
+    sincos(p[5], &T.sw, &T.cw);
+    T.sq1me2 = sqrt(1 - sq(e));
+    T.sq1me = sqrt(1 - e);
+    T.cn = pow(kEnvCorner, kEnvN);
+    const double Ps = T.Pd * kSecDay;
+    for (int k = 0; k < 2; k++) {
+        const double q = T.M[1 - k] / T.M[k];
+        T.pm[k] = pow(T.M[k], kEnvN);
+        T.envroot[k] = pow(T.pm[k] + T.cn, 1 / kEnvN);
+        T.Te[k] = pow(10., te_arg(p, k, T.M[k]));
+        T.R[k] = pow(10., r_arg(p, k, T.M[k], T.envroot[k]));
+        T.lTe[k] = log10(T.Te[k]);
+        T.cM[k] = cbrt(T.M[k]);
+        T.cq[k] = cbrt(1 + q);
+        for (int j = 0; j < 4; j++) T.ex[k][j] = exp(bb_exp_arg(j, T.Te[k]));
+    }
+    T.cP = cbrt(T.Pd);
+    T.a = pow(a_arg(T.M, Ps), 1. / 3.);
+    T.sep = cbrt(sep_arg(T.M, Ps));
+    const double qr = (T.M[0] * kMsun) / (T.M[1] * kMsun);
+    T.eq[0] = cbrt(qr);
+    T.eq[1] = cbrt(1 / qr);
+    T.elog[0] = log(1 + T.eq[0]);
+    T.elog[1] = log(1 + T.eq[1]);
+    for (int j = 0; j < 4; j++)
+        T.lf[j] = log10(bb_flux(j, T.R[0], T.R[1], T.ex[0][j], T.ex[1][j], ms.mag_data[0], p[19]));
+}
+
+#ifndef HB_HOST_EMUL
+// warp fill: the lanes of one warp call each libm routine ONCE, on different arguments, and
+// exchange the results by shuffle -- five dependent levels instead of ~50 sequential calls.
+__device__ inline void prologue_trans_warp(const double* __restrict__ p, const MagSetup& ms, PrologueT& T, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const double e = p[3];
+    auto bc = [&](double v, int src) { return __shfl_sync(full, v, src); };
+    // level 0: pow lanes 0-3, exp lanes 0-1, sincos lanes 0-1, sqrt lanes 0-1
+    {
+        const double pa = (lane == 3) ? kEnvCorner : 10., pb = (lane < 3) ? p[lane] : ((lane == 3) ? kEnvN : 0.);
+        const double pw = pow(pa, pb);
+        const double ex = exp(p[15 + (lane & 1)]);
+        double sn, cs;
+        sincos(p[4 + (lane & 1)], &sn, &cs);
+        const double sr = sqrt((lane & 1) ? (1 - e) : (1 - sq(e)));
+        T.M[0] = bc(pw, 0); T.M[1] = bc(pw, 1); T.Pd = bc(pw, 2); T.cn = bc(pw, 3);
+        T.xb[0] = bc(ex, 0); T.xb[1] = bc(ex, 1);
+        T.si = bc(sn, 0); T.ci = bc(cs, 0); T.sw = bc(sn, 1); T.cw = bc(cs, 1);
+        T.sq1me2 = bc(sr, 0); T.sq1me = bc(sr, 1);
+    }
+    const double Ps = T.Pd * kSecDay;
+    const double qr = (T.M[0] * kMsun) / (T.M[1] * kMsun);
+    // level 1: pow lanes 0-1 (M^4.22), 2-3 (Teff), 4 (a); cbrt lanes 0-1 (M), 2-3 (1+q), 4 (Pd), 5 (sep), 6-7 (q, 1/q)
+    {
+        const int k = lane & 1;
+        double pa = 1., pb = 1.;
+        if (lane < 2) { pa = T.M[k]; pb = kEnvN; }
+        else if (lane < 4) { pa = 10.; pb = te_arg(p, k, T.M[k]); }
+        else if (lane == 4) { pa = a_arg(T.M, Ps); pb = 1. / 3.; }
+        const double pw = pow(pa, pb);
+        double ca = 1.;
+        if (lane < 2) ca = T.M[k];
+        else if (lane < 4) ca = 1 + T.M[1 - k] / T.M[k];
+        else if (lane == 4) ca = T.Pd;
+        else if (lane == 5) ca = sep_arg(T.M, Ps);
+        else if (lane == 6) ca = qr;
+        else if (lane == 7) ca = 1 / qr;
+        const double cb = cbrt(ca);
+        T.pm[0] = bc(pw, 0); T.pm[1] = bc(pw, 1); T.Te[0] = bc(pw, 2); T.Te[1] = bc(pw, 3); T.a = bc(pw, 4);
+        T.cM[0] = bc(cb, 0); T.cM[1] = bc(cb, 1); T.cq[0] = bc(cb, 2); T.cq[1] = bc(cb, 3);
+        T.cP = bc(cb, 4); T.sep = bc(cb, 5); T.eq[0] = bc(cb, 6); T.eq[1] = bc(cb, 7);
+    }
+    // level 2: pow lanes 0-1 (envelope root); log10 lanes 0-1 (Teff); exp lanes 0-7 (blackbody); log lanes 0-1
+    {
+        const int k = lane & 1;
+        const double pw = pow(T.pm[k] + T.cn, 1 / kEnvN);
+        const double lg = log10(T.Te[k]);
+        const double ex = exp(bb_exp_arg((lane >> 1) & 3, T.Te[k]));  // lane = 2 j + k
+        const double ln = log(1 + T.eq[k]);
+        T.envroot[0] = bc(pw, 0); T.envroot[1] = bc(pw, 1);
+        T.lTe[0] = bc(lg, 0); T.lTe[1] = bc(lg, 1);
+        for (int j = 0; j < 4; j++) { T.ex[0][j] = bc(ex, 2 * j); T.ex[1][j] = bc(ex, 2 * j + 1); }
+        T.elog[0] = bc(ln, 0); T.elog[1] = bc(ln, 1);
+    }
+    // level 3: radii
+    {
+        const int k = lane & 1;
+        const double pw = pow(10., r_arg(p, k, T.M[k], T.envroot[k]));
+        T.R[0] = bc(pw, 0); T.R[1] = bc(pw, 1);
+    }
+    // level 4: magnitudes
+    {
+        const int j = lane & 3;
+        const double lg = log10(bb_flux(j, T.R[0], T.R[1], T.ex[0][j], T.ex[1][j], ms.mag_data[0], p[19]));
+        for (int i = 0; i < 4; i++) T.lf[i] = bc(lg, i);
+    }
+}
+#endif
+
+// pure arithmetic: PrologueT -> ChainConst
+__device__ inline void prologue_assemble(const double* __restrict__ p, const MagSetup& ms, const PrologueT& T, ChainConst& cc)
+{
+    const double Pd = T.Pd;
+    const double e = p[3], T0 = p[6];
     const double mu[2] = {p[9], p[11]}, tau[2] = {p[10], p[12]};
     const double aref[2] = {p[13], p[14]};
     const double blending = p[19], ft = p[20];
-
-    // Transcendentals are the latency of this kernel (one thread per chain).  Everything that feeds
-    // the orbit phase or the eclipse geometry (P, M, R, a) keeps the reference's pow() calls: CUDA's
-    // pow and glibc's agree to the last bit almost always, and an ulp there is amplified ~1e5 x by
-    // the ill-conditioned asin(h/R) of eclipse_area (measured: worst logL deviation 1.1e-11 with
-    // pow, 8.5e-11 with exp10/cbrt).  10^logM is formed once per star instead of four times, and
-    // the flux COEFFICIENTS (smooth, O(1e-3) terms) use cbrt instead of pow(x, k/3).
-    const double M[2] = {pow(10., logM1), pow(10., logM2)};
-    // radii / temperatures (likelihood3.c:693-717)
-    const double R[2] = {pow(10., dev_getR_m(M[0]) + p[7] * dev_envelope_radius_m(M[0])),
-                         pow(10., dev_getR_m(M[1]) + p[8] * dev_envelope_radius_m(M[1]))};
-    const double Te[2] = {pow(10., dev_getT_m(M[0]) + p[17] * dev_envelope_temp(logM1)),
-                          pow(10., dev_getT_m(M[1]) + p[18] * dev_envelope_temp(logM2))};
+    const double* M = T.M;
+    const double* R = T.R;
+    const double* Te = T.Te;
     // luminosity fractions (likelihood3.c:612-614)
     const double L1 = sq(R[0]) * sq(sq(Te[0])), L2 = sq(R[1]) * sq(sq(Te[1]));
     const double Nrm[2] = {L1 / (L1 + L2), L2 / (L1 + L2)};
     // beaming alphas (likelihood3.c:617-624)
-    const double ab[2] = {dev_alpha_beam(log10(Te[0])) * exp(p[15]), dev_alpha_beam(log10(Te[1])) * exp(p[16])};
-
-    double si, ci, sw, cw;
-    sincos(inc, &si, &ci);
-    sincos(omega0, &sw, &cw);
+    const double ab[2] = {dev_alpha_beam(T.lTe[0]) * T.xb[0], dev_alpha_beam(T.lTe[1]) * T.xb[1]};
+    const double si = T.si, ci = T.ci;
     const double si2 = si * si, si3 = si2 * si, si4 = si2 * si2;
-    const double ome2 = 1 - sq(e);
 
     cc.e = e;
-    cc.sq1me2 = sqrt(ome2);
+    cc.sq1me2 = T.sq1me2;
     cc.T0s = T0 * kSecDay;
     cc.Ps = Pd * kSecDay;
     cc.rPs = __drcp_rn(cc.Ps);
-    cc.cw = cw;
-    cc.sw = sw;
+    cc.cw = T.cw;
+    cc.sw = T.sw;
     cc.ci = ci;
     cc.si = si;
-    // semi-major axis as traj() forms it (likelihood3.c:141-142)
-    {
-        const double Mtot = M[0] * kMsun + M[1] * kMsun;
-        const double a = pow(kG * Mtot * sq(cc.Ps) / sq(2 * kPi), 1. / 3.);
-        cc.ar = a / kRsun;
-    }
+    cc.ar = T.a / kRsun;  // semi-major axis as traj() forms it (likelihood3.c:141-142)
 
     const double ppm = 1.e-6;
-    const double Pm13 = 1.0 / cbrt(Pd), Pm43 = Pm13 / Pd, Pm83 = Pm43 * Pm43, Pm103 = Pm83 * Pm13 * Pm13;
-    const double Prot = Pd * ((1 - e) * sqrt(1 - e));
+    const double Pm13 = 1.0 / T.cP, Pm43 = Pm13 / Pd, Pm83 = Pm43 * Pm43, Pm103 = Pm83 * Pm13 * Pm13;
+    const double Prot = Pd * ((1 - e) * T.sq1me);
 
     double K0 = 0, K1 = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, c1 = 0, c3 = 0, d0 = 0, d2 = 0, d4 = 0;
 #pragma unroll
@@ -244,7 +389,7 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
         const double sgn = (k == 0) ? 1.0 : -1.0;  // star 2 sees omega0 + pi: odd harmonics flip
         const double N = Nrm[k];
         const double q = Mb / Ma;
-        const double Ma13 = cbrt(Ma), q13 = cbrt(1 + q);                 // Ma^(1/3), (1+q)^(1/3)
+        const double Ma13 = T.cM[k], q13 = T.cq[k];                          // Ma^(1/3), (1+q)^(1/3)
         const double iMa23 = 1.0 / (Ma13 * Ma13), iq23 = 1.0 / (q13 * q13);  // ^(-2/3)
         // beaming, likelihood3.c:224-236 (pow(1+q, 2/3) == 1, quirk Q1)
         const double B = -2830. * ab[k] * q * Ma13 * Pm13 * si / cc.sq1me2 * ppm;
@@ -291,9 +436,9 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     cc.blend = blending;
     cc.ft = ft;
 
-    // Gaia magnitude / colour chi^2 terms (likelihood3.c:834-860)
-    double mags[4];
-    two_bb_mags(R[0], R[1], Te[0], Te[1], ms.mag_data[0], blending, 0, mags);
+    // Gaia magnitude / colour chi^2 terms (likelihood3.c:780-789, 834-860)
+    const double Bm = -2.5 * T.lf[0] - 48.6, Vm = -2.5 * T.lf[1] - 48.6, Gm = -2.5 * T.lf[2] - 48.6, Tm = -2.5 * T.lf[3] - 48.6;
+    const double mags[4] = {Gm, Bm - Vm, Vm - Gm, Gm - Tm};
     double extra = 0.;
     if (ms.use_gmag) {
         double r = (mags[0] - ms.mag_data[1]) / ms.magerr[0];
@@ -307,15 +452,15 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
     }
     cc.chi2_extra = extra;
 
-    // Roche overflow (likelihood3.c:953-974)
+    // Roche overflow (likelihood3.c:945-974)
     int roche;
     {
-        const double M1 = M[0] * kMsun, M2 = M[1] * kMsun;
-        const double q = M1 / M2;
-        const double sep = cbrt(kG * (M1 + M2) * sq(cc.Ps) / (4.0 * kPi * kPi));
-        const double r1 = R[0] * kRsun / (sep * (1 - e));
-        const double r2 = R[1] * kRsun / (sep * (1 - e));
-        roche = ((eggleton_dev(q) < r1) || (eggleton_dev(1 / q) < r2)) ? 1 : 0;
+        const double r1 = R[0] * kRsun / (T.sep * (1 - e));
+        const double r2 = R[1] * kRsun / (T.sep * (1 - e));
+        const double q23a = T.eq[0] * T.eq[0], q23b = T.eq[1] * T.eq[1];
+        const double RL1 = 0.49 * q23a / (0.6 * q23a + T.elog[0]);
+        const double RL2 = 0.49 * q23b / (0.6 * q23b + T.elog[1]);
+        roche = ((RL1 < r1) || (RL2 < r2)) ? 1 : 0;
     }
     // e >= 1 (reachable, quirk Q4) or NaN e: the reference's template is NaN at every sample
     const int nan_model = !(e < 1.0) ? 1 : 0;
@@ -334,6 +479,14 @@ __device__ inline void chain_prologue(const double* __restrict__ p, const MagSet
 
     cc.info[0] = R[0]; cc.info[1] = R[1]; cc.info[2] = Te[0]; cc.info[3] = Te[1];
     cc.info[4] = mags[0]; cc.info[5] = mags[1]; cc.info[6] = mags[2]; cc.info[7] = mags[3];
+}
+
+// one thread per chain (host emulation, small helpers)
+__device__ inline void chain_prologue(const double* __restrict__ p, const MagSetup& ms, ChainConst& cc)
+{
+    PrologueT T;
+    prologue_trans_seq(p, ms, T);
+    prologue_assemble(p, ms, T, cc);
 }
 
 // ---------------------------------------------------------------------------

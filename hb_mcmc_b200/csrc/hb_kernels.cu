@@ -16,13 +16,24 @@
 namespace hb {
 
 // ---------------------------------------------------------------------------
-__global__ void k_prologue(const double* __restrict__ params, int n, MagSetup ms, ChainConst* __restrict__ out)
+// One warp per chain: the lanes share out the ~50 libm calls (prologue_trans_warp), lane 0 assembles
+// and the warp stores the 43 doubles of ChainConst together.
+__global__ void __launch_bounds__(128) k_prologue(const double* __restrict__ params, int n, MagSetup ms,
+                                                  ChainConst* __restrict__ out)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= n) return;
-    ChainConst cc;
-    chain_prologue(params + (size_t)c * NPARS, ms, cc);
-    out[c] = cc;
+    __shared__ ChainConst s_cc[4];
+    ChainConst& cc = s_cc[threadIdx.x >> 5];
+    const double* p = params + (size_t)c * NPARS;
+    PrologueT T;
+    prologue_trans_warp(p, ms, T, lane);
+    if (lane == 0) prologue_assemble(p, ms, T, cc);
+    __syncwarp();
+    const double* src = reinterpret_cast<const double*>(&cc);
+    double* dst = reinterpret_cast<double*>(out + c);
+    for (int i = lane; i < (int)(sizeof(ChainConst) / sizeof(double)); i += 32) dst[i] = src[i];
 }
 
 // ---- staging of the data stream ---------------------------------------------------------------
@@ -551,7 +562,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_prologue<<<(n + 127) / 128, 128, 0, s>>>(params, n, ms, out);
+    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out);
     return cudaGetLastError();
 }
 
