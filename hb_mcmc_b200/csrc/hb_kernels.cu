@@ -196,7 +196,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         }
 
         // ---- pre-sample: bracket of the median rank + expansion point ----
-        const bool bracketed = N > kThreads;
+        // small light curves fit the shared-memory candidate list whole: no bracket, no pre-sample
+        const bool bracketed = N > kCandA / 2;
         uint64_t* cand = sm.candA;  // first-round survivors
         int cand_cap = kCandA;
         double lo = -INFINITY, hi = INFINITY;
@@ -349,6 +350,19 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 lc_out[(size_t)chain * N + i] = finish_template(dunkey(tmpl[i]), med, blend, ft);
         }
         if (logL != nullptr) {
+            if (!bracketed) {
+                // small light curve: no sample-based pivot exists, so chi^2 is summed directly from the
+                // stored template in the reference's own form (likelihood3.c:681-685, 829-830)
+                S0 = 0.;
+                const double blend = cc.blend;
+                if (flux != nullptr)
+                    for (int i = tid; i < N; i += kThreads) {
+                        const double r = (finish_template(dunkey(tmpl[i]), med, blend, ft) - flux[i]) * w[i];
+                        S0 = fma(r, r, S0);
+                    }
+                S1 = 0.;
+                S2 = 0.;
+            }
             // three block sums in one go
             const int wid = tid >> 5;
 #pragma unroll
@@ -371,7 +385,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                     t2 += sm.red[64 + i];
                 }
                 const double d = -A * (med - u0);
-                const double chi2 = t0 + d * (2.0 * t1 + d * t2);
+                const double chi2 = bracketed ? t0 + d * (2.0 * t1 + d * t2) : t0;
                 logL[chain] = roche ? -0.5 * kBig : -0.5 * (chi2 + cc.chi2_extra);
             }
         }

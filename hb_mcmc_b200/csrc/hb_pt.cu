@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps;
     __shared__ int s_b[kPtMaxTemps];
-    __shared__ double s_beta[kPtMaxTemps];
+    __shared__ double s_beta[kPtMaxTemps];  // log of the acceptance draw
     __shared__ int s_idx[kPtMaxTemps];
     __shared__ double s_logL[kPtMaxTemps];
     for (int s = lane; s < T; s += 32) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
         int b = (int)(u0 * (double)(T - 1));
         if (b > T - 2) b = T - 2;
         s_b[s] = b;
-        s_beta[s] = u1;
+        s_beta[s] = log(u1);  // exp(x) >= beta  <=>  x >= log(beta): the log is taken here, in parallel
         s_idx[s] = index[(size_t)ens * T + s];
         s_logL[s] = logLx[(size_t)ens * T + s];
     }
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
             const int b = s_b[s], a = b + 1;
             const int olda = s_idx[a], oldb = s_idx[b];
             const double heat1 = cfg.temp[a], heat2 = cfg.temp[b];
-            const double alpha = exp((s_logL[oldb] - s_logL[olda]) * ((heat2 - heat1) / (heat2 * heat1)));
-            if (alpha >= s_beta[s]) {
+            const double lalpha = (s_logL[oldb] - s_logL[olda]) * ((heat2 - heat1) / (heat2 * heat1));
+            if (lalpha >= s_beta[s]) {
                 s_idx[a] = oldb;
                 s_idx[b] = olda;
                 nacc++;
