@@ -59,6 +59,10 @@ struct hb_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     bool ev_valid = false;
     bool time_kernels = false;
+
+    // bumped whenever a device pointer or a by-value kernel argument of the step changes
+    // (hb_set_data, hb_set_mags, buffer growth): captured graphs of older generations are stale
+    unsigned long generation = 0;
 };
 
 namespace {
@@ -132,6 +136,7 @@ int ensure_chains(hb_ctx* ctx, long n)
     CK(cudaMalloc((void**)&ctx->d_cc, (size_t)cap * sizeof(ChainConst)));
     CK(cudaMalloc((void**)&ctx->d_logL, (size_t)cap * sizeof(double)));
     ctx->cap_chains = cap;
+    ctx->generation++;
     return HB_OK;
 }
 
@@ -145,6 +150,7 @@ int ensure_scratch(hb_ctx* ctx, long n_points)
     ctx->scratch_stride = 0;
     CK(cudaMalloc((void**)&ctx->d_scratch, (size_t)ctx->grid * 3 * stride * sizeof(uint64_t)));
     ctx->scratch_stride = stride;
+    ctx->generation++;
     return HB_OK;
 }
 
@@ -337,6 +343,7 @@ int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* 
     ctx->N = n;
     if ((rc = ensure_scratch(ctx, n)) != HB_OK) return rc;
     ctx->has_data = true;
+    ctx->generation++;
     return HB_OK;
 }
 
@@ -349,6 +356,7 @@ int hb_set_mags(hb_ctx* ctx, const double* mag_data, const double* magerr, int u
     for (int i = 0; i < 4; i++) ctx->ms.magerr[i] = magerr[i];
     ctx->ms.use_gmag = use_gmag ? 1 : 0;
     ctx->ms.use_color = use_color ? 1 : 0;
+    ctx->generation++;
     return HB_OK;
 }
 
@@ -641,6 +649,11 @@ struct hb_pt {
     double *history = nullptr, *xmap = nullptr, *logLmap = nullptr, *tmp = nullptr;
     int *index = nullptr, *jump = nullptr;
     unsigned long long* counters = nullptr;
+    unsigned* d_iter = nullptr;  // [0] iteration, [1] arrival ticket of k_pt_swap
+    // one iteration captured as a CUDA graph (the step is latency-bound at the reference's sizes)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long graph_generation = 0;
 };
 
 namespace {
@@ -721,7 +734,8 @@ int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc
               cudaMalloc((void**)&pt->logLmap, (size_t)n_ens * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void**)&pt->index, (size_t)W * sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&pt->jump, (size_t)W * sizeof(int)) == cudaSuccess &&
-              cudaMalloc((void**)&pt->counters, (size_t)n_ens * 8 * sizeof(unsigned long long)) == cudaSuccess;
+              cudaMalloc((void**)&pt->counters, (size_t)n_ens * 8 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->d_iter, 2 * sizeof(unsigned)) == cudaSuccess;
     if (!ok) {
         fail_cuda(ctx, cudaGetLastError(), "hb_pt_create: cudaMalloc");
         hb_pt_destroy(pt);
@@ -731,6 +745,7 @@ int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc
     CK(cudaMemsetAsync(pt->history, 0, wd * kPtNpars * (size_t)npast, ctx->stream));
     CK(cudaMemsetAsync(pt->counters, 0, (size_t)n_ens * 8 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(pt->xmap, 0, (size_t)n_ens * kPtNpars * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(pt->d_iter, 0, 2 * sizeof(unsigned), ctx->stream));
     std::vector<int> idx((size_t)W);
     for (int i = 0; i < W; i++) idx[i] = i % n_temps;  // index[i] = i (mcmc_wrapper2.c:333-338)
     CK(cudaMemcpyAsync(pt->index, idx.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -749,7 +764,9 @@ void hb_pt_destroy(hb_pt* pt)
         cudaStreamSynchronize(pt->ctx->stream);
         cudaFree(pt->d_cfg); cudaFree(pt->x); cudaFree(pt->y); cudaFree(pt->logLx); cudaFree(pt->logLy);
         cudaFree(pt->logPy); cudaFree(pt->tmp); cudaFree(pt->history); cudaFree(pt->xmap); cudaFree(pt->logLmap);
-        cudaFree(pt->index); cudaFree(pt->jump); cudaFree(pt->counters);
+        cudaFree(pt->index); cudaFree(pt->jump); cudaFree(pt->counters); cudaFree(pt->d_iter);
+        if (pt->graph_exec) cudaGraphExecDestroy(pt->graph_exec);
+        if (pt->graph) cudaGraphDestroy(pt->graph);
     }
     delete pt;
 }
@@ -763,6 +780,7 @@ int hb_pt_init_random(hb_pt* pt)
     CK(launch_pt_init_random(pt->d_cfg, pt->x, pt->W, ctx->stream));
     ctx->launches += 1;
     pt->iter = 0;
+    CK(cudaMemsetAsync(pt->d_iter, 0, 2 * sizeof(unsigned), ctx->stream));
     return pt_eval_current(pt);
 }
 
@@ -777,6 +795,21 @@ int hb_pt_set_state(hb_pt* pt, const double* x)
     return pt_eval_current(pt);
 }
 
+// enqueue the kernels of ONE iteration on the context's stream
+static int pt_enqueue_step(hb_pt* pt)
+{
+    hb_ctx* ctx = pt->ctx;
+    int rc;
+    CK(launch_pt_propose(pt->d_cfg, pt->d_iter, pt->x, pt->index, pt->history, pt->y, pt->logPy, pt->jump, pt->W, ctx->stream));
+    if ((rc = run_eval(ctx, pt->y, pt->W, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, pt->logLy, nullptr)) != HB_OK) return rc;
+    CK(launch_pt_accept(pt->d_cfg, pt->d_iter, pt->x, pt->y, pt->logLx, pt->logLy, pt->logPy, pt->jump, pt->index, pt->history,
+                        pt->counters, pt->W, ctx->stream));
+    CK(launch_pt_swap(pt->d_cfg, pt->d_iter, pt->index, pt->logLx, pt->x, pt->counters, pt->xmap, pt->logLmap, pt->cfg.n_ens,
+                      ctx->stream));
+    ctx->launches += 3;
+    return HB_OK;
+}
+
 int hb_pt_step(hb_pt* pt, long n_iters)
 {
     if (!pt || n_iters < 0) return HB_ERR_ARG;
@@ -785,15 +818,30 @@ int hb_pt_step(hb_pt* pt, long n_iters)
     DeviceGuard g(ctx->device);
     int rc;
     if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
+    // Several iterations in one call: replay a captured graph of one iteration (6 nodes) instead of
+    // issuing 6 launches per iteration.  The graph is re-captured when the context's buffers or
+    // by-value kernel arguments changed (generation), never while kernel timing is on.
+    const bool use_graph = n_iters >= 4 && !ctx->time_kernels;
+    if (use_graph && (pt->graph_exec == nullptr || pt->graph_generation != ctx->generation)) {
+        if (pt->graph_exec) { cudaGraphExecDestroy(pt->graph_exec); pt->graph_exec = nullptr; }
+        if (pt->graph) { cudaGraphDestroy(pt->graph); pt->graph = nullptr; }
+        const long launches_before = ctx->launches;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = pt_enqueue_step(pt);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &pt->graph);
+        ctx->launches = launches_before;  // capturing launches nothing
+        if (rc != HB_OK) return rc;
+        if (ce != cudaSuccess) return fail_cuda(ctx, ce, "cudaStreamEndCapture");
+        CK(cudaGraphInstantiate(&pt->graph_exec, pt->graph, 0));
+        pt->graph_generation = ctx->generation;
+    }
     for (long k = 0; k < n_iters; k++) {
-        const unsigned it = (unsigned)pt->iter;
-        CK(launch_pt_propose(pt->d_cfg, it, pt->x, pt->index, pt->history, pt->y, pt->logPy, pt->jump, pt->W, ctx->stream));
-        if ((rc = run_eval(ctx, pt->y, pt->W, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, pt->logLy, nullptr)) != HB_OK) return rc;
-        CK(launch_pt_accept(pt->d_cfg, it, pt->x, pt->y, pt->logLx, pt->logLy, pt->logPy, pt->jump, pt->index, pt->history,
-                            pt->counters, pt->W, ctx->stream));
-        CK(launch_pt_swap(pt->d_cfg, it, pt->index, pt->logLx, pt->x, pt->counters, pt->xmap, pt->logLmap, pt->cfg.n_ens,
-                          ctx->stream));
-        ctx->launches += 3;
+        if (use_graph) {
+            CK(cudaGraphLaunch(pt->graph_exec, ctx->stream));
+            ctx->launches += 5;
+        } else if ((rc = pt_enqueue_step(pt)) != HB_OK) {
+            return rc;
+        }
         pt->iter++;
     }
     return HB_OK;

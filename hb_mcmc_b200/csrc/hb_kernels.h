@@ -53,12 +53,12 @@ cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t s)
 // parallel tempering (hb_pt.cu)
 struct PtConfig;
 cudaError_t launch_pt_init_random(const PtConfig* cfg, double* x, int W, cudaStream_t s);
-cudaError_t launch_pt_propose(const PtConfig* cfg, unsigned iter, const double* x, const int* index, const double* history,
+cudaError_t launch_pt_propose(const PtConfig* cfg, const unsigned* iter, const double* x, const int* index, const double* history,
                               double* y, double* logPy, int* jump, int W, cudaStream_t s);
-cudaError_t launch_pt_accept(const PtConfig* cfg, unsigned iter, double* x, const double* y, double* logLx,
+cudaError_t launch_pt_accept(const PtConfig* cfg, const unsigned* iter, double* x, const double* y, double* logLx,
                              const double* logLy, const double* logPy, const int* jump, const int* index, double* history,
                              unsigned long long* counters, int W, cudaStream_t s);
-cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned iter, int* index, const double* logLx, const double* x,
+cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned* iter, int* index, const double* logLx, const double* x,
                            unsigned long long* counters, double* xmap, double* logLmap, int E, cudaStream_t s);
 cudaError_t launch_pt_gather_cold(const PtConfig* cfg, const int* index, const double* x, const double* logLx,
                                   double* out_x, double* out_logL, int E, cudaStream_t s);

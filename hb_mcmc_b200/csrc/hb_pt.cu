@@ -41,7 +41,7 @@ __device__ __forceinline__ double warp_ordered_sum(double term, int count)
     return acc;  // identical on every lane
 }
 
-__global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__ cfgp, unsigned iter,
+__global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__ cfgp, const unsigned* __restrict__ iter_ptr,
                                                     const double* __restrict__ x, const int* __restrict__ index,
                                                     const double* __restrict__ history, double* __restrict__ y,
                                                     double* __restrict__ logPy, int* __restrict__ jump, int W)
@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global rung id = ens * T + j
     const int lane = threadIdx.x & 31;
     if (r >= W) return;
+    const unsigned iter = *iter_ptr;
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
     const int c = ens * T + index[r];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
 // counters per ensemble: 0 acc (chain slot 0 accepted, the reference's `acc`), 1 DE trials of slot 0,
 // 2 DE accepted of slot 0, 3 accepted over all rungs, 4 proposals over all rungs, 5 swaps accepted,
 // 6 swaps proposed, 7 iterations
-__global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ cfgp, unsigned iter, double* __restrict__ x,
+__global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ cfgp, const unsigned* __restrict__ iter_ptr, double* __restrict__ x,
                                                    const double* __restrict__ y, double* __restrict__ logLx,
                                                    const double* __restrict__ logLy, const double* __restrict__ logPy,
                                                    const int* __restrict__ jump, const int* __restrict__ index,
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ 
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= W) return;
+    const unsigned iter = *iter_ptr;
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
     const int slot = index[r], c = ens * T + slot;
@@ -156,13 +158,14 @@ __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ 
 // One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
 // (swap s consumes exactly block s of the ensemble's Philox stream), lane 0 then applies them in
 // order -- each decision depends on the permutation left by the previous one (mcmc_wrapper2.c:554-563).
-__global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfgp, unsigned iter, int* __restrict__ index,
-                                                const double* __restrict__ logLx, const double* __restrict__ x,
-                                                unsigned long long* __restrict__ counters, double* __restrict__ xmap,
-                                                double* __restrict__ logLmap, int E)
+__global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfgp, unsigned* __restrict__ iter_ptr,
+                                                int* __restrict__ index, const double* __restrict__ logLx,
+                                                const double* __restrict__ x, unsigned long long* __restrict__ counters,
+                                                double* __restrict__ xmap, double* __restrict__ logLmap, int E)
 {
     const int ens = blockIdx.x, lane = threadIdx.x;
     if (ens >= E) return;
+    const unsigned iter = iter_ptr[0];
     const PtConfig& cfg = *cfgp;
     const int T = cfg.n_temps;
     __shared__ int s_b[kPtMaxTemps];
@@ -210,6 +213,15 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
         if (lane < kPtNpars) xmap[(size_t)ens * kPtNpars + lane] = x[(size_t)c0 * kPtNpars + lane];
         if (lane == 0) logLmap[ens] = logLx[c0];
     }
+    // The iteration counter lives on the device so that a captured CUDA graph of one step can be
+    // replayed: the last ensemble to finish advances it (iter_ptr[1] is the arrival ticket).
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&iter_ptr[1], 1u) == (unsigned)E - 1u) {
+            iter_ptr[1] = 0u;
+            iter_ptr[0] = iter + 1u;
+        }
+    }
 }
 
 // gather the cold-rung state of every ensemble: out_x[E][21], out_logL[E]
@@ -242,20 +254,20 @@ __global__ void k_pt_logL_by_rung(const PtConfig* __restrict__ cfgp, const int* 
     } while (0)
 
 cudaError_t launch_pt_init_random(const PtConfig* cfg, double* x, int W, cudaStream_t s) { LAUNCH1D(k_pt_init_random, W, s, cfg, x, W); }
-cudaError_t launch_pt_propose(const PtConfig* cfg, unsigned iter, const double* x, const int* index, const double* history,
+cudaError_t launch_pt_propose(const PtConfig* cfg, const unsigned* iter, const double* x, const int* index, const double* history,
                               double* y, double* logPy, int* jump, int W, cudaStream_t s)
 {
     if (W > 0) k_pt_propose<<<(W + 3) / 4, 128, 0, s>>>(cfg, iter, x, index, history, y, logPy, jump, W);
     return cudaGetLastError();
 }
-cudaError_t launch_pt_accept(const PtConfig* cfg, unsigned iter, double* x, const double* y, double* logLx,
+cudaError_t launch_pt_accept(const PtConfig* cfg, const unsigned* iter, double* x, const double* y, double* logLx,
                              const double* logLy, const double* logPy, const int* jump, const int* index, double* history,
                              unsigned long long* counters, int W, cudaStream_t s)
 {
     if (W > 0) k_pt_accept<<<(W + 3) / 4, 128, 0, s>>>(cfg, iter, x, y, logLx, logLy, logPy, jump, index, history, counters, W);
     return cudaGetLastError();
 }
-cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned iter, int* index, const double* logLx, const double* x,
+cudaError_t launch_pt_swap(const PtConfig* cfg, unsigned* iter, int* index, const double* logLx, const double* x,
                            unsigned long long* counters, double* xmap, double* logLmap, int E, cudaStream_t s)
 {
     if (E > 0) k_pt_swap<<<E, 32, 0, s>>>(cfg, iter, index, logLx, x, counters, xmap, logLmap, E);

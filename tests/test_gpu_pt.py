@@ -117,3 +117,33 @@ def test_sampler_recovers_truth_region(ctx, setup):
     _, lc = s.cold()
     assert np.all(np.isfinite(lc)) and np.median(-2 * lc) < 3 * len(t)
     s.close()
+
+
+def test_graph_replay_equals_single_steps(ctx, setup):
+    """hb_pt_step(n >= 4) replays a captured CUDA graph of one iteration; it must walk exactly the
+    same chain as n single (un-captured) iterations, including after the data set changes."""
+    t, flux, err = setup
+    a = PTSampler(ctx, 7, 4, float(wl.TRUTH_A[2]), seed=99, npast=12)
+    b = PTSampler(ctx, 7, 4, float(wl.TRUTH_A[2]), seed=99, npast=12)
+    a.init_random()
+    b.init_random()
+    for _ in range(40):
+        a.step(1)
+    b.step(40)
+    xa, la, ia = a.state()
+    xb, lb, ib = b.state()
+    assert np.array_equal(xa, xb, equal_nan=True) and np.array_equal(la, lb, equal_nan=True) and np.array_equal(ia, ib)
+    assert a.iteration == b.iteration == 40
+    for k, v in a.counters().items():
+        assert np.array_equal(v, b.counters()[k]), k
+    # new data set: buffers are re-created, the captured graph must not be reused blindly
+    ctx.set_data(t[:300], flux[:300], err[:300])
+    a.set_state(xa)
+    b.set_state(xb)
+    for _ in range(8):
+        a.step(1)
+    b.step(8)
+    assert np.array_equal(a.state()[0], b.state()[0], equal_nan=True)
+    ctx.set_data(t, flux, err)
+    a.close()
+    b.close()
