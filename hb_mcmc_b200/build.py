@@ -7,6 +7,7 @@ Outputs (git-ignored, shipped to the GPU box by gpurun):
     hb_mcmc_b200/csrc/libhb_b200.so          CUDA kernels + the C ABI of include/hb_b200.h
     hb_mcmc_b200/csrc/libhb_likelihood3.so   the reference's likelihood3.h symbols on top of it
     host/hb_mcmc                              the C driver (mcmc_wrapper2-compatible CLI)
+    host/hb_gaia_mcmc                         the C driver of the Gaia-colour sampler (GAIA_mcmc-compatible CLI)
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ LIB = os.path.join(CSRC, "libhb_b200.so")
 SHIM = os.path.join(CSRC, "libhb_likelihood3.so")
 HOST_DIR = os.path.join(ROOT, "host")
 DRIVER = os.path.join(HOST_DIR, "hb_mcmc")
+GAIA_DRIVER = os.path.join(HOST_DIR, "hb_gaia_mcmc")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -48,7 +50,7 @@ def _glob(d: str, exts: tuple[str, ...]) -> list[str]:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("hb_kernels.cu", "hb_capi.cu", "hb_pt.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("hb_kernels.cu", "hb_capi.cu", "hb_pt.cu", "hb_gaia_pt.cu")]
     srcs = [s for s in srcs if os.path.exists(s)]
     deps = _glob(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "hb_b200.h")]
     if force or _stale(LIB, deps):
@@ -69,14 +71,17 @@ def build_shim(force: bool = False) -> str | None:
 
 
 def build_driver(force: bool = False) -> str | None:
-    src = os.path.join(HOST_DIR, "hb_mcmc.c")
-    if not os.path.exists(src):
-        return None
-    if force or _stale(DRIVER, _glob(HOST_DIR, (".c", ".h")) + [LIB]):
-        cmd = ["gcc", "-O2", "-std=gnu99", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", DRIVER, src, "-L", CSRC,
-               "-lhb_b200", "-Wl,-rpath," + CSRC, "-lm"]
-        subprocess.run(cmd, check=True, cwd=HOST_DIR)
-    return DRIVER
+    built = None
+    for name, target in (("hb_mcmc.c", DRIVER), ("hb_gaia_mcmc.c", GAIA_DRIVER)):
+        src = os.path.join(HOST_DIR, name)
+        if not os.path.exists(src):
+            continue
+        if force or _stale(target, [src, LIB, os.path.join(ROOT, "include", "hb_b200.h")]):
+            cmd = ["gcc", "-O2", "-std=gnu99", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", target, src, "-L", CSRC,
+                   "-lhb_b200", "-Wl,-rpath," + CSRC, "-lm"]
+            subprocess.run(cmd, check=True, cwd=HOST_DIR)
+        built = built or target
+    return built
 
 
 def build_all(force: bool = False, verbose: bool = False) -> None:

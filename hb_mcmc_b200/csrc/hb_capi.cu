@@ -12,6 +12,7 @@
 #include "../../include/hb_b200.h"
 #include "hb_device.cuh"
 #include "hb_kernels.h"
+#include "hb_gaia_pt.cuh"
 #include "hb_pt.cuh"
 
 using namespace hb;
@@ -939,6 +940,308 @@ int hb_pt_cold_logL_dev(hb_pt* pt, double* d_out)
     const int E = pt->cfg.n_ens;
     CK(launch_pt_gather_cold(pt->d_cfg, pt->index, pt->x, pt->logLx, pt->tmp, d_out, E, ctx->stream));
     ctx->launches += 1;
+    return HB_OK;
+}
+
+
+/* ---- Gaia-colour sampler (GAIA_mcmc.c) ------------------------------------------------------ */
+}  // extern "C"
+
+struct hb_gaia_pt {
+    hb_ctx* ctx = nullptr;
+    GaiaPtConfig cfg;
+    GaiaPtConfig* d_cfg = nullptr;
+    GaiaPtArrays a;
+    double* d_obs = nullptr;  // D[E], data[E][4], err[E][4]
+    int W = 0;
+    long iter = 0;
+    bool has_data = false, has_state = false;
+    long rec_cap = 0;  // capacity (records per ensemble) of the device log buffers
+};
+
+namespace {
+
+int gaia_grow_rec(hb_gaia_pt* pt, long need)
+{
+    hb_ctx* ctx = pt->ctx;
+    if (need <= pt->rec_cap) return HB_OK;
+    cudaFree(pt->a.rec_chain);
+    cudaFree(pt->a.rec_logL);
+    pt->a.rec_chain = pt->a.rec_logL = nullptr;
+    pt->rec_cap = 0;
+    const size_t E = (size_t)pt->cfg.n_ens;
+    CK(cudaMalloc((void**)&pt->a.rec_chain, E * (size_t)need * (kGaiaNpars + 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&pt->a.rec_logL, E * (size_t)need * (size_t)pt->cfg.n_temps * sizeof(double)));
+    pt->rec_cap = need;
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_gaia_pt_create(hb_ctx* ctx, hb_gaia_pt** out, int n_temps, int n_ens, unsigned long long seed, double dtemp,
+                      int npast)
+{
+    if (!ctx || !out) return HB_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n_temps < 1 || n_temps > kGaiaMaxTemps || n_ens < 1 || npast < 2 || !(dtemp > 1.0))
+        return fail_arg(ctx, "hb_gaia_pt_create: need 1 <= n_temps <= 32, n_ens >= 1, npast >= 2, dtemp > 1");
+    DeviceGuard g(ctx->device);
+    hb_gaia_pt* pt = new hb_gaia_pt();
+    pt->ctx = ctx;
+    std::memset(&pt->a, 0, sizeof(pt->a));
+    GaiaPtConfig& c = pt->cfg;
+    std::memset(&c, 0, sizeof(c));
+    c.n_temps = n_temps; c.n_ens = n_ens; c.npast = npast; c.seed = seed;
+    c.gamma = 2.388 / sqrt(2. * kGaiaNpars);
+    c.temp[0] = 1.0;
+    for (int i = 1; i < n_temps; i++) c.temp[i] = c.temp[i - 1] * dtemp;
+    // set_limits (GAIA_mcmc.c:346-390) and init_proposals (:449-458).  The reference sets sigma[0]
+    // and sigma[1] only; sigma[2..5] are read from a fresh malloc block, i.e. 0 in practice: the shape
+    // parameters move through DE jumps alone.  hb_gaia_pt_set_sigma overrides.
+    for (int i = 0; i < kGaiaNpars; i++) {
+        c.lo[i] = (i < 2) ? -1.5 : -3.;
+        c.hi[i] = (i < 2) ? 2.0 : 3.;
+        c.mode_lo[i] = c.mode_hi[i] = 1;
+        c.gauss[i] = (i < 2) ? 0 : 1;
+        c.sigma[i] = (i < 2) ? 1.e-2 : 0.;
+    }
+    const int W = pt->W = n_temps * n_ens;
+    const size_t wd = (size_t)W * sizeof(double), E = (size_t)n_ens;
+    GaiaPtArrays& a = pt->a;
+    bool ok = cudaMalloc((void**)&pt->d_cfg, sizeof(GaiaPtConfig)) == cudaSuccess &&
+              cudaMalloc((void**)&a.x, wd * kGaiaNpars) == cudaSuccess && cudaMalloc((void**)&a.logL, wd) == cudaSuccess &&
+              cudaMalloc((void**)&a.index, (size_t)W * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&a.history, wd * kGaiaNpars * (size_t)npast) == cudaSuccess &&
+              cudaMalloc((void**)&a.xmap, E * kGaiaNpars * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&a.logLmap, E * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&a.counters, E * 8 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->d_obs, E * 9 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&a.last_y, wd * kGaiaNpars) == cudaSuccess && cudaMalloc((void**)&a.last_logLy, wd) == cudaSuccess &&
+              cudaMalloc((void**)&a.last_logPy, wd) == cudaSuccess && cudaMalloc((void**)&a.last_jump, (size_t)W * sizeof(int)) == cudaSuccess;
+    if (!ok) {
+        fail_cuda(ctx, cudaGetLastError(), "hb_gaia_pt_create: cudaMalloc");
+        hb_gaia_pt_destroy(pt);
+        return HB_ERR_CUDA;
+    }
+    a.D = pt->d_obs;
+    a.data = pt->d_obs + E;
+    a.err = pt->d_obs + 5 * E;
+    CK(cudaMemcpyAsync(pt->d_cfg, &c, sizeof(c), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(a.history, 0, wd * kGaiaNpars * (size_t)npast, ctx->stream));
+    CK(cudaMemsetAsync(a.counters, 0, E * 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(a.last_y, 0, wd * kGaiaNpars, ctx->stream));
+    CK(cudaMemsetAsync(a.last_logLy, 0, wd, ctx->stream));
+    CK(cudaMemsetAsync(a.last_logPy, 0, wd, ctx->stream));
+    CK(cudaMemsetAsync(a.last_jump, 0, (size_t)W * sizeof(int), ctx->stream));
+    std::vector<int> idx((size_t)W);
+    for (int i = 0; i < W; i++) idx[i] = i % n_temps;  // index[i] = i (GAIA_mcmc.c:478-484)
+    CK(cudaMemcpyAsync(a.index, idx.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = pt;
+    return HB_OK;
+}
+
+void hb_gaia_pt_destroy(hb_gaia_pt* pt)
+{
+    if (!pt) return;
+    {
+        DeviceGuard g(pt->ctx->device);
+        cudaStreamSynchronize(pt->ctx->stream);
+        GaiaPtArrays& a = pt->a;
+        cudaFree(pt->d_cfg); cudaFree(a.x); cudaFree(a.logL); cudaFree(a.index); cudaFree(a.history); cudaFree(a.xmap);
+        cudaFree(a.logLmap); cudaFree(a.counters); cudaFree(pt->d_obs); cudaFree(a.last_y); cudaFree(a.last_logLy);
+        cudaFree(a.last_logPy); cudaFree(a.last_jump); cudaFree(a.rec_chain); cudaFree(a.rec_logL);
+    }
+    delete pt;
+}
+
+int hb_gaia_pt_set_data(hb_gaia_pt* pt, const double* D, const double* data, const double* err)
+{
+    if (!pt || !D || !data || !err) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    const size_t E = (size_t)pt->cfg.n_ens;
+    std::vector<double> obs(E * 9);
+    std::memcpy(obs.data(), D, E * sizeof(double));
+    std::memcpy(obs.data() + E, data, 4 * E * sizeof(double));
+    std::memcpy(obs.data() + 5 * E, err, 4 * E * sizeof(double));
+    int rc;
+    if ((rc = upload(ctx, pt->d_obs, obs.data(), E * 9)) != HB_OK) return rc;
+    pt->has_data = true;
+    if (pt->has_state) {  // new data: the cached likelihoods are stale
+        CK(launch_gaia_pt_eval(pt->d_cfg, pt->a, pt->W, ctx->stream));
+        ctx->launches += 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HB_OK;
+}
+
+int hb_gaia_pt_set_sigma(hb_gaia_pt* pt, const double* sigma)
+{
+    if (!pt || !sigma) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < kGaiaNpars; i++) pt->cfg.sigma[i] = sigma[i];
+    CK(cudaMemcpyAsync(pt->d_cfg, &pt->cfg, sizeof(pt->cfg), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+static int gaia_after_state(hb_gaia_pt* pt)
+{
+    hb_ctx* ctx = pt->ctx;
+    std::vector<int> idx((size_t)pt->W);
+    for (int i = 0; i < pt->W; i++) idx[i] = i % pt->cfg.n_temps;
+    CK(cudaMemcpyAsync(pt->a.index, idx.data(), (size_t)pt->W * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_gaia_pt_eval(pt->d_cfg, pt->a, pt->W, ctx->stream));
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    pt->iter = 0;
+    pt->has_state = true;
+    return HB_OK;
+}
+
+int hb_gaia_pt_init_random(hb_gaia_pt* pt)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!pt->has_data) {
+        ctx->err = "hb_gaia_pt_init_random: hb_gaia_pt_set_data has not been called";
+        return HB_ERR_STATE;
+    }
+    DeviceGuard g(ctx->device);
+    CK(launch_gaia_pt_init(pt->d_cfg, pt->a.x, pt->W, ctx->stream));
+    ctx->launches += 1;
+    return gaia_after_state(pt);
+}
+
+int hb_gaia_pt_set_state(hb_gaia_pt* pt, const double* x)
+{
+    if (!pt || !x) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!pt->has_data) {
+        ctx->err = "hb_gaia_pt_set_state: hb_gaia_pt_set_data has not been called";
+        return HB_ERR_STATE;
+    }
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = upload(ctx, pt->a.x, x, (size_t)pt->W * kGaiaNpars)) != HB_OK) return rc;
+    return gaia_after_state(pt);
+}
+
+long hb_gaia_pt_records(const hb_gaia_pt* pt, long n_iters, int thin)
+{
+    if (!pt || n_iters < 0 || thin <= 0) return 0;
+    const long i0 = pt->iter, i1 = pt->iter + n_iters;  // records at iterations i0 <= it < i1 with it % thin == 0
+    return (i1 + thin - 1) / thin - (i0 + thin - 1) / thin;
+}
+
+int hb_gaia_pt_run(hb_gaia_pt* pt, long n_iters, int thin, double* chain, double* logL_by_rung)
+{
+    if (!pt || n_iters < 0) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!pt->has_state) {
+        ctx->err = "hb_gaia_pt_run: no state (hb_gaia_pt_init_random / hb_gaia_pt_set_state)";
+        return HB_ERR_STATE;
+    }
+    if ((chain || logL_by_rung) && thin <= 0) return fail_arg(ctx, "hb_gaia_pt_run: thin must be positive when a log is requested");
+    if (pt->iter + n_iters > 0xFFFFFFF0L) return fail_arg(ctx, "hb_gaia_pt_run: iteration counter would exceed 32 bits");
+    DeviceGuard g(ctx->device);
+    const bool want = chain || logL_by_rung;
+    const long nrec = want ? hb_gaia_pt_records(pt, n_iters, thin) : 0;
+    int rc;
+    if (nrec > 0 && (rc = gaia_grow_rec(pt, nrec)) != HB_OK) return rc;
+    CK(launch_gaia_pt_run(pt->d_cfg, pt->a, pt->cfg.n_ens, (unsigned)pt->iter, (unsigned)n_iters, want ? thin : 0,
+                          pt->rec_cap, ctx->stream));
+    if (n_iters > 0) ctx->launches += 1;
+    pt->iter += n_iters;
+    const size_t E = (size_t)pt->cfg.n_ens, T = (size_t)pt->cfg.n_temps;
+    if (nrec > 0) {
+        // device layout [E][rec_cap][..] -> caller layout [E][nrec][..]
+        for (size_t e = 0; e < E; e++) {
+            if (chain) CK(cudaMemcpyAsync(chain + e * nrec * (kGaiaNpars + 1), pt->a.rec_chain + e * pt->rec_cap * (kGaiaNpars + 1),
+                                          (size_t)nrec * (kGaiaNpars + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (logL_by_rung) CK(cudaMemcpyAsync(logL_by_rung + e * nrec * T, pt->a.rec_logL + e * pt->rec_cap * T,
+                                                 (size_t)nrec * T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+long hb_gaia_pt_iteration(const hb_gaia_pt* pt) { return pt ? pt->iter : -1; }
+
+int hb_gaia_pt_get_state(hb_gaia_pt* pt, double* x, double* logL, int* index)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (x && (rc = download(ctx, x, pt->a.x, (size_t)pt->W * kGaiaNpars)) != HB_OK) return rc;
+    if (logL && (rc = download(ctx, logL, pt->a.logL, (size_t)pt->W)) != HB_OK) return rc;
+    if (index) {
+        CK(cudaMemcpyAsync(index, pt->a.index, (size_t)pt->W * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HB_OK;
+}
+
+int hb_gaia_pt_get_proposal(hb_gaia_pt* pt, double* y, double* logLy, double* logPy, int* jump)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (y && (rc = download(ctx, y, pt->a.last_y, (size_t)pt->W * kGaiaNpars)) != HB_OK) return rc;
+    if (logLy && (rc = download(ctx, logLy, pt->a.last_logLy, (size_t)pt->W)) != HB_OK) return rc;
+    if (logPy && (rc = download(ctx, logPy, pt->a.last_logPy, (size_t)pt->W)) != HB_OK) return rc;
+    if (jump) {
+        CK(cudaMemcpyAsync(jump, pt->a.last_jump, (size_t)pt->W * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HB_OK;
+}
+
+int hb_gaia_pt_get_history(hb_gaia_pt* pt, double* history)
+{
+    if (!pt || !history) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    return download(ctx, history, pt->a.history, (size_t)pt->W * (size_t)pt->cfg.npast * kGaiaNpars);
+}
+
+int hb_gaia_pt_get_map(hb_gaia_pt* pt, double* xmap, double* logLmap)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (xmap && (rc = download(ctx, xmap, pt->a.xmap, (size_t)pt->cfg.n_ens * kGaiaNpars)) != HB_OK) return rc;
+    if (logLmap && (rc = download(ctx, logLmap, pt->a.logLmap, (size_t)pt->cfg.n_ens)) != HB_OK) return rc;
+    return HB_OK;
+}
+
+int hb_gaia_pt_get_counters(hb_gaia_pt* pt, unsigned long long* out)
+{
+    if (!pt || !out) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(out, pt->a.counters, (size_t)pt->cfg.n_ens * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return HB_OK;
 }
 

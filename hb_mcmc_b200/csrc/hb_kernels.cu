@@ -521,12 +521,8 @@ __global__ void k_gaia(const double* __restrict__ p6, int n, double D, const dou
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const double* p = p6 + (size_t)c * 6;
-    const double R1 = pow(10., dev_getR(p[0]) + p[2] * dev_envelope_radius(p[0]));
-    const double R2 = pow(10., dev_getR(p[1]) + p[3] * dev_envelope_radius(p[1]));
-    const double T1 = pow(10., dev_getT(p[0]) + p[4] * dev_envelope_temp(p[0]));
-    const double T2 = pow(10., dev_getT(p[1]) + p[5] * dev_envelope_temp(p[1]));
     double m[4];
-    two_bb_mags(R1, R2, T1, T2, D, 0., 1, m);
+    gaia_mags(p, D, m);
     if (mags_out != nullptr)
         for (int i = 0; i < 4; i++) mags_out[(size_t)c * 4 + i] = m[i];
     if (logL != nullptr) {

@@ -32,6 +32,9 @@ ABI_SYMBOLS = (
     "hb_pt_create", "hb_pt_destroy", "hb_pt_init_random", "hb_pt_set_state", "hb_pt_step", "hb_pt_iteration",
     "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
     "hb_pt_get_counters", "hb_pt_device_logL", "hb_pt_cold_logL_dev",
+    "hb_gaia_pt_create", "hb_gaia_pt_destroy", "hb_gaia_pt_set_data", "hb_gaia_pt_set_sigma", "hb_gaia_pt_init_random",
+    "hb_gaia_pt_set_state", "hb_gaia_pt_records", "hb_gaia_pt_run", "hb_gaia_pt_iteration", "hb_gaia_pt_get_state",
+    "hb_gaia_pt_get_proposal", "hb_gaia_pt_get_history", "hb_gaia_pt_get_map", "hb_gaia_pt_get_counters",
 )
 
 _lib = None
@@ -97,6 +100,24 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_pt_device_logL.argtypes = [vp]
     L.hb_pt_device_logL.restype = vp
     L.hb_pt_cold_logL_dev.argtypes = [vp, vp]
+    ip = C.POINTER(i)
+    L.hb_gaia_pt_create.argtypes = [vp, C.POINTER(vp), i, i, ull, d, i]
+    L.hb_gaia_pt_destroy.argtypes = [vp]
+    L.hb_gaia_pt_destroy.restype = None
+    L.hb_gaia_pt_set_data.argtypes = [vp, _dp, _dp, _dp]
+    L.hb_gaia_pt_set_sigma.argtypes = [vp, _dp]
+    L.hb_gaia_pt_init_random.argtypes = [vp]
+    L.hb_gaia_pt_set_state.argtypes = [vp, _dp]
+    L.hb_gaia_pt_records.argtypes = [vp, l, i]
+    L.hb_gaia_pt_records.restype = l
+    L.hb_gaia_pt_run.argtypes = [vp, l, i, _dp, _dp]
+    L.hb_gaia_pt_iteration.argtypes = [vp]
+    L.hb_gaia_pt_iteration.restype = l
+    L.hb_gaia_pt_get_state.argtypes = [vp, _dp, _dp, ip]
+    L.hb_gaia_pt_get_proposal.argtypes = [vp, _dp, _dp, _dp, ip]
+    L.hb_gaia_pt_get_history.argtypes = [vp, _dp]
+    L.hb_gaia_pt_get_map.argtypes = [vp, _dp, _dp]
+    L.hb_gaia_pt_get_counters.argtypes = [vp, C.POINTER(ull)]
     if path == _build.LIB:
         _lib = L
     return L

@@ -126,6 +126,38 @@ void* hb_pt_device_logL(hb_pt* pt);
  * stream: the send buffer of the per-step NCCL all-gather */
 int hb_pt_cold_logL_dev(hb_pt* pt, double* d_out);
 
+/* ---- Gaia-colour sampler ---------------------------------------------------------------- */
+/* The stand-alone sampler of GAIA_mcmc.c:663-780 (run_mcmc) on the device: n_ens independent
+ * ladders (one warp each, one lane per rung; n_temps <= 32; the reference: NCHAINS = 20 rungs with
+ * ratio dtemp = 1.2, NPAST = 100, GAIA_mcmc.c:23-24,476) walk 6 parameters {logM1, logM2, rr1, rr2,
+ * aT1, aT2} against the 4-point likelihood of hb_gaia_batch.  The whole run is ONE kernel launch;
+ * Philox replaces GSL ranlxs1 / rand().  Limits and priors: set_limits (:346-390); proposal sigmas:
+ * init_proposals (:449-458) -- {1e-2, 1e-2, 0, 0, 0, 0}, see hb_gaia_pt_set_sigma. */
+typedef struct hb_gaia_pt hb_gaia_pt;
+int hb_gaia_pt_create(hb_ctx* ctx, hb_gaia_pt** out, int n_temps, int n_ens, unsigned long long seed, double dtemp,
+                      int npast);
+void hb_gaia_pt_destroy(hb_gaia_pt* pt);
+/* per ensemble: distance D[n_ens] (pc), data[n_ens][4] = {G, B-V, V-G, G-T} and err[n_ens][4]
+ * (read_mag_data, GAIA_mcmc.c:314-343) */
+int hb_gaia_pt_set_data(hb_gaia_pt* pt, const double* D, const double* data, const double* err);
+/* the reference leaves sigma[2..5] unset (fresh heap memory, 0 in practice); override here */
+int hb_gaia_pt_set_sigma(hb_gaia_pt* pt, const double* sigma6);
+int hb_gaia_pt_init_random(hb_gaia_pt* pt);                 /* init_chain, :463-473, + first logL */
+int hb_gaia_pt_set_state(hb_gaia_pt* pt, const double* x);  /* x[n_ens*n_temps][6] by chain slot */
+/* number of log records n_iters further iterations produce: iterations it with it % thin == 0 (:760) */
+long hb_gaia_pt_records(const hb_gaia_pt* pt, long n_iters, int thin);
+/* n_iters iterations in one launch.  chain[n_ens][records][7] = {logL, x[6]} of the cold rung (the
+ * chain file, log_data :599-605) and logL_by_rung[n_ens][records][n_temps] (the logL file, :617-622);
+ * either may be NULL (thin is then ignored). */
+int hb_gaia_pt_run(hb_gaia_pt* pt, long n_iters, int thin, double* chain, double* logL_by_rung);
+long hb_gaia_pt_iteration(const hb_gaia_pt* pt);
+int hb_gaia_pt_get_state(hb_gaia_pt* pt, double* x, double* logL, int* index);  /* any may be NULL */
+/* proposals of the LAST iteration by rung: y[n_ens*n_temps][6], logLy, logPy, jump type (1 Gaussian, 2 DE) */
+int hb_gaia_pt_get_proposal(hb_gaia_pt* pt, double* y, double* logLy, double* logPy, int* jump);
+int hb_gaia_pt_get_history(hb_gaia_pt* pt, double* history);  /* [n_ens*n_temps][npast][6] by rung */
+int hb_gaia_pt_get_map(hb_gaia_pt* pt, double* xmap, double* logLmap);  /* [n_ens][6], [n_ens] */
+int hb_gaia_pt_get_counters(hb_gaia_pt* pt, unsigned long long* out);  /* as hb_pt_get_counters */
+
 /* ---- measurement ----------------------------------------------------------------------- */
 /* DFMA throughput of the device in TFLOP/s (2 flop per FMA), the FP64 roofline denominator. */
 int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);

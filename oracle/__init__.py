@@ -327,3 +327,122 @@ class ReferenceSampler:
         gauss = (C.c_int * NPARS)()
         self.lib.set_limits(limited, limits, gauss, lc_period)
         return self.lib.get_logP(_p(_f64(pars).copy()), limited, limits, gauss)
+
+
+GAIA_NPARS = 6
+
+
+def gaia_protos(L):
+    """argtypes of the oracle's Gaia-sampler restatement (hb_oracle.c, GAIA_mcmc.c flavour)."""
+    ip = C.POINTER(C.c_int)
+    L.orc_gaia_gaussian.restype = C.c_double
+    L.orc_gaia_gaussian.argtypes = [C.c_double] * 3
+    L.orc_gaia_get_logP.restype = C.c_double
+    L.orc_gaia_get_logP.argtypes = [_dp, _dp, _dp, ip]
+    L.orc_gaia_set_limits.argtypes = [_dp, _dp, _dp, _dp, ip]
+    L.orc_gaia_enforce_bounds.argtypes = [_dp] * 5
+    L.orc_gaia_propose.restype = C.c_int
+    L.orc_gaia_propose.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
+                                   ip, _dp, _dp, _dp]
+    L.orc_gaia_accept.restype = C.c_int
+    L.orc_gaia_accept.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint] + [C.c_double] * 5
+    L.orc_gaia_swap_ensemble.restype = C.c_int
+    L.orc_gaia_swap_ensemble.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_int, _dp, ip, _dp, ip]
+    L.orc_pt_uniforms.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_uint, C.c_int, _dp]
+    return L
+
+
+def gaia_limits(L):
+    """(lo, hi, mode_lo, mode_hi, gauss) of orc_gaia_set_limits."""
+    lo, hi, ml, mh = (np.empty(GAIA_NPARS) for _ in range(4))
+    g = np.empty(GAIA_NPARS, dtype=np.int32)
+    L.orc_gaia_set_limits(_p(lo), _p(hi), _p(ml), _p(mh), g.ctypes.data_as(C.POINTER(C.c_int)))
+    return lo, hi, ml, mh, g
+
+
+class ReferenceGaia:
+    """The unmodified GAIA_mcmc.c (oracle/_ref/libref_gaia.so, main renamed) linked against
+    oracle/gsl_stub.  `feed` queues the uniforms / normals its next gsl calls will return."""
+
+    NCHAINS, NPAST = 20, 100
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_gaia.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = self.lib = C.CDLL(path)
+        vp = C.c_void_p
+        L.gaussian.restype = C.c_double
+        L.gaussian.argtypes = [C.c_double] * 3
+        L.get_logP.restype = C.c_double
+        L.get_logP.argtypes = [_dp, vp, vp, vp]
+        L.get_mags.argtypes = [_dp, C.c_double, _dp]
+        L.model_likelihood.restype = C.c_double
+        L.model_likelihood.argtypes = [_dp, _dp, _dp, _dp, C.c_double]
+        L.set_limits.argtypes = [vp, vp, vp]
+        L.init_proposals.argtypes = [_dp, vp]
+        L.gsl_rng_alloc.restype = vp
+        L.gsl_rng_alloc.argtypes = [vp]
+        L.gsl_stub_feed.argtypes = [_dp, C.c_int, _dp, C.c_int]
+        L.gsl_stub_feed_left.argtypes = [C.c_int]
+        L.run_chain.argtypes = [vp, C.c_int, vp, _dp, _dp, vp, vp, C.c_int, vp, vp, vp, _dp, _dp, _dp, C.c_double, _dp,
+                                _dp, _dp, vp, vp]
+        L.ptmcmc.argtypes = [vp, _dp, _dp]
+        self.rng = L.gsl_rng_alloc(None)
+        self.limited = (C.c_double * (2 * GAIA_NPARS))()
+        self.limits = (C.c_double * (2 * GAIA_NPARS))()
+        self.gauss = (C.c_int * GAIA_NPARS)()
+        L.set_limits(self.limited, self.limits, self.gauss)
+
+    def set_limits(self):
+        ld = np.array(self.limited).reshape(GAIA_NPARS, 2)
+        lm = np.array(self.limits).reshape(GAIA_NPARS, 2)
+        return lm[:, 0].copy(), lm[:, 1].copy(), ld[:, 0].copy(), ld[:, 1].copy(), np.array(self.gauss, dtype=np.int32)
+
+    def proposal_sigmas(self):
+        """init_proposals writes sigma[0..1] only; the rest is whatever the caller's buffer held."""
+        s = np.full(GAIA_NPARS, np.nan)
+        self.lib.init_proposals(_p(s), None)
+        return s
+
+    def gaussian(self, x, m, s): return self.lib.gaussian(x, m, s)
+
+    def get_logP(self, pars):
+        return self.lib.get_logP(_p(_f64(pars).copy()), self.limited, self.limits, self.gauss)
+
+    def get_mags(self, p6, D):
+        out = np.empty(4)
+        self.lib.get_mags(_p(_f64(p6).copy()), D, _p(out))
+        return out
+
+    def model_likelihood(self, data, err, p6, D):
+        model = np.empty(4)
+        return self.lib.model_likelihood(_p(_f64(data).copy()), _p(_f64(err).copy()), _p(model), _p(_f64(p6).copy()), D)
+
+    def run_chain(self, it, x, sigma, temp, index, history, chain_id, data, err, D, logLx, uniforms, normals):
+        """One call of run_chain (GAIA_mcmc.c:518-590) for rung `chain_id`, with the gsl draws fed.
+        x[NCHAINS][6], history[NCHAINS][NPAST][6], logLx[NCHAINS], index[NCHAINS] are updated in
+        place; returns (y, accepted, DE accepted, draws left over)."""
+        n, T = GAIA_NPARS, x.shape[0]
+        rows = lambda a: (C.c_void_p * a.shape[0])(*[a[i].ctypes.data for i in range(a.shape[0])])
+        xr = rows(x)
+        y = np.zeros((T, n))
+        yr = rows(y)
+        hrows = [rows(history[j]) for j in range(T)]
+        hr = (C.c_void_p * T)(*[C.addressof(h) for h in hrows])
+        detrial = (C.c_int * T)()
+        acc = np.zeros(T)
+        deacc = np.zeros(T)
+        model = np.empty(4)
+        u = _f64(uniforms).copy()
+        z = _f64(normals).copy()
+        self.lib.gsl_stub_feed(_p(u), u.size, _p(z), z.size)
+        self.lib.run_chain(self.rng, int(it), xr, _p(sigma), _p(temp), index.ctypes.data, hr, int(chain_id), detrial,
+                           self.limits, self.limited, _p(data), _p(err), _p(model), float(D), _p(acc), _p(deacc),
+                           _p(logLx), yr, self.gauss)
+        left = (self.lib.gsl_stub_feed_left(0), self.lib.gsl_stub_feed_left(1))
+        self.lib.gsl_stub_feed(None, 0, None, 0)
+        return y[chain_id].copy(), left
+
+    def ptmcmc(self, index, temp, logL):
+        self.lib.ptmcmc(index.ctypes.data, _p(temp), _p(logL))

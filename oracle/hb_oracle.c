@@ -776,3 +776,142 @@ int orc_pt_swap_ensemble(unsigned long long seed, unsigned ens, unsigned iter, i
     }
     return acc;
 }
+
+/* ------------------------------------------------------------------ */
+/* Gaia-colour sampler (GAIA_mcmc.c), SURVEY 8f row 4                  */
+/* ------------------------------------------------------------------ */
+/* 6 parameters {logM1, logM2, rr1, rr2, aT1, aT2}, NCHAINS = 20 rungs with ratio 1.2, NPAST = 100
+ * (GAIA_mcmc.c:24-29,476).  The flavour differs from mcmc_wrapper2.c in several places (SURVEY
+ * quirk Q11), all restated as written:
+ *   - `gaussian` has no 1/2 in the exponent (:168-172);
+ *   - the prior is log10 of that pdf with mean = box centre, sigma = half the box (:175-191) and
+ *     enters the Hastings ratio as pow(10, dlogP) (:569);
+ *   - the boundary conditions are single `if`s, not loops (:546-559);
+ *   - the DE jump draws both history samples (a != b) and scales every COMPONENT by its own normal
+ *     (:1007-1021);
+ *   - the swaps run before the history ring is filled, interleaved rung by rung (:741-748).
+ * GSL's ranlxs1 / libc rand() are replaced by the Philox streams of the device path. */
+#define ORC_GPARS 6
+
+/* GAIA_mcmc.c:168-172 */
+double orc_gaia_gaussian(double x, double mean, double sigma)
+{
+    return (1 / sigma / 2.5066282746) * exp(-pow((x - mean) / sigma, 2.));
+}
+
+/* GAIA_mcmc.c:175-191 */
+double orc_gaia_get_logP(const double *pars, const double *lo, const double *hi, const int *gauss)
+{
+    double logP = 0.;
+    for (int i = 0; i < ORC_GPARS; i++) {
+        if (gauss[i] == 1) {
+            double mean = 0.5 * (lo[i] + hi[i]);
+            double sigma = (hi[i] - lo[i]) / 2.;
+            logP += log10(orc_gaia_gaussian(pars[i], mean, sigma));
+        }
+    }
+    return logP;
+}
+
+/* GAIA_mcmc.c:346-390: all six parameters reflect at both ends; the four shape parameters carry
+ * the Gaussian prior */
+void orc_gaia_set_limits(double *lo, double *hi, double *mode_lo, double *mode_hi, int *gauss)
+{
+    for (int i = 0; i < ORC_GPARS; i++) {
+        mode_lo[i] = 1; mode_hi[i] = 1;
+        lo[i] = (i < 2) ? -1.5 : -3.;
+        hi[i] = (i < 2) ? 2.0 : 3.;
+        gauss[i] = (i < 2) ? 0 : 1;
+    }
+}
+
+/* GAIA_mcmc.c:546-559 */
+void orc_gaia_enforce_bounds(double *y, const double *lo, const double *hi, const double *mode_lo, const double *mode_hi)
+{
+    for (int i = 0; i < ORC_GPARS; i++) {
+        if ((mode_lo[i] == 1) && (y[i] < lo[i])) y[i] = 2.0 * lo[i] - y[i];
+        if ((mode_hi[i] == 1) && (y[i] > hi[i])) y[i] = 2.0 * hi[i] - y[i];
+        if ((mode_lo[i] == 2) && (y[i] < lo[i])) y[i] = hi[i] + (y[i] - lo[i]);
+        if ((mode_hi[i] == 2) && (y[i] > hi[i])) y[i] = lo[i] + (y[i] - hi[i]);
+    }
+}
+
+/* GAIA_mcmc.c:987-1002 (normals consumed in pairs, component order) */
+static void gaia_gaussian_jump(orc_stream *s, const double *x, const double *sigma, double scale, double temp, double *y)
+{
+    double sq = sqrt(temp), z[ORC_GPARS];
+    for (int n = 0; n < ORC_GPARS; n += 2) stream_normal_pair(s, &z[n], &z[n + 1]);
+    for (int n = 0; n < ORC_GPARS; n++) y[n] = x[n] + z[n] * sigma[n] * sq * scale;
+}
+
+/* One proposal of run_chain (GAIA_mcmc.c:525-563) for stream `id` at iteration `iter`; history is
+ * this rung's ring [npast][6].  Returns the jump type (1 Gaussian, 2 DE). */
+int orc_gaia_propose(unsigned long long seed, unsigned id, unsigned iter, double temp, int npast, const double *x,
+                     const double *history, const double *lo, const double *hi, const double *mode_lo,
+                     const double *mode_hi, const int *gauss, const double *sigma, double *y, double *logPy)
+{
+    orc_stream s;
+    stream_open(&s, seed, id, iter, 0u);
+    double alpha = stream_next(&s);
+    double jscale = pow(10., -6. + 6. * alpha);
+    int type = 1;
+    int de = (stream_next(&s) < 0.5) && ((long)iter > (long)npast);
+    if (!de) {
+        gaia_gaussian_jump(&s, x, sigma, jscale, temp, y);
+    } else {
+        const double gamma = 2.388 / sqrt(2. * ORC_GPARS); /* GAIA_mcmc.c:27 */
+        int a = (int)(stream_next(&s) * npast), b = a;
+        while (b == a) b = (int)(stream_next(&s) * npast);
+        double dx[ORC_GPARS], mag = 0.;
+        for (int n = 0; n < ORC_GPARS; n++) dx[n] = history[b * ORC_GPARS + n] - history[a * ORC_GPARS + n];
+        if (stream_next(&s) < 0.9) {
+            double z[ORC_GPARS];
+            for (int n = 0; n < ORC_GPARS; n += 2) stream_normal_pair(&s, &z[n], &z[n + 1]);
+            for (int n = 0; n < ORC_GPARS; n++) dx[n] *= z[n] * gamma;
+        }
+        for (int n = 0; n < ORC_GPARS; n++) {
+            y[n] = x[n] + dx[n];
+            mag += (x[n] - y[n]) * (x[n] - y[n]);
+        }
+        type = 2;
+        if (mag < 1e-6) {
+            gaia_gaussian_jump(&s, x, sigma, jscale, temp, y);
+            type = 1;
+        }
+    }
+    orc_gaia_enforce_bounds(y, lo, hi, mode_lo, mode_hi);
+    *logPy = orc_gaia_get_logP(y, lo, hi, gauss);
+    return type;
+}
+
+/* GAIA_mcmc.c:569-574 with the accept stream (stage 1) */
+int orc_gaia_accept(unsigned long long seed, unsigned id, unsigned iter, double temp, double logLx, double logLy,
+                    double logPx, double logPy)
+{
+    orc_stream s;
+    stream_open(&s, seed, id, iter, 1u);
+    double alpha = stream_next(&s);
+    double H = exp((logLy - logLx) / temp) * pow(10., logPy - logPx);
+    return alpha <= H;
+}
+
+/* The post-step loop of run_mcmc (GAIA_mcmc.c:741-748): for every rung k, one swap proposal
+ * (ptmcmc, :893-938, same rule as orc_pt_swap_pair) and THEN the history fill of rung k from the
+ * slot index[k] holds at that moment; fill_slot[k] reports that slot.  Returns accepted swaps. */
+int orc_gaia_swap_ensemble(unsigned long long seed, unsigned ens, unsigned iter, int n_temps, const double *temp,
+                           int *index, const double *logL, int *fill_slot)
+{
+    orc_stream s;
+    stream_open(&s, seed, 0x80000000u | ens, iter, 2u);
+    int acc = 0;
+    for (int k = 0; k < n_temps; k++) {
+        if (n_temps > 1) {
+            int b = (int)(stream_next(&s) * (double)(n_temps - 1));
+            if (b > n_temps - 2) b = n_temps - 2;
+            double beta = stream_next(&s);
+            acc += orc_pt_swap_pair(index, temp, logL, b, beta);
+        }
+        fill_slot[k] = index[k];
+    }
+    return acc;
+}

@@ -67,6 +67,19 @@ int orc_pt_accept(unsigned long long seed, unsigned id, unsigned iter, double te
                   double logPx, double logPy);
 int orc_pt_swap_ensemble(unsigned long long seed, unsigned ens, unsigned iter, int n_temps, const double *temp,
                          int *index, const double *logL);
+/* Gaia-colour sampler, GAIA_mcmc.c (6 parameters) */
+double orc_gaia_gaussian(double x, double mean, double sigma);
+double orc_gaia_get_logP(const double *pars, const double *lo, const double *hi, const int *gauss);
+void orc_gaia_set_limits(double *lo, double *hi, double *mode_lo, double *mode_hi, int *gauss);
+void orc_gaia_enforce_bounds(double *y, const double *lo, const double *hi, const double *mode_lo, const double *mode_hi);
+int orc_gaia_propose(unsigned long long seed, unsigned id, unsigned iter, double temp, int npast, const double *x,
+                     const double *history, const double *lo, const double *hi, const double *mode_lo,
+                     const double *mode_hi, const int *gauss, const double *sigma, double *y, double *logPy);
+int orc_gaia_accept(unsigned long long seed, unsigned id, unsigned iter, double temp, double logLx, double logLy,
+                    double logPx, double logPy);
+int orc_gaia_swap_ensemble(unsigned long long seed, unsigned ens, unsigned iter, int n_temps, const double *temp,
+                           int *index, const double *logL, int *fill_slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,3 +52,39 @@ def test_driver_cli_and_file_formats(tmp_path, ctx):
     # missing light-curve file: the reference prints and exits 0 (mcmc_wrapper2.c:279-283)
     r = subprocess.run([exe, "10", "NOPE", "0.3", "1"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "Lightcurve datafile not found" in r.stdout
+
+
+def test_gaia_driver_cli_and_file_formats(tmp_path, ctx):
+    """host/hb_gaia_mcmc: `NITER TIC NTHREADS` and the four files of GAIA_mcmc.c (create_log_files
+    :397-426, log_data :595-636) -- the layout oracle/_ref/gaia_mcmc_ref produces."""
+    build.build_lib()
+    build.build_driver()
+    exe = build.GAIA_DRIVER
+    prefix = tmp_path / "data"
+    for d in ("chains", "logL", "subpars", "GAIA_runs", "magnitudes"):
+        (prefix / d).mkdir(parents=True)
+    with open(prefix / "magnitudes/186260283.txt", "w") as f:  # read_mag_data, :314-343
+        f.write("234.296\n7.16094512\t0.0230834782584296\n-0.0066265000000005\t0.0367165032930016\n"
+                "0.0212387299999997\t0.0586013200752551\n-0.0066558899999999\t0.0086725406204692\n")
+    env = dict(os.environ, HB_DATA_PREFIX=str(prefix), HB_GAIA_BLOCK="700", HB_NENS="3")
+    r = subprocess.run([exe, "2005", "186260283", "4"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Opening magnitude file" in r.stdout and "initial chi2" in r.stdout and "Iter: 0 \t Best likelihood" in r.stdout
+    raw = open(prefix / "chains/186260283_GAIA_run.txt").read().splitlines()
+    assert len(raw) == 201 and all(ln.endswith("\t") and len(ln.split("\t")) == 8 for ln in raw)  # its 0,10,...,2000
+    chain = np.loadtxt(prefix / "chains/186260283_GAIA_run.txt", ndmin=2)
+    rung = np.loadtxt(prefix / "logL/186260283_GAIA_run.txt", ndmin=2)
+    assert chain.shape == (201, 7) and rung.shape == (201, 20)
+    assert np.allclose(chain[:, 0], rung[:, 0], rtol=1e-9)
+    assert np.all(chain[:, 1:3] >= -1.5) and np.all(chain[:, 1:3] <= 2.0) and np.all(np.abs(chain[:, 3:]) <= 3.0)
+    sub = np.loadtxt(prefix / "subpars/186260283_GAIA_run.txt")
+    mags = np.loadtxt(prefix / "GAIA_runs/186260283_GAIA_run.txt")
+    assert sub.shape == (6,) and np.allclose(sub, chain[-1, 1:], rtol=1e-9) and mags.shape == (4,)
+    assert np.allclose(mags, ctx.gaia(sub[None], 234.296)[0], rtol=1e-8)
+    assert chain[-40:, 0].mean() > chain[:5, 0].mean()  # the cold rung climbs from its random start
+    for e in (1, 2):
+        other = np.loadtxt(prefix / f"chains/186260283_GAIA_run.ens{e}.txt", ndmin=2)
+        assert other.shape == (201, 7) and not np.array_equal(other, chain)
+    # missing magnitude file: the reference prints and carries on with garbage; the driver stops
+    r = subprocess.run([exe, "10", "NOPE", "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert "Could not open magnitude file" in r.stdout
