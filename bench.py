@@ -46,7 +46,7 @@ NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
 BYTES_PER_POINT = 8.0       # algorithmic HBM bytes: the template key store (the data stream is shared by all chains)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_chain_eval launch on C2, ncu --set full
 # (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload
-NCU_TRAFFIC_C2_BYTES = 62.551296e6 + 674.616064e6
+NCU_TRAFFIC_C2_BYTES = 62.551040e6 + 673.756416e6
 
 
 def measured_hbm_peak():

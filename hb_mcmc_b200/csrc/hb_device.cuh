@@ -177,10 +177,12 @@ __device__ inline void two_bb_mags(double R1, double R2, double T1, double T2, d
 // GAIA_mcmc.c:198-250 get_mags: {G, B-V, V-G, G-T} of the 6-parameter layout {logM1, logM2, rr1, rr2, aT1, aT2}
 __device__ inline void gaia_mags(const double* p, double D, double m[4])
 {
-    const double R1 = pow(10., dev_getR(p[0]) + p[2] * dev_envelope_radius(p[0]));
-    const double R2 = pow(10., dev_getR(p[1]) + p[3] * dev_envelope_radius(p[1]));
-    const double T1 = pow(10., dev_getT(p[0]) + p[4] * dev_envelope_temp(p[0]));
-    const double T2 = pow(10., dev_getT(p[1]) + p[5] * dev_envelope_temp(p[1]));
+    // _getR, _getT and envelope_Radius each start with the same pow(10., logM): evaluate it once per star
+    const double m1 = pow(10., p[0]), m2 = pow(10., p[1]);
+    const double R1 = pow(10., dev_getR_m(m1) + p[2] * dev_envelope_radius_m(m1));
+    const double R2 = pow(10., dev_getR_m(m2) + p[3] * dev_envelope_radius_m(m2));
+    const double T1 = pow(10., dev_getT_m(m1) + p[4] * dev_envelope_temp(p[0]));
+    const double T2 = pow(10., dev_getT_m(m2) + p[5] * dev_envelope_temp(p[1]));
     two_bb_mags(R1, R2, T1, T2, D, 0., 1, m);
 }
 

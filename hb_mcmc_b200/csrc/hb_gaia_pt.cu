@@ -31,7 +31,8 @@ namespace hb {
 // GAIA_mcmc.c:168-172
 __device__ __forceinline__ double gaia_gaussian(double x, double mean, double sigma)
 {
-    return (1 / sigma / 2.5066282746) * exp(-pow((x - mean) / sigma, 2.));
+    const double r = (x - mean) / sigma;  // pow(r, 2.) of the reference is the correctly rounded r * r
+    return (1 / sigma / 2.5066282746) * exp(-(r * r));
 }
 
 // GAIA_mcmc.c:175-191
@@ -98,6 +99,7 @@ __global__ void k_gaia_pt_eval(const GaiaPtConfig* __restrict__ cfgp, const doub
 struct GaiaWarpState {
     double x[32][kGaiaNpars];  // by chain slot
     double logL[32];           // by chain slot
+    double logP[32];           // log prior by chain slot (the reference recomputes it every step, :563)
     double beta[32];           // log of swap k's acceptance draw
     int idx[32];               // rung -> slot
     int b[32];                 // swap k's lower rung
@@ -129,6 +131,7 @@ k_gaia_pt_run(const GaiaPtConfig* __restrict__ cfgp, GaiaPtArrays a, unsigned it
         for (int i = 0; i < kGaiaNpars; i++) s.x[lane][i] = a.x[((size_t)ens * T + lane) * kGaiaNpars + i];
         s.logL[lane] = a.logL[(size_t)ens * T + lane];
         s.idx[lane] = a.index[(size_t)ens * T + lane];
+        s.logP[lane] = gaia_log_prior(s.x[lane], cfg);
     }
     double* hist = a.history + (size_t)rid * npast * kGaiaNpars;  // this rung's ring
     double logLmap = a.logLmap[ens];
@@ -185,7 +188,7 @@ k_gaia_pt_run(const GaiaPtConfig* __restrict__ cfgp, GaiaPtArrays a, unsigned it
             if ((cfg.mode_hi[i] == 2) && (y[i] > cfg.hi[i])) y[i] = cfg.lo[i] + (y[i] - cfg.hi[i]);
         }
         // ---- priors, likelihood, Metropolis-Hastings (:561-583)
-        const double logPx = gaia_log_prior(x, cfg), logPy = gaia_log_prior(y, cfg);
+        const double logPx = s.logP[slot], logPy = gaia_log_prior(y, cfg);
         const double logLy = gaia_logL(y, D, data, err);
         const double H = exp((logLy - logLx) / temp) * pow(10., logPy - logPx);
         const double u_acc = pt_draw(cfg.seed, rid, it, 1u, 0u);
@@ -194,6 +197,7 @@ k_gaia_pt_run(const GaiaPtConfig* __restrict__ cfgp, GaiaPtArrays a, unsigned it
             if (acc) {
                 for (int i = 0; i < kGaiaNpars; i++) s.x[slot][i] = y[i];
                 s.logL[slot] = logLy;
+                s.logP[slot] = logPy;
                 n_acc++;
                 if (slot == 0) n_acc0++;
                 if (slot == 0 && jt == 2) n_de_acc++;
