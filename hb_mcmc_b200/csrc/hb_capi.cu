@@ -30,7 +30,8 @@ struct hb_ctx {
     long launches = 0;
 
     // observed light curve (device)
-    double *d_t = nullptr, *d_flux = nullptr, *d_w = nullptr;  // d_t: seconds (t * 86400)
+    double* d_t = nullptr;    // seconds (t * 86400)
+    double2* d_fw = nullptr;  // {flux, 1 / max(sigma, 1e-5)} interleaved: one 16-byte load per sample
     long N = 0;
     bool has_data = false;
     MagSetup ms;
@@ -64,6 +65,9 @@ struct hb_ctx {
     // bumped whenever a device pointer or a by-value kernel argument of the step changes
     // (hb_set_data, hb_set_mags, buffer growth): captured graphs of older generations are stale
     unsigned long generation = 0;
+
+    // half-width, in binomial sigmas, of the median bracket taken from the pre-sample (hb_set_bracket_sigma)
+    float bracket_sigma = 2.5f;
 };
 
 namespace {
@@ -175,13 +179,13 @@ int download(hb_ctx* ctx, double* dst, const double* src, size_t n)
     return HB_OK;
 }
 
-int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, const double* d_flux, const double* d_w,
+int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, const double2* d_fw,
              long N, double* d_logL, double* d_lc)
 {
     CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->stream));
     if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
-    CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_flux, d_w, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
-                         d_logL, d_lc, ctx->d_counter, ctx->stream));
+    CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_fw, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
+                         d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->stream));
     if (ctx->time_kernels) {
         CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
         ctx->ev_valid = true;
@@ -266,7 +270,7 @@ void hb_destroy(hb_ctx* ctx)
     {
         DeviceGuard g(ctx->device);
         cudaDeviceSynchronize();
-        cudaFree(ctx->d_t); cudaFree(ctx->d_flux); cudaFree(ctx->d_w);
+        cudaFree(ctx->d_t); cudaFree(ctx->d_fw);
         cudaFree(ctx->d_params); cudaFree(ctx->d_cc); cudaFree(ctx->d_logL);
         cudaFree(ctx->d_scratch); cudaFree(ctx->d_counter); cudaFree(ctx->d_lc);
         cudaFree(ctx->d_times2); cudaFree(ctx->d_small); cudaFree(ctx->d_aux);
@@ -319,28 +323,29 @@ int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* 
     if (n > 0x7fffff00L) return fail_arg(ctx, "hb_set_data: n too large");
     DeviceGuard g(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_t); cudaFree(ctx->d_flux); cudaFree(ctx->d_w);
-    ctx->d_t = ctx->d_flux = ctx->d_w = nullptr;
+    cudaFree(ctx->d_t); cudaFree(ctx->d_fw);
+    ctx->d_t = nullptr;
+    ctx->d_fw = nullptr;
     ctx->has_data = false;
     // padded to whole TMA tiles (k_chain_eval copies full tiles); the padding is finite and never used
     const size_t tile = (size_t)eval_tile();
     const size_t padded = ((size_t)std::max(n, 1L) + tile - 1) / tile * tile;
     size_t alloc = padded * sizeof(double);
     CK(cudaMalloc((void**)&ctx->d_t, alloc));
-    CK(cudaMalloc((void**)&ctx->d_flux, alloc));
-    CK(cudaMalloc((void**)&ctx->d_w, alloc));
+    CK(cudaMalloc((void**)&ctx->d_fw, 2 * alloc));
     CK(cudaMemsetAsync(ctx->d_t, 0, alloc, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_flux, 0, alloc, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_w, 0, alloc, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_fw, 0, 2 * alloc, ctx->stream));  // padding: flux 0, weight 0 (adds nothing to chi^2)
     // weights 1/max(sigma, 1e-5): the clamp of likelihood3.c:824-827 applied once at upload
-    std::vector<double> w((size_t)n);
-    for (long i = 0; i < n; i++) w[i] = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
+    std::vector<double> fw(2 * (size_t)n);
+    for (long i = 0; i < n; i++) {
+        fw[2 * i] = flux[i];
+        fw[2 * i + 1] = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
+    }
     int rc;
     if ((rc = upload(ctx, ctx->d_t, t, (size_t)n)) != HB_OK) return rc;
     CK(launch_to_seconds(ctx->d_t, (int)n, ctx->d_t, ctx->stream));  // d_t holds t * 86400 from here on
     ctx->launches += (n > 0);
-    if ((rc = upload(ctx, ctx->d_flux, flux, (size_t)n)) != HB_OK) return rc;
-    if ((rc = upload(ctx, ctx->d_w, w.data(), (size_t)n)) != HB_OK) return rc;
+    if ((rc = upload(ctx, reinterpret_cast<double*>(ctx->d_fw), fw.data(), 2 * (size_t)n)) != HB_OK) return rc;
     ctx->N = n;
     if ((rc = ensure_scratch(ctx, n)) != HB_OK) return rc;
     ctx->has_data = true;
@@ -374,7 +379,7 @@ int hb_loglikelihood_batch_dev(hb_ctx* ctx, const double* d_params, long n_chain
     DeviceGuard g(ctx->device);
     int rc;
     if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
-    return run_eval(ctx, d_params, n_chains, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, d_logL, nullptr);
+    return run_eval(ctx, d_params, n_chains, ctx->d_t, ctx->d_fw, ctx->N, d_logL, nullptr);
 }
 
 int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, double* logL)
@@ -394,7 +399,7 @@ int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, dou
     CK(grow_pin(ctx, np));
     std::memcpy(ctx->h_pin, params, np * sizeof(double));
     CK(cudaMemcpyAsync(ctx->d_params, ctx->h_pin, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, ctx->d_logL, nullptr)) != HB_OK)
+    if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, ctx->d_fw, ctx->N, ctx->d_logL, nullptr)) != HB_OK)
         return rc;
     // the D2H lands in the head of the pinned buffer; stream order keeps it after the H2D read
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_logL, (size_t)n_chains * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -418,7 +423,7 @@ int hb_light_curve_batch(hb_ctx* ctx, const double* params, long n_chains, doubl
     if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
     CK(grow(ctx->d_lc, ctx->cap_lc, (size_t)n_chains * (size_t)ctx->N));
     if ((rc = upload(ctx, ctx->d_params, params, (size_t)n_chains * NPARS)) != HB_OK) return rc;
-    if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, nullptr, nullptr, ctx->N, nullptr, ctx->d_lc)) != HB_OK) return rc;
+    if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, nullptr, ctx->N, nullptr, ctx->d_lc)) != HB_OK) return rc;
     return download(ctx, templates, ctx->d_lc, (size_t)n_chains * (size_t)ctx->N);
 }
 
@@ -453,7 +458,7 @@ int hb_calc_light_curve(hb_ctx* ctx, const double* times, long nt, const double*
     ctx->launches += 1;
     CK(grow(ctx->d_lc, ctx->cap_lc, (size_t)nt));
     if ((rc = upload(ctx, ctx->d_params, pars, NPARS)) != HB_OK) return rc;
-    if ((rc = run_eval(ctx, ctx->d_params, 1, ctx->d_times2, nullptr, nullptr, nt, nullptr, ctx->d_lc)) != HB_OK) return rc;
+    if ((rc = run_eval(ctx, ctx->d_params, 1, ctx->d_times2, nullptr, nt, nullptr, ctx->d_lc)) != HB_OK) return rc;
     return download(ctx, tmpl, ctx->d_lc, (size_t)nt);
 }
 
@@ -578,6 +583,16 @@ int hb_gaia_batch(hb_ctx* ctx, const double* p6, long n, double D, const double*
     return HB_OK;
 }
 
+int hb_set_bracket_sigma(hb_ctx* ctx, double sigma)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!(sigma >= 0.0) || sigma > 100.0) return fail_arg(ctx, "hb_set_bracket_sigma: need 0 <= sigma <= 100");
+    ctx->bracket_sigma = (float)sigma;
+    ctx->generation++;  // a by-value argument of the captured step changed
+    return HB_OK;
+}
+
 int hb_time_kernels(hb_ctx* ctx, int enable)
 {
     if (!ctx) return HB_ERR_ARG;
@@ -692,7 +707,7 @@ int pt_eval_current(hb_pt* pt)
     hb_ctx* ctx = pt->ctx;
     int rc;
     if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
-    return run_eval(ctx, pt->x, pt->W, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, pt->logLx, nullptr);
+    return run_eval(ctx, pt->x, pt->W, ctx->d_t, ctx->d_fw, ctx->N, pt->logLx, nullptr);
 }
 
 }  // namespace
@@ -802,7 +817,7 @@ static int pt_enqueue_step(hb_pt* pt)
     hb_ctx* ctx = pt->ctx;
     int rc;
     CK(launch_pt_propose(pt->d_cfg, pt->d_iter, pt->x, pt->index, pt->history, pt->y, pt->logPy, pt->jump, pt->W, ctx->stream));
-    if ((rc = run_eval(ctx, pt->y, pt->W, ctx->d_t, ctx->d_flux, ctx->d_w, ctx->N, pt->logLy, nullptr)) != HB_OK) return rc;
+    if ((rc = run_eval(ctx, pt->y, pt->W, ctx->d_t, ctx->d_fw, ctx->N, pt->logLy, nullptr)) != HB_OK) return rc;
     CK(launch_pt_accept(pt->d_cfg, pt->d_iter, pt->x, pt->y, pt->logLx, pt->logLy, pt->logPy, pt->jump, pt->index, pt->history,
                         pt->counters, pt->W, ctx->stream));
     CK(launch_pt_swap(pt->d_cfg, pt->d_iter, pt->index, pt->logLx, pt->x, pt->counters, pt->xmap, pt->logLmap, pt->cfg.n_ens,

@@ -648,7 +648,9 @@ static __device__ __noinline__ double fmod_twopi_fix(double q, double r, double 
 __device__ __forceinline__ double fmod_twopi(double M)
 {
     const double am = fabs(M);
-    const double q = fma(am, kMisc[1], kMisc[2]) - kMisc[3];  // rint(am / y - 0.5) ~ floor
+    // floor(am / y): the magic-number trick with the FMA rounding toward -inf (at 1.5 * 2^52 one ulp is 1).
+    // Adding `magic - 0.5` in round-to-nearest does NOT work: that constant is not representable.
+    const double q = __fma_rd(am, kMisc[1], kMisc[3]) - kMisc[3];
     double r = fma(-q, kMisc[0], am);
     if (!(r >= 0.0 && r < kMisc[0])) r = fmod_twopi_fix(q, r, am);
     return copysign(r, M);

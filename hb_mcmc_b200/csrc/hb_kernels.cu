@@ -9,6 +9,8 @@
 //   k_fp64_peak   DFMA throughput probe (the roofline denominator, measured on the box)
 //
 // Replaces likelihood3.c:809-873 (loglikelihood) and :530-686 (calc_light_curve).
+#include <type_traits>
+
 #include "hb_kernels.h"
 #include "hb_device.cuh"
 #include "hb_select.cuh"
@@ -56,7 +58,8 @@ constexpr int kTile = kPointsPerThread * kEvalThreads;  // samples per loop iter
 [[maybe_unused]] constexpr int kStages = 2;
 
 struct TileStage {
-    double ts[kTile], fl[kTile], wv[kTile];
+    double ts[kTile];
+    double2 fw[kTile];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,8 +133,9 @@ __device__ __forceinline__ int median_rank(int N)
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
 k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
-             const double* __restrict__ flux, const double* __restrict__ w, int N, uint64_t* __restrict__ scratch,
-             size_t scratch_stride, double* __restrict__ logL, double* __restrict__ lc_out, int* __restrict__ counter)
+             const double2* __restrict__ fw, int N, uint64_t* __restrict__ scratch,
+             size_t scratch_stride, double* __restrict__ logL, double* __restrict__ lc_out, int* __restrict__ counter,
+             float bracket_sigma)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -207,7 +211,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
             const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
             int r_lo, r_hi, r_mid;
-            bracket_ranks(kThreads, N, krank, 2.5f, r_lo, r_hi, r_mid);
+            bracket_ranks(kThreads, N, krank, bracket_sigma, r_lo, r_hi, r_mid);
             const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)kThreads);
             if ((int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // large N: survivors go to global scratch
                 cand = gbufB;
@@ -235,20 +239,26 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const double A = cc.ft * (1.0 - cc.blend), ft = cc.ft;
 
         // ---- model pass: kPointsPerThread samples per thread and iteration ----
+        // The template keys go to global scratch only when something will read them back: light-curve
+        // output, the small-N direct chi^2, or the re-run after a missed bracket (below).  The common
+        // logL-only pass keeps everything on chip: no store, no address arithmetic for it.
         int nanflag = 0, c_lt = 0;
         double S0 = 0., S1 = 0., S2 = 0.;
         constexpr int V = kPointsPerThread;
+        auto model_pass = [&](auto store_tag, auto data_tag) {
+        constexpr bool kStore = decltype(store_tag)::value;
+        constexpr bool kData = decltype(data_tag)::value;  // fw != nullptr, known at compile time in the hot variant
+        nanflag = 0;
+        c_lt = 0;
+        S0 = S1 = S2 = 0.;
 #if HB_TMA_STAGING
         // the data arrays are padded to whole tiles by the host side, so every copy is a full tile
         auto issue_tile = [&](int tile, uint32_t g) {
             const int st = g % kStages;
             const size_t off = (size_t)tile * kTile;
-            mbar_expect_tx(&sm.full_bar[st], flux != nullptr ? 3 * tile_bytes : tile_bytes);
+            mbar_expect_tx(&sm.full_bar[st], fw != nullptr ? 3 * tile_bytes : tile_bytes);
             bulk_g2s(sm.stage[st].ts, tsec + off, tile_bytes, &sm.full_bar[st]);
-            if (flux != nullptr) {
-                bulk_g2s(sm.stage[st].fl, flux + off, tile_bytes, &sm.full_bar[st]);
-                bulk_g2s(sm.stage[st].wv, w + off, tile_bytes, &sm.full_bar[st]);
-            }
+            if (fw != nullptr) bulk_g2s(sm.stage[st].fw, fw + off, 2 * tile_bytes, &sm.full_bar[st]);
         };
         if (tid == 0) issue_tile(0, git);  // every stage is free here: the chain-level barriers drained the pipe
         for (int tile = 0; tile < n_tiles; tile++, git++) {
@@ -266,8 +276,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             for (int j = 0; j < V; j++) {
                 idx[j] = base + j * kThreads + tid;
                 ts[j] = sm.stage[st].ts[j * kThreads + tid];
-                fl[j] = sm.stage[st].fl[j * kThreads + tid];
-                wv[j] = sm.stage[st].wv[j * kThreads + tid];
+                fl[j] = sm.stage[st].fw[j * kThreads + tid].x;
+                wv[j] = sm.stage[st].fw[j * kThreads + tid].y;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty_bar[st]);
@@ -287,8 +297,12 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 idx[j] = base + j * kThreads + tid;
                 ts[j] = ts_next[j];
                 if (tile + 1 < n_tiles) ts_next[j] = tsec[idx[j] + kTile];
-                fl[j] = (flux != nullptr) ? flux[idx[j]] : 0.0;
-                wv[j] = (flux != nullptr) ? w[idx[j]] : 0.0;
+                fl[j] = wv[j] = 0.0;
+                if (kData) {  // one 16-byte load: {flux, 1/sigma} are interleaved
+                    const double2 v = fw[idx[j]];
+                    fl[j] = v.x;
+                    wv[j] = v.y;
+                }
             }
 #endif
             raw_flux<V, true>(cc, ktab, ts, u);
@@ -297,9 +311,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 const int i = idx[j];
                 const bool valid = i < N;
                 const double uj = u[j];
-                nanflag |= (uj != uj);
-                if (valid) tmpl[i] = dkey(uj);
-                c_lt += (valid & (uj < lo));
+                // with data, a NaN sample poisons S0 and is detected once after the loop
+                if (!kData) nanflag |= (uj != uj);
+                if (kStore && valid) tmpl[i] = dkey(uj);
+                if (valid & (uj < lo)) c_lt++;
                 const bool inr = valid & (uj >= lo) & (uj <= hi);
                 const unsigned mask = __ballot_sync(0xffffffffu, inr);
                 if (mask) {
@@ -312,7 +327,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                         if (pos < cand_cap) cand[pos] = dkey(uj);
                     }
                 }
-                if (flux != nullptr && valid) {
+                if (kData) {  // padded samples carry weight 0 and a finite model: they add exactly 0
                     const double wi = wv[j];
                     const double a = fma(A, uj - u0, ft - fl[j]);
                     const double r = a * wi;
@@ -322,6 +337,17 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
         }
+        if (kData) nanflag = (S0 != S0);
+        };
+        // two instantiations: the hot logL-only pass, and a general one (template stored) for
+        // light-curve output, small N and the re-run after a missed bracket
+        const bool store_template = (lc_out != nullptr) || !bracketed || (fw == nullptr);
+        auto general_pass = [&]() {
+            if (fw != nullptr) model_pass(std::true_type{}, std::true_type{});
+            else model_pass(std::true_type{}, std::false_type{});
+        };
+        if (store_template) general_pass();
+        else model_pass(std::false_type{}, std::true_type{});
         const int any_nan = __syncthreads_or(nanflag);
         if (any_nan) {
             if (lc_out != nullptr)
@@ -339,8 +365,17 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         uint64_t mkey;
         if (krank >= c_lt && krank < c_lt + c_in && c_in <= cand_cap)
             mkey = block_select_key<kThreads>(cand, c_in, krank - c_lt, sm.ctl, bufs, 4, seed2);
-        else  // the bracket missed (or overflowed): select on the stored template
+        else {
+            // the bracket missed (or overflowed; ~1 % of chains by construction of the 2.5 sigma bracket):
+            // evaluate the chain once more, this time storing the template, and select on that
+            if (!store_template) {
+                if (tid == 0) sm.ctl.cnt = 0;
+                __syncthreads();
+                general_pass();
+                __syncthreads();
+            }
             mkey = block_select_key<kThreads>(tmpl, N, krank, sm.ctl, bufs, 4, seed2);
+        }
         const double med = dunkey(mkey);
 
         // ---- results ----
@@ -355,9 +390,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 // stored template in the reference's own form (likelihood3.c:681-685, 829-830)
                 S0 = 0.;
                 const double blend = cc.blend;
-                if (flux != nullptr)
+                if (fw != nullptr)
                     for (int i = tid; i < N; i += kThreads) {
-                        const double r = (finish_template(dunkey(tmpl[i]), med, blend, ft) - flux[i]) * w[i];
+                        const double2 v = fw[i];
+                        const double r = (finish_template(dunkey(tmpl[i]), med, blend, ft) - v.x) * v.y;
                         S0 = fma(r, r, S0);
                     }
                 S1 = 0.;
@@ -582,16 +618,16 @@ cudaError_t configure_eval()
                                 (int)sizeof(EvalShared));
 }
 
-cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double* flux, const double* w,
+cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
                               int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
-                              int* counter, cudaStream_t s)
+                              int* counter, float bracket_sigma, cudaStream_t s)
 {
     if (n_chains <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     if (grid > n_chains) grid = n_chains;
-    k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, flux, w, N, scratch,
-                                                                               scratch_stride, logL, lc_out, counter);
+    k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, fw, N, scratch,
+                                                                               scratch_stride, logL, lc_out, counter, bracket_sigma);
     return cudaGetLastError();
 }
 

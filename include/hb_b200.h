@@ -161,6 +161,12 @@ int hb_gaia_pt_get_counters(hb_gaia_pt* pt, unsigned long long* out);  /* as hb_
 /* ---- measurement ----------------------------------------------------------------------- */
 /* DFMA throughput of the device in TFLOP/s (2 flop per FMA), the FP64 roofline denominator. */
 int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);
+/* Tuning / test knob of the fused median: half-width (in binomial standard deviations, default 2.5) of
+ * the rank bracket the 256-sample pre-sample puts around the reference's median rank (remove_median,
+ * likelihood3.c:86-105).  A chain whose bracket misses is evaluated a second time with its template stored
+ * and selected exactly, so the result never depends on this value -- only the cost does (0 forces every
+ * chain down the miss path; the tests use that). */
+int hb_set_bracket_sigma(hb_ctx* ctx, double sigma);
 /* When enabled, every likelihood / light-curve call records CUDA events around its k_chain_eval
  * launch on the launching stream; hb_last_eval_kernel_ms waits for and returns that duration. */
 int hb_time_kernels(hb_ctx* ctx, int enable);

@@ -2,6 +2,7 @@
 // of the device model (prologue folding, Kepler solve, flux polynomial, eclipse) against the
 // oracle without a GPU.  CUDA intrinsics are mapped to their IEEE host equivalents; the
 // product never uses this file.
+#include <cfenv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -15,6 +16,15 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline double __drcp_rn(double a) { volatile double r = 1.0 / a; return r; }
+static inline double __fma_rd(double a, double b, double c)
+{
+    volatile double va = a, vb = b, vc = c;
+    const int mode = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile double r = fma(va, vb, vc);
+    fesetround(mode);
+    return r;
+}
 static inline void hb_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 #define sincos hb_sincos
 static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }

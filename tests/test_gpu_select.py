@@ -36,3 +36,23 @@ def test_nan_input(ctx):
     x = np.random.default_rng(0).standard_normal(5000)
     x[1234] = np.nan
     assert np.isnan(ctx.order_statistic(x, 2500))
+
+
+@pytest.mark.parametrize("N", [5000, 20001])
+def test_missed_bracket_reruns_and_agrees(ctx, N):
+    """The fused median brackets the reference's rank from a 256-sample pre-sample; a chain whose bracket
+    misses is evaluated again with its template stored and selected exactly.  Forcing every chain down
+    that path (sigma = 0) and widening the bracket until candidates overflow to global scratch (sigma =
+    40) must give the bits of the default path."""
+    from hb_mcmc_b200 import workload as wl
+    t, flux, err = wl.make_dataset(N, wl.TRUTH_A, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    P = wl.draw_chains(96, wl.TRUTH_A, lambda P: ctx.roche_overflow(P), seed=3)
+    base = ctx.loglikelihood(P)
+    try:
+        for sigma in (0.0, 0.3, 40.0):
+            ctx.set_bracket_sigma(sigma)
+            assert np.array_equal(ctx.loglikelihood(P), base, equal_nan=True), sigma
+    finally:
+        ctx.set_bracket_sigma(2.5)
+    assert np.isfinite(base).all()
