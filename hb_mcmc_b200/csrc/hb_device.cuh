@@ -40,14 +40,20 @@ constexpr double kBig = 1.e15;
 // Per-chain folded constants (written by chain_prologue, read by the point kernels).
 struct ChainConst {
     // orbit
-    double e, sq1me2;  // eccentricity, sqrt(1-e^2)
+    double e;          // eccentricity
     double T0s, Ps;    // T0*86400, P[s]  (exactly the reference's T0_cgs / P_cgs)
     double rPs;        // RN(1/Ps): seed of the exact phase division
     double cw, sw;     // cos/sin omega0
+    double cwq, swq;   // cos/sin omega0 times sqrt(1 - e^2)
     double ci, si;     // cos/sin inc
     double ar;         // a / RSUN
     // raw flux u = K0 + K1 c + b^2 (a0 + a1 s + a2 c2 + b (b0 + b1 c2 + b (c1 s + c3 s3 + b (d0 + d2 c2 + d4 c4))))
-    double K0, K1, a0, a1, a2, b0, b1, c1, c3, d0, d2, d4;
+    // with the two highest harmonics rewritten in c2 = cos 2x:  sin 3x = s (1 + 2 c2),  cos 4x = 2 c2^2 - 1
+    //   c1 s + c3 s3 = s (q1 + q3 c2),          q1 = c1 + c3,  q3 = 2 c3
+    //   d0 + d2 c2 + d4 c4 = r0 + c2 (d2 + r4 c2),  r0 = d0 - d4,  r4 = 2 d4
+    double K0, K1, a0, a1, a2, b0, b1, q1, q3, r0, d2, r4;
+    // eclipse pre-test on squared quantities: (1 - e cos E)^2 (ci^2 + si^2 c^2) < thr, thr = ((R1 + R2)/ar)^2 (1 + 1e-9)
+    double si2, ci2, thr;
     // eclipse (radii in Rsun, sorted big/small as eclipse_area does)
     double Rb, Rs, ecl1, ecl2;  // ecl_k = Norm_k / (pi R_k^2)
     // normalisation: model = A (u - median) + ft,  A = ft (1 - blending)
@@ -379,12 +385,13 @@ __device__ inline void prologue_assemble(const double* __restrict__ p, const Mag
     const double si2 = si * si, si3 = si2 * si, si4 = si2 * si2;
 
     cc.e = e;
-    cc.sq1me2 = T.sq1me2;
     cc.T0s = T0 * kSecDay;
     cc.Ps = Pd * kSecDay;
     cc.rPs = __drcp_rn(cc.Ps);
     cc.cw = T.cw;
     cc.sw = T.sw;
+    cc.cwq = T.cw * T.sq1me2;
+    cc.swq = T.sw * T.sq1me2;
     cc.ci = ci;
     cc.si = si;
     cc.ar = T.a / kRsun;  // semi-major axis as traj() forms it (likelihood3.c:141-142)
@@ -404,7 +411,7 @@ __device__ inline void prologue_assemble(const double* __restrict__ p, const Mag
         const double Ma13 = T.cM[k], q13 = T.cq[k];                          // Ma^(1/3), (1+q)^(1/3)
         const double iMa23 = 1.0 / (Ma13 * Ma13), iq23 = 1.0 / (q13 * q13);  // ^(-2/3)
         // beaming, likelihood3.c:224-236 (pow(1+q, 2/3) == 1, quirk Q1)
-        const double B = -2830. * ab[k] * q * Ma13 * Pm13 * si / cc.sq1me2 * ppm;
+        const double B = -2830. * ab[k] * q * Ma13 * Pm13 * si / T.sq1me2 * ppm;
         // ellipsoidal coefficient set, likelihood3.c:258-264
         const double al11 = 15 * mu[k] * (2 + tau[k]) / (32 * (3 - mu[k]));
         const double al21 = 3 * (15 + mu[k]) * (1 + tau[k]) / (20 * (3 - mu[k]));
@@ -439,10 +446,16 @@ __device__ inline void prologue_assemble(const double* __restrict__ p, const Mag
         d4 += N * C4;
     }
     cc.K0 = K0; cc.K1 = K1; cc.a0 = a0; cc.a1 = a1; cc.a2 = a2; cc.b0 = b0; cc.b1 = b1;
-    cc.c1 = c1; cc.c3 = c3; cc.d0 = d0; cc.d2 = d2; cc.d4 = d4;
+    cc.q1 = c1 + c3; cc.q3 = 2.0 * c3; cc.r0 = d0 - d4; cc.d2 = d2; cc.r4 = 2.0 * d4;
 
     cc.Rb = fmax(R[0], R[1]);
     cc.Rs = fmin(R[0], R[1]);
+    cc.si2 = si * si;
+    cc.ci2 = ci * ci;
+    {
+        const double lim = (cc.Rb + cc.Rs) / cc.ar;
+        cc.thr = lim * lim * (1.0 + 1e-9);
+    }
     cc.ecl1 = Nrm[0] / (kPi * sq(R[0]));
     cc.ecl2 = Nrm[1] / (kPi * sq(R[1]));
     cc.blend = blending;
@@ -722,16 +735,13 @@ __device__ __forceinline__ double kepler_table_guess(const double* __restrict__ 
     int j = __double2int_rd(x);
     j = min(j, kTableN - 1);
     const double t = x - (double)j;  // in [0, 1]
-    const double a = t + 1.0, b = t - 1.0, c = t - 2.0;
-    const double tb = t * b, at = a * t;
-    const double w0 = tb * c * kMisc[5];
-    const double w1 = a * b * c * 0.5;
-    const double w2 = at * c * (-0.5);
-    const double w3 = at * b * kMisc[6];
-    double E = w0 * tab[j];
-    E = fma(w1, tab[j + 1], E);
-    E = fma(w2, tab[j + 2], E);
-    E = fma(w3, tab[j + 3], E);
+    // cubic Lagrange on the nodes -1, 0, 1, 2 with the weights paired up:
+    //   E = a/6 (y3 (t+1) - y0 (t-2)) + b/2 (y1 (t-1) - y2 t),  a = t (t-1),  b = (t+1)(t-2) = a - 2
+    const double y0 = tab[j], y1 = tab[j + 1], y2 = tab[j + 2], y3 = tab[j + 3];
+    const double a = fma(t, t, -t);
+    const double p = fma(t, y3 - y0, fma(2.0, y0, y3));
+    const double q = fma(t, y1 - y2, -y1);
+    const double E = fma(fma(a, 0.5, -1.0), q, (a * kMisc[6]) * p);
     return copysign(E, m);
 }
 
@@ -856,28 +866,28 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
-        const double cnu = (cE[j] - cc.e) * beta;
-        const double snu = cc.sq1me2 * sE[j] * beta;
-        const double c = cc.cw * cnu - cc.sw * snu;  // cos(omega0 + nu)
-        const double s = cc.sw * cnu + cc.cw * snu;  // sin(omega0 + nu)
-        const double c2 = fma(2.0 * c, c, -1.0);     // cos 2x
-        const double s3 = s * fma(-4.0 * s, s, 3.0); // sin 3x
-        const double c4 = fma(2.0 * c2, c2, -1.0);   // cos 4x
+        // cos nu = (cos E - e) beta, sin nu = sqrt(1 - e^2) sin E beta; rotate by omega0, then scale
+        const double X = cE[j] - cc.e;
+        const double c = fma(-cc.swq, sE[j], cc.cw * X) * beta;  // cos(omega0 + nu)
+        const double s = fma(cc.cwq, sE[j], cc.sw * X) * beta;   // sin(omega0 + nu)
+        const double cc2 = c * c;
+        const double c2 = fma(2.0, cc2, -1.0);                   // cos 2x
 
-        const double P5 = fma(cc.d4, c4, fma(cc.d2, c2, cc.d0));
-        const double P4 = fma(cc.c3, s3, cc.c1 * s);
+        const double P5 = fma(fma(cc.r4, c2, cc.d2), c2, cc.r0);
+        const double P4 = s * fma(cc.q3, c2, cc.q1);
         const double P3 = fma(cc.b1, c2, cc.b0);
         const double P2 = fma(cc.a2, c2, fma(cc.a1, s, cc.a0));
         const double poly = fma(beta, fma(beta, fma(beta, P5, P4), P3), P2);
         double uj = fma(beta * beta, poly, fma(cc.K1, c, cc.K0));
 
-        // eclipse: projected separation in Rsun (likelihood3.c:173-176, 365)
-        const double sc = s * cc.ci;
-        const double proj2 = fma(c, c, sc * sc);
-        const double rr = cc.ar * den[j];
-        const double d2 = rr * rr * proj2;
-        const double lim = cc.Rb + cc.Rs;
-        if (may_eclipse && d2 < lim * lim * (1.0 + 1e-9)) {
+        // eclipse: the squared projected separation over a^2 against the chain's threshold (s^2 = 1 - c^2 to
+        // rounding; the 1e-9 slack of thr absorbs that); the rare in-eclipse sample then forms the
+        // separation exactly as the reference does (likelihood3.c:173-176, 365)
+        if (may_eclipse && den[j] * den[j] * fma(cc2, cc.si2, cc.ci2) < cc.thr) {
+            const double sc = s * cc.ci;
+            const double proj2 = fma(c, c, sc * sc);
+            const double rr = cc.ar * den[j];
+            const double lim = cc.Rb + cc.Rs;
             const double d = fabs(rr * sqrt(proj2));
             if (!(d >= lim)) {
                 const double area = eclipse_area_dev(cc.Rb, cc.Rs, d);

@@ -85,9 +85,12 @@ __device__ __noinline__ uint64_t block_sort(uint64_t key, uint64_t* xch)
 {
     static_assert((kThreads & (kThreads - 1)) == 0, "block size must be a power of two");
     const int tid = threadIdx.x;
-#pragma unroll 1
+    // fully unrolled: k and j are compile-time constants in each of the log2(n)(log2(n)+1)/2 stages,
+    // so a stage is two shuffles (or one shared-memory exchange), a 64-bit compare and two selects
+#pragma unroll
     for (int k = 2; k <= kThreads; k <<= 1) {
-#pragma unroll 1
+        const bool descending = (tid & k) != 0;
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             uint64_t other;
             if (j >= 32) {
@@ -100,7 +103,8 @@ __device__ __noinline__ uint64_t block_sort(uint64_t key, uint64_t* xch)
                 const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
                 other = ((uint64_t)hi << 32) | lo;
             }
-            const bool take_min = (((tid & k) == 0) == ((tid & j) == 0));
+            // the lower partner of an ascending pair keeps the minimum
+            const bool take_min = descending == ((tid & j) != 0);
             const bool less = other < key;
             key = (less == take_min) ? other : key;
         }

@@ -4,6 +4,7 @@
 // product never uses this file.
 #include <cfenv>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -53,6 +54,9 @@ static MagSetup default_mags(const double* md, const double* me, int g, int c)
 }
 
 extern "C" int emul_const_size(void) { return (int)(sizeof(ChainConst) / sizeof(double)); }
+// positions (in doubles) of the fields the tests look at
+extern "C" int emul_const_flag_index(void) { return (int)(offsetof(ChainConst, flag) / sizeof(double)); }
+extern "C" int emul_const_info_index(void) { return (int)(offsetof(ChainConst, info) / sizeof(double)); }
 
 extern "C" void emul_prologue(const double* p, const double* md, const double* me, int g, int c, double* out)
 {

@@ -141,10 +141,11 @@ def test_prologue_flags(emul, orc, golden):
     md = np.array([1000.0, 1, 1, 1, 1])
     me = np.full(4, 1e15)
     n = emul.emul_const_size()
+    i_flag, i_info = emul.emul_const_flag_index(), emul.emul_const_info_index()
     for p, flag in zip(golden["roche_params"], golden["roche_flags"]):
         cc = np.empty(n)
         p = np.ascontiguousarray(p)
         emul.emul_prologue(p.ctypes.data_as(dp), md.ctypes.data_as(dp), me.ctypes.data_as(dp), 1, 0, cc.ctypes.data_as(dp))
-        assert (int(cc[29]) & 1) == int(flag)
+        assert (int(cc[i_flag]) & 1) == int(flag)
         R1, R2, T1, T2 = orc.radii_teffs(p)
-        np.testing.assert_allclose(cc[31:35], [R1, R2, T1, T2], rtol=1e-14)
+        np.testing.assert_allclose(cc[i_info:i_info + 4], [R1, R2, T1, T2], rtol=1e-14)
