@@ -14,6 +14,7 @@
 #include "hb_kernels.h"
 #include "hb_gaia_pt.cuh"
 #include "hb_pt.cuh"
+#include "hb_sincos_tab.h"
 
 using namespace hb;
 
@@ -31,6 +32,7 @@ struct hb_ctx {
 
     // observed light curve (device)
     double* d_t = nullptr;    // seconds (t * 86400)
+    double2* d_sctab = nullptr;  // {sin, cos}(2 pi k / 1024) for sincos_tab, filled at hb_create
     double2* d_fw = nullptr;  // {flux, 1 / max(sigma, 1e-5)} interleaved: one 16-byte load per sample
     long N = 0;
     bool has_data = false;
@@ -185,7 +187,7 @@ int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, con
     CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->stream));
     if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_fw, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
-                         d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->stream));
+                         d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->d_sctab, ctx->stream));
     if (ctx->time_kernels) {
         CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
         ctx->ev_valid = true;
@@ -252,8 +254,14 @@ int hb_create(hb_ctx** out, int device)
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_counter, sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_small, 64 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_sctab, kSinTabN * sizeof(double2)) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess &&
               configure_eval() == cudaSuccess;
+    if (ok) {
+        std::vector<double> tab(2 * kSinTabN);
+        fill_sincos_table(tab.data());
+        ok = cudaMemcpy(ctx->d_sctab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) {
         set_global(std::string("hb_create: ") + cudaGetErrorString(cudaGetLastError()));
         hb_destroy(ctx);
@@ -273,7 +281,7 @@ void hb_destroy(hb_ctx* ctx)
         cudaFree(ctx->d_t); cudaFree(ctx->d_fw);
         cudaFree(ctx->d_params); cudaFree(ctx->d_cc); cudaFree(ctx->d_logL);
         cudaFree(ctx->d_scratch); cudaFree(ctx->d_counter); cudaFree(ctx->d_lc);
-        cudaFree(ctx->d_times2); cudaFree(ctx->d_small); cudaFree(ctx->d_aux);
+        cudaFree(ctx->d_times2); cudaFree(ctx->d_small); cudaFree(ctx->d_aux); cudaFree(ctx->d_sctab);
         if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
         if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
         if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);

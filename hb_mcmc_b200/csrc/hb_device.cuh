@@ -645,6 +645,38 @@ __device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out
     }
 }
 
+// Table sincos for the hot loop: x = k h + r with h = 2 pi / 1024 (the Cody-Waite split of pi/2
+// scaled by 2^-8, exact), |r| <= h/2 = 3.1e-3, so sin r and cos r need two Taylor terms each
+// (next terms: r^6/5040 = 2e-19, r^6/720 = 1e-18 relative) and sin/cos(k h) come from a 1024-entry
+// table of correctly rounded values (16 KB in global memory, L1-resident; filled once per context
+// on the host in extended precision, hb_sincos_tab.h).  14 FP64 instructions and one 16-byte load
+// against 22 + 11 quadrant instructions + 5 constant loads of sincos_lean; same ~1 ulp accuracy
+// (sin is exact-relative near its zeros, which are table nodes).  Same contract as sincos_lean.
+constexpr int kSinTabN = 1024;
+// 0 nodes per radian  1, 2 h = pi/512 as (pi/2 hi, lo of kRed) / 256  3-5 Taylor coefficients
+__constant__ double kTabC[6] = {162.97466172610082624, 1.57079632679489655800e+00 / 256.0, 6.12323399573676603587e-17 / 256.0,
+                                1.0 / 120.0, -1.0 / 6.0, 1.0 / 24.0};
+template <int V>
+__device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* __restrict__ tab, double (&s_out)[V],
+                                           double (&c_out)[V], int& hi_max)
+{
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        hi_max = max(hi_max, __double2hiint(x[j]) & 0x7fffffff);
+        const double t = fma(x[j], kTabC[0], kRed[4]);
+        const int k = __double2loint(t) & (kSinTabN - 1);  // nearest node, periodic (two's complement for x < 0)
+        const double kd = t - kRed[4];
+        double r = fma(-kd, kTabC[1], x[j]);
+        r = fma(-kd, kTabC[2], r);
+        const double2 sc = tab[k];  // {sin, cos}(k h)
+        const double z = r * r;
+        const double sd = fma(r * z, fma(z, kTabC[3], kTabC[4]), r);
+        const double cd = fma(z, fma(z, kTabC[5], -0.5), 1.0);
+        s_out[j] = fma(sc.y, sd, sc.x * cd);
+        c_out[j] = fma(-sc.x, sd, sc.y * cd);
+    }
+}
+
 // rare tail of fmod_twopi: quotient off by one (|M| within rounding of a multiple of 2 pi), or
 // huge / inf / NaN input
 static __device__ __noinline__ double fmod_twopi_fix(double q, double r, double am)
@@ -760,10 +792,12 @@ __device__ __forceinline__ double kepler_table_node(int j, double e)
 // likelihood3.c:149-160 for V samples: outputs cos E, sin E, den = 1 - e cos E and beta = 1/den.
 // kFullWarp: all 32 lanes of the warp execute this call together (true in the model pass).
 // ktab: the chain's E(M) table (nullptr: reference starter, always valid).
+// sctab: the sin/cos table of sincos_tab (nullptr: polynomial sincos_lean).
 template <int V, bool kFullWarp>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
-                                              const double rPs, const double* __restrict__ ktab, double (&cE)[V],
-                                              double (&sE)[V], double (&den)[V], double (&beta)[V])
+                                              const double rPs, const double* __restrict__ ktab,
+                                              const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
+                                              double (&den)[V], double (&beta)[V])
 {
     double M[V], E[V], dE[V], yr[V];
 #pragma unroll
@@ -781,7 +815,8 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
     int hi_max = 0;
 #pragma unroll kNewtonUnroll
     for (int k = 0; k < 5; k++) {
-        sincos_lean<V>(E, sE, cE, hi_max);
+        if (sctab != nullptr) sincos_tab<V>(E, sctab, sE, cE, hi_max);
+        else sincos_lean<V>(E, sE, cE, hi_max);
         tiny = true;
 #pragma unroll
         for (int j = 0; j < V; j++) {
@@ -807,7 +842,8 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
             beta[j] = fma(yr[j], fma(-den[j], yr[j], 1.0), yr[j]);
         }
     } else {
-        sincos_lean<V>(E, sE, cE, hi_max);
+        if (sctab != nullptr) sincos_tab<V>(E, sctab, sE, cE, hi_max);
+        else sincos_lean<V>(E, sE, cE, hi_max);
 #pragma unroll
         for (int j = 0; j < V; j++) {
             den[j] = fma(-e, cE[j], 1.0);
@@ -857,12 +893,12 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 // Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
 template <int V, bool kFullWarp>
-__device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab, const double (&tsec)[V],
-                                         double (&u)[V])
+__device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab,
+                                         const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V])
 {
     const bool may_eclipse = (((int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
-    kepler_points<V, kFullWarp>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cE, sE, den, bet);
+    kepler_points<V, kFullWarp>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, sctab, cE, sE, den, bet);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
@@ -901,11 +937,12 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
 }
 
 template <bool kFullWarp>
-__device__ __forceinline__ double raw_flux1(const ChainConst& cc, const double* __restrict__ ktab, double tsec)
+__device__ __forceinline__ double raw_flux1(const ChainConst& cc, const double* __restrict__ ktab,
+                                            const double2* __restrict__ sctab, double tsec)
 {
     const double t[1] = {tsec};
     double u[1];
-    raw_flux<1, kFullWarp>(cc, ktab, t, u);
+    raw_flux<1, kFullWarp>(cc, ktab, sctab, t, u);
     return u[0];
 }
 

@@ -103,6 +103,7 @@ struct EvalShared {
     double red[3 * 32];
     double pivot;  // chi^2 expansion point u0 (a template value near the median)
     double ktab[kTableSize];  // the chain's E(M) starter table (hb_device.cuh)
+    double2 sctab[kSinTabN];  // {sin, cos}(2 pi k / 1024) for sincos_tab, copied once per CTA
     uint64_t candA[kCandA];
     uint64_t candB[kCandB];
 };
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
 k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
              const double2* __restrict__ fw, int N, uint64_t* __restrict__ scratch,
              size_t scratch_stride, double* __restrict__ logL, double* __restrict__ lc_out, int* __restrict__ counter,
-             float bracket_sigma)
+             float bracket_sigma, const double2* __restrict__ sctab_g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -148,6 +149,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int krank = median_rank(N);
     const int n_tiles = (N + kTile - 1) / kTile;
+    for (int i = tid; i < kSinTabN; i += kThreads) sm.sctab[i] = sctab_g[i];  // published by the first barrier below
+    const double2* sctab = sm.sctab;
 #if HB_TMA_STAGING
     if (tid == 0) {
         for (int st = 0; st < kStages; st++) {
@@ -207,7 +210,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         double lo = -INFINITY, hi = INFINITY;
         if (bracketed) {
             const uint32_t seed = (uint32_t)cc.seed;
-            const double us = raw_flux1<true>(cc, ktab, tsec[sample_index(tid, kThreads, N, seed)]);
+            const double us = raw_flux1<true>(cc, ktab, sctab, tsec[sample_index(tid, kThreads, N, seed)]);
             // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
             const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
             int r_lo, r_hi, r_mid;
@@ -305,7 +308,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
 #endif
-            raw_flux<V, true>(cc, ktab, ts, u);
+            raw_flux<V, true>(cc, ktab, sctab, ts, u);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -481,7 +484,7 @@ __global__ void k_traj(const double* __restrict__ times, int Nt, const double* _
     const double a = pow(kG * Mtot * sq(P) / sq(2 * kPi), 1. / 3.);
     const double ts[1] = {__dmul_rn(times[i], kSecDay)};
     double cE[1], sE[1], den[1], bet[1];
-    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), nullptr, cE, sE, den, bet);
+    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), nullptr, nullptr, cE, sE, den, bet);
     const double r = a * den[0];
     const double sq1 = sqrt(1 - e * e);
     const double nu = atan2(sq1 * sE[0], cE[0] - e);
@@ -620,14 +623,14 @@ cudaError_t configure_eval()
 
 cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
                               int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
-                              int* counter, float bracket_sigma, cudaStream_t s)
+                              int* counter, float bracket_sigma, const double2* sctab, cudaStream_t s)
 {
     if (n_chains <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     if (grid > n_chains) grid = n_chains;
     k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, fw, N, scratch,
-                                                                               scratch_stride, logL, lc_out, counter, bracket_sigma);
+                                                                               scratch_stride, logL, lc_out, counter, bracket_sigma, sctab);
     return cudaGetLastError();
 }
 

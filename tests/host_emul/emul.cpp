@@ -40,8 +40,22 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int __double2int_rd(double x) { return (int)floor(x); }
 #define HB_HOST_EMUL 1
 #define __constant__ static const
+struct double2 { double x, y; };
 #include "hb_device_host.cuh"
+#include "../../hb_mcmc_b200/csrc/hb_sincos_tab.h"
 using namespace hb;
+
+// the sin/cos table of sincos_tab, filled exactly as hb_create does
+static const double2* host_sctab()
+{
+    static double2 tab[kSinTabN];
+    static bool ready = false;
+    if (!ready) {
+        fill_sincos_table(reinterpret_cast<double*>(tab));
+        ready = true;
+    }
+    return tab;
+}
 
 static MagSetup default_mags(const double* md, const double* me, int g, int c)
 {
@@ -66,15 +80,17 @@ extern "C" void emul_prologue(const double* p, const double* md, const double* m
 }
 
 // raw (un-normalised) template, likelihood3.c:673
+// use_table: bit 0 = the kernel's E(M) starter table, bit 1 = the table sincos (both on in the kernel)
 extern "C" void emul_raw(const double* p, const double* t, long n, double* out, int use_table)
 {
+    const double2* sctab = (use_table & 2) ? host_sctab() : nullptr;
     const double md[5] = {1000, 1, 1, 1, 1}, me[4] = {1e15, 1e15, 1e15, 1e15};
     ChainConst cc;
     chain_prologue(p, default_mags(md, me, 1, 0), cc);
     // the kernel's starter table for chains with 0 <= e <= kTableMaxE (use_table != 0)
     static double tab[kTableSize];
     const double* ktab = nullptr;
-    if (use_table && cc.e >= 0.0 && cc.e <= kTableMaxE) {
+    if ((use_table & 1) && cc.e >= 0.0 && cc.e <= kTableMaxE) {
         for (int j = 0; j < kTableSolved; j++) tab[j] = kepler_table_node(j, cc.e);
         for (int j = kTableSolved; j < kTableSize; j++) tab[j] = kTwoPi - tab[kTableN + 2 - j];
         ktab = tab;
@@ -83,11 +99,11 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out, 
     for (; i + 2 <= n; i += 2) {  // the two-wide path the kernel uses
         const double ts[2] = {__dmul_rn(t[i], kSecDay), __dmul_rn(t[i + 1], kSecDay)};
         double u[2];
-        raw_flux<2, true>(cc, ktab, ts, u);
+        raw_flux<2, true>(cc, ktab, sctab, ts, u);
         out[i] = u[0];
         out[i + 1] = u[1];
     }
-    for (; i < n; i++) out[i] = raw_flux1<false>(cc, ktab, __dmul_rn(t[i], kSecDay));
+    for (; i < n; i++) out[i] = raw_flux1<false>(cc, ktab, sctab, __dmul_rn(t[i], kSecDay));
 }
 
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
@@ -109,6 +125,19 @@ extern "C" void emul_sincos(const double* x, long n, double* s, double* c)
         c[i] = cv[0];
     }
 }
+extern "C" void emul_sincos_tab(const double* x, long n, double* s, double* c)
+{
+    for (long i = 0; i < n; i++) {
+        const double xv[1] = {x[i]};
+        double sv[1], cv[1];
+        int hm = 0;
+        sincos_tab<1>(xv, host_sctab(), sv, cv, hm);
+        if (hm > kSincosHiLimit) { sv[0] = sin(x[i]); cv[0] = cos(x[i]); }
+        s[i] = sv[0];
+        c[i] = cv[0];
+    }
+}
+extern "C" void emul_sincos_table(double* out) { memcpy(out, host_sctab(), sizeof(double2) * kSinTabN); }
 extern "C" void emul_div(const double* a, const double* b, long n, double* q, double* r)
 {
     for (long i = 0; i < n; i++) { q[i] = div_fast(a[i], b[i]); r[i] = rcp_fast(b[i]); }

@@ -31,6 +31,8 @@ def emul():
     L.emul_fmod_twopi.argtypes = [C.c_double]
     L.emul_prologue.argtypes = [dp, dp, dp, C.c_int, C.c_int, dp]
     L.emul_sincos.argtypes = [dp, C.c_long, dp, dp]
+    L.emul_sincos_tab.argtypes = [dp, C.c_long, dp, dp]
+    L.emul_sincos_table.argtypes = [dp]
     L.emul_div.argtypes = [dp, dp, C.c_long, dp, dp]
     L.emul_phase_div.argtypes = [dp, dp, C.c_long, dp]
     return L
@@ -46,6 +48,33 @@ def test_lean_sincos_accuracy(emul):
     ulp_c = np.abs(c - np.cos(x)) / np.spacing(np.abs(np.cos(x)))
     assert ulp_s.max() <= 2.0 and ulp_c.max() <= 2.0, (ulp_s.max(), ulp_c.max())
     assert np.mean(s == np.sin(x)) > 0.6 and np.mean(c == np.cos(x)) > 0.6
+
+
+def test_table_sincos_accuracy(emul):
+    """sincos_tab (the hot loop's sin/cos): table nodes correctly rounded, results within 2 ulp, exact
+    relative accuracy next to the zeros of sin and cos."""
+    import mpmath as mp
+    mp.mp.prec = 200
+    tab = np.empty(2048)
+    emul.emul_sincos_table(tab.ctypes.data_as(dp))
+    for k in range(1024):
+        a = 2 * mp.pi * k / 1024
+        ws, wc = float(mp.sin(a)), float(mp.cos(a))
+        if k % 256 == 0:  # multiples of pi/2: exact 0 and +-1 by symmetry
+            ws, wc = float(round(ws)), float(round(wc))
+        assert tab[2 * k] == ws + 0.0 and tab[2 * k + 1] == wc + 0.0, k
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 50000), np.arange(-40, 41) * (np.pi / 4),
+                        np.pi + rng.uniform(-1e-3, 1e-3, 2000), np.pi / 2 + rng.uniform(-1e-6, 1e-6, 2000),
+                        [0.0, 1e-300, -1e-9, 2e5, -3e7]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    emul.emul_sincos_tab(x.ctypes.data_as(dp), x.size, s.ctypes.data_as(dp), c.ctypes.data_as(dp))
+    small = np.abs(x) <= 10
+    err_s = np.abs(s - np.sin(x)) / np.spacing(np.maximum(np.abs(np.sin(x)), 2.0 ** -10))
+    err_c = np.abs(c - np.cos(x)) / np.spacing(np.maximum(np.abs(np.cos(x)), 2.0 ** -10))
+    assert err_s[small].max() <= 2.0 and err_c[small].max() <= 2.0, (err_s[small].max(), err_c[small].max())
+    assert err_s.max() <= 3.0 and err_c.max() <= 3.0, (err_s.max(), err_c.max())
+    assert np.mean(s == np.sin(x)) > 0.5 and np.mean(c == np.cos(x)) > 0.5
 
 
 def test_fast_division_accuracy(emul):
@@ -120,12 +149,25 @@ def test_table_starter_equals_reference_starter(emul, orc):
             P[k] = q
     worst = 0.0
     for p in P:
-        a, b = raw(emul, p, t, 1), raw(emul, p, t, 0)
+        a, b, c = raw(emul, p, t, 1), raw(emul, p, t, 0), raw(emul, p, t, 3)  # 3 = the kernel's configuration
         scale = np.maximum(np.abs(b), 1.0)
-        worst = max(worst, np.nanmax(np.abs(a - b) / scale))
+        worst = max(worst, np.nanmax(np.abs(a - b) / scale), np.nanmax(np.abs(c - b) / scale))
         _, want = orc.calc_light_curve(t, p, raw=True)
         assert np.nanmax(np.abs(a - want) / scale) < 1e-11
+        assert np.nanmax(np.abs(c - want) / scale) < 1e-11
     assert worst < 2e-13, worst
+
+
+def test_table_sincos_high_e(emul, orc):
+    """The table sincos in the un-converged Newton tail (e up to 0.99, reference starter)."""
+    t = wl.time_grid(3000) * 7.0 - 5.0
+    P = wl.draw_chains(48, wl.TRUTH_B, lambda P: np.zeros(len(P)), seed=4, e_max=0.99)
+    P[:, 3] = np.linspace(0.8, 0.99, len(P))
+    for p in P:
+        _, want = orc.calc_light_curve(t, p, raw=True)
+        got = raw(emul, p, t, 2)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) < 1e-11
 
 
 def test_finish_matches_reference_order(emul, orc):
