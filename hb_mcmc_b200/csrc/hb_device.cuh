@@ -792,8 +792,8 @@ __device__ __forceinline__ double kepler_table_node(int j, double e)
 // likelihood3.c:149-160 for V samples: outputs cos E, sin E, den = 1 - e cos E and beta = 1/den.
 // kFullWarp: all 32 lanes of the warp execute this call together (true in the model pass).
 // ktab: the chain's E(M) table (nullptr: reference starter, always valid).
-// sctab: the sin/cos table of sincos_tab (nullptr: polynomial sincos_lean).
-template <int V, bool kFullWarp>
+// kSinTab: use sincos_tab with the table sctab (else the polynomial sincos_lean; sctab is ignored).
+template <int V, bool kFullWarp, bool kSinTab = false>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
                                               const double rPs, const double* __restrict__ ktab,
                                               const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
@@ -815,7 +815,7 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
     int hi_max = 0;
 #pragma unroll kNewtonUnroll
     for (int k = 0; k < 5; k++) {
-        if (sctab != nullptr) sincos_tab<V>(E, sctab, sE, cE, hi_max);
+        if (kSinTab) sincos_tab<V>(E, sctab, sE, cE, hi_max);
         else sincos_lean<V>(E, sE, cE, hi_max);
         tiny = true;
 #pragma unroll
@@ -842,7 +842,7 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
             beta[j] = fma(yr[j], fma(-den[j], yr[j], 1.0), yr[j]);
         }
     } else {
-        if (sctab != nullptr) sincos_tab<V>(E, sctab, sE, cE, hi_max);
+        if (kSinTab) sincos_tab<V>(E, sctab, sE, cE, hi_max);
         else sincos_lean<V>(E, sE, cE, hi_max);
 #pragma unroll
         for (int j = 0; j < V; j++) {
@@ -892,13 +892,13 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 
 // Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
-template <int V, bool kFullWarp>
+template <int V, bool kFullWarp, bool kSinTab = false>
 __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab,
                                          const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V])
 {
     const bool may_eclipse = (((int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
-    kepler_points<V, kFullWarp>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, sctab, cE, sE, den, bet);
+    kepler_points<V, kFullWarp, kSinTab>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, sctab, cE, sE, den, bet);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)
@@ -936,13 +936,13 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
     }
 }
 
-template <bool kFullWarp>
+template <bool kFullWarp, bool kSinTab = false>
 __device__ __forceinline__ double raw_flux1(const ChainConst& cc, const double* __restrict__ ktab,
                                             const double2* __restrict__ sctab, double tsec)
 {
     const double t[1] = {tsec};
     double u[1];
-    raw_flux<1, kFullWarp>(cc, ktab, sctab, t, u);
+    raw_flux<1, kFullWarp, kSinTab>(cc, ktab, sctab, t, u);
     return u[0];
 }
 

@@ -210,7 +210,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         double lo = -INFINITY, hi = INFINITY;
         if (bracketed) {
             const uint32_t seed = (uint32_t)cc.seed;
-            const double us = raw_flux1<true>(cc, ktab, sctab, tsec[sample_index(tid, kThreads, N, seed)]);
+            const double us = raw_flux1<true, true>(cc, ktab, sctab, tsec[sample_index(tid, kThreads, N, seed)]);
             // a NaN sample sorts above every number; the model pass flags NaN and aborts the chain
             const uint64_t sorted = block_sort<kThreads>(dkey(us), sm.ctl.xch);
             int r_lo, r_hi, r_mid;
@@ -308,7 +308,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
 #endif
-            raw_flux<V, true>(cc, ktab, sctab, ts, u);
+            raw_flux<V, true, true>(cc, ktab, sctab, ts, u);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];

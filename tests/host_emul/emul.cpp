@@ -41,6 +41,7 @@ static inline int __double2int_rd(double x) { return (int)floor(x); }
 #define HB_HOST_EMUL 1
 #define __constant__ static const
 struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
 #include "hb_device_host.cuh"
 #include "../../hb_mcmc_b200/csrc/hb_sincos_tab.h"
 using namespace hb;
@@ -99,11 +100,14 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out, 
     for (; i + 2 <= n; i += 2) {  // the two-wide path the kernel uses
         const double ts[2] = {__dmul_rn(t[i], kSecDay), __dmul_rn(t[i + 1], kSecDay)};
         double u[2];
-        raw_flux<2, true>(cc, ktab, sctab, ts, u);
+        if (sctab) raw_flux<2, true, true>(cc, ktab, sctab, ts, u);
+        else raw_flux<2, true, false>(cc, ktab, sctab, ts, u);
         out[i] = u[0];
         out[i + 1] = u[1];
     }
-    for (; i < n; i++) out[i] = raw_flux1<false>(cc, ktab, sctab, __dmul_rn(t[i], kSecDay));
+    for (; i < n; i++)
+        out[i] = sctab ? raw_flux1<false, true>(cc, ktab, sctab, __dmul_rn(t[i], kSecDay))
+                       : raw_flux1<false, false>(cc, ktab, sctab, __dmul_rn(t[i], kSecDay));
 }
 
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
