@@ -653,6 +653,19 @@ __device__ __forceinline__ void sincos_lean(const double (&x)[V], double (&s_out
 // against 22 + 11 quadrant instructions + 5 constant loads of sincos_lean; same ~1 ulp accuracy
 // (sin is exact-relative near its zeros, which are table nodes).  Same contract as sincos_lean.
 constexpr int kSinTabN = 1024;
+// Doubles whose low 32 bits are zero are encoded as immediates in FP64 SASS instructions (no constant
+// load, no register).  Used where 20 mantissa bits are enough:
+//   kMagic   1.5 * 2^52, exact
+//   kNodesA  1024 / (2 pi) to 20 bits: only picks the nearest table node, the reduction r = x - k h is exact
+//   kT5, kT4 1/120 and 1/24 to 20 bits: the Taylor terms they scale are below 1e-11 and 4e-12
+// With the 20-bit node constant the nearest-node pick drifts by |x| * 2^-20 nodes: negligible for
+// |x| <= 1024 (0.16 % of a node), so that is the validity range; beyond it (wild Newton iterates at
+// e -> 1) the caller falls back to the library path like sincos_lean does at 1e5.
+constexpr int kSincosTabHiLimit = 0x40900000;  // high word of 1024.0
+constexpr double kMagic = 6755399441055744.0;
+constexpr double kNodesA = 0x1.45F30p+7;
+constexpr double kT5 = 0x1.11111p-7;
+constexpr double kT4 = 0x1.55555p-5;
 // 0 nodes per radian  1, 2 h = pi/512 as (pi/2 hi, lo of kRed) / 256  3-5 Taylor coefficients
 __constant__ double kTabC[6] = {162.97466172610082624, 1.57079632679489655800e+00 / 256.0, 6.12323399573676603587e-17 / 256.0,
                                 1.0 / 120.0, -1.0 / 6.0, 1.0 / 24.0};
@@ -663,15 +676,15 @@ __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* 
 #pragma unroll
     for (int j = 0; j < V; j++) {
         hi_max = max(hi_max, __double2hiint(x[j]) & 0x7fffffff);
-        const double t = fma(x[j], kTabC[0], kRed[4]);
+        const double t = fma(x[j], kNodesA, kMagic);
         const int k = __double2loint(t) & (kSinTabN - 1);  // nearest node, periodic (two's complement for x < 0)
-        const double kd = t - kRed[4];
+        const double kd = t - kMagic;
         double r = fma(-kd, kTabC[1], x[j]);
         r = fma(-kd, kTabC[2], r);
         const double2 sc = tab[k];  // {sin, cos}(k h)
         const double z = r * r;
-        const double sd = fma(r * z, fma(z, kTabC[3], kTabC[4]), r);
-        const double cd = fma(z, fma(z, kTabC[5], -0.5), 1.0);
+        const double sd = fma(r * z, fma(z, kT5, kTabC[4]), r);
+        const double cd = fma(z, fma(z, kT4, -0.5), 1.0);
         s_out[j] = fma(sc.y, sd, sc.x * cd);
         c_out[j] = fma(-sc.x, sd, sc.y * cd);
     }
@@ -695,7 +708,7 @@ __device__ __forceinline__ double fmod_twopi(double M)
     const double am = fabs(M);
     // floor(am / y): the magic-number trick with the FMA rounding toward -inf (at 1.5 * 2^52 one ulp is 1).
     // Adding `magic - 0.5` in round-to-nearest does NOT work: that constant is not representable.
-    const double q = __fma_rd(am, kMisc[1], kMisc[3]) - kMisc[3];
+    const double q = __fma_rd(am, kMisc[1], 6755399441055744.0) - 6755399441055744.0;
     double r = fma(-q, kMisc[0], am);
     if (!(r >= 0.0 && r < kMisc[0])) r = fmod_twopi_fix(q, r, am);
     return copysign(r, M);
@@ -850,7 +863,7 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
             beta[j] = rcp_fast(den[j]);
         }
     }
-    if (hi_max > kSincosHiLimit) {  // some iterate left the range of the lean sincos: redo with the library
+    if (hi_max > (kSinTab ? kSincosTabHiLimit : kSincosHiLimit)) {  // an iterate left the fast sincos' range: library
 #pragma unroll
         for (int j = 0; j < V; j++) {
             kepler_point_careful(M[j], e, &cE[j], &sE[j]);

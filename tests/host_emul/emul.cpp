@@ -136,7 +136,7 @@ extern "C" void emul_sincos_tab(const double* x, long n, double* s, double* c)
         double sv[1], cv[1];
         int hm = 0;
         sincos_tab<1>(xv, host_sctab(), sv, cv, hm);
-        if (hm > kSincosHiLimit) { sv[0] = sin(x[i]); cv[0] = cos(x[i]); }
+        if (hm > kSincosTabHiLimit) { sv[0] = sin(x[i]); cv[0] = cos(x[i]); }
         s[i] = sv[0];
         c[i] = cv[0];
     }

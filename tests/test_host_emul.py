@@ -64,7 +64,8 @@ def test_table_sincos_accuracy(emul):
             ws, wc = float(round(ws)), float(round(wc))
         assert tab[2 * k] == ws + 0.0 and tab[2 * k + 1] == wc + 0.0, k
     rng = np.random.default_rng(1)
-    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 50000), np.arange(-40, 41) * (np.pi / 4),
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1024, 1024, 50000), rng.uniform(-1e5, 1e5, 5000),
+                        np.arange(-40, 41) * (np.pi / 4), [1024.0, -1024.0, 1023.999, 1024.001],
                         np.pi + rng.uniform(-1e-3, 1e-3, 2000), np.pi / 2 + rng.uniform(-1e-6, 1e-6, 2000),
                         [0.0, 1e-300, -1e-9, 2e5, -3e7]])
     s, c = np.empty_like(x), np.empty_like(x)
