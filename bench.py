@@ -16,8 +16,11 @@ One JSON line on stdout (rank 0):
   e2e        same metric through hb_loglikelihood_batch with HOST buffers (H2D of the parameter
              batch from pinned memory + D2H of logL inside every step)
   roofline   FP64 CUDA-core roofline of k_chain_eval: 520 algorithmic flop / model point
-              / kernel duration (events on the launching stream) against the DFMA
-             peak measured on this box by hb_fp64_peak in the same run
+             (the work of the reference's formulation) / kernel duration (events on
+             the launching stream) against the DFMA peak measured on this box by hb_fp64_peak in
+             the same run.  The kernel EXECUTES far fewer flops than that count (table starter,
+             table sincos, folded harmonics), so `frac` can exceed 1; `executed` gives the
+             hardware view (FP64 instructions and pipe utilisation from the committed ncu capture)
   cpu_baseline  the reference's own loglikelihood() (oracle/_ref, or the oracle port when the
              compiled reference is absent) on all host cores over a bounded sample
 `--impl reference` times that CPU path alone on the same config and prints the same line.
@@ -43,10 +46,18 @@ METRIC = "model_point_logL_evals_per_sec"
 UNIT = "points/s"
 FLOP_PER_POINT = 520.0  # 156 plain + 6 sincos x 40 + 8 div x 14 + 1 sqrt x 14
 NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
-BYTES_PER_POINT = 8.0       # algorithmic HBM bytes: the template key store (the data stream is shared by all chains)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_chain_eval launch on C2, ncu --set full
-# (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload
-NCU_TRAFFIC_C2_BYTES = 62.551040e6 + 673.756416e6
+CHAIN_CONST_BYTES = 47 * 8  # sizeof(ChainConst): what k_chain_eval reads per chain
+# From the committed `ncu --set full` capture of one k_chain_eval launch on C2
+# (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload:
+NCU_TRAFFIC_C2_BYTES = 2.098688e6 + 2.245376e6  # dram__bytes_read.sum + dram__bytes_write.sum
+NCU_EXECUTED = {
+    "fp64_instr_per_point": 92.9,   # DFMA 55.1 + DMUL 19.7 + DADD 12.6 + DSETP 5.5 (warp instructions / 32 samples)
+    "flop_per_point": 142.5,        # 2 x DFMA + DMUL + DADD
+    "all_instr_per_point": 249.5,
+    "fp64_pipe_active": 0.521,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "issue_active": 0.700,          # smsp__issue_active.avg.pct_of_peak_sustained_active
+    "source": "profiles/r1_chain_eval_ncu_summary.txt",
+}
 
 
 def measured_hbm_peak():
@@ -366,6 +377,7 @@ def gpu_arm(args, cfg, rank, local_rank, world):
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_chain_eval_ncu_summary.txt)",
                 "hbm": hbm_block(n, N, k_ms),
                 "flop_per_point": FLOP_PER_POINT, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "executed": executed_block(n, N, k_ms, peak_tf),
                 "peak_source": "hb_fp64_peak DFMA probe on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
                 "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
@@ -387,12 +399,22 @@ def gpu_arm(args, cfg, rank, local_rank, world):
 
 
 def hbm_block(n, N, k_ms):
-    """Secondary roofline: the kernel's algorithmic HBM stream against the measured copy bandwidth
-    (it is not the bound: ~7 % of peak)."""
+    """Secondary roofline: the kernel's algorithmic HBM stream (per-chain constants in, logL out, the
+    light curve once) against the measured copy bandwidth.  It is nowhere near the bound: the
+    template never leaves the chip."""
     peak, src = measured_hbm_peak()
-    gbs = float(n) * N * BYTES_PER_POINT / (k_ms * 1e-3) * 1e-9
-    return {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bytes_per_point": BYTES_PER_POINT,
-            "peak_source": src}
+    nbytes = float(n) * (CHAIN_CONST_BYTES + 8) + 24.0 * N
+    gbs = nbytes / (k_ms * 1e-3) * 1e-9
+    return {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bytes_per_launch": nbytes,
+            "bytes_per_point": nbytes / (float(n) * N), "peak_source": src}
+
+
+def executed_block(n, N, k_ms, peak_tf):
+    """What the hardware executes (instruction counts from the committed ncu capture, time from this run)."""
+    ex = dict(NCU_EXECUTED)
+    tf = float(n) * N * ex["flop_per_point"] / (k_ms * 1e-3) * 1e-12
+    ex.update({"achieved": tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf > 0 else None})
+    return ex
 
 
 def pt_leg(args, ctx, cfg, rank, world, dist, stream):
