@@ -1,6 +1,6 @@
 // hb_kernels.cu -- sm_100a kernels of the batched heartbeat-star likelihood.
 //
-//   k_prologue    one thread per chain: parameters -> ChainConst (hb_device.cuh)
+//   k_prologue    one warp per chain: parameters -> ChainConst (hb_device.cuh)
 //   k_chain_eval  persistent CTAs, one chain at a time per CTA:
 //                   pre-sample  256 model values -> bracket of the median rank + chi^2 pivot
 //                   model pass  u at every sample; candidates in the bracket, chi^2 partial sums
@@ -19,7 +19,7 @@ namespace hb {
 
 // ---------------------------------------------------------------------------
 // One warp per chain: the lanes share out the ~50 libm calls (prologue_trans_warp), lane 0 assembles
-// and the warp stores the 43 doubles of ChainConst together.
+// and the warp stores the 47 doubles of ChainConst together.
 __global__ void __launch_bounds__(128) k_prologue(const double* __restrict__ params, int n, MagSetup ms,
                                                   ChainConst* __restrict__ out)
 {
