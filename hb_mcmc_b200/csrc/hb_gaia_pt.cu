@@ -101,6 +101,7 @@ struct GaiaWarpState {
     double logL[32];           // by chain slot
     double logP[32];           // log prior by chain slot (the reference recomputes it every step, :563)
     double beta[32];           // log of swap k's acceptance draw
+    double dbeta[32];          // (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of the adjacent pair (b, b+1)
     int idx[32];               // rung -> slot
     int b[32];                 // swap k's lower rung
     int fill[32];              // slot whose state fills rung k's history ring
@@ -132,6 +133,10 @@ k_gaia_pt_run(const GaiaPtConfig* __restrict__ cfgp, GaiaPtArrays a, unsigned it
         s.logL[lane] = a.logL[(size_t)ens * T + lane];
         s.idx[lane] = a.index[(size_t)ens * T + lane];
         s.logP[lane] = gaia_log_prior(s.x[lane], cfg);
+        if (lane + 1 < T) {
+            const double heat1 = cfg.temp[lane + 1], heat2 = cfg.temp[lane];
+            s.dbeta[lane] = (heat2 - heat1) / (heat2 * heat1);
+        }
     }
     double* hist = a.history + (size_t)rid * npast * kGaiaNpars;  // this rung's ring
     double logLmap = a.logLmap[ens];
@@ -228,8 +233,7 @@ k_gaia_pt_run(const GaiaPtConfig* __restrict__ cfgp, GaiaPtArrays a, unsigned it
                 if (T > 1) {
                     const int b = s.b[k], a2 = b + 1;
                     const int olda = s.idx[a2], oldb = s.idx[b];
-                    const double heat1 = cfg.temp[a2], heat2 = cfg.temp[b];
-                    const double lalpha = (s.logL[oldb] - s.logL[olda]) * ((heat2 - heat1) / (heat2 * heat1));
+                    const double lalpha = (s.logL[oldb] - s.logL[olda]) * s.dbeta[b];
                     if (lalpha >= s.beta[k]) {
                         s.idx[a2] = oldb;
                         s.idx[b] = olda;

@@ -172,6 +172,13 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
     __shared__ double s_beta[kPtMaxTemps];  // log of the acceptance draw
     __shared__ int s_idx[kPtMaxTemps];
     __shared__ double s_logL[kPtMaxTemps];
+    // (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop below
+    // touches shared memory only (the ladder lives in global memory: a dependent load per swap otherwise)
+    __shared__ double s_dbeta[kPtMaxTemps];
+    for (int s = lane; s + 1 < T; s += 32) {
+        const double heat1 = cfg.temp[s + 1], heat2 = cfg.temp[s];
+        s_dbeta[s] = (heat2 - heat1) / (heat2 * heat1);
+    }
     for (int s = lane; s < T; s += 32) {
         U4 c; c.x = 0x80000000u | (uint32_t)ens; c.y = iter; c.z = 2u; c.w = (uint32_t)s;
         const U4 r = philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
@@ -190,8 +197,7 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
         for (int s = 0; s < T && T > 1; s++) {
             const int b = s_b[s], a = b + 1;
             const int olda = s_idx[a], oldb = s_idx[b];
-            const double heat1 = cfg.temp[a], heat2 = cfg.temp[b];
-            const double lalpha = (s_logL[oldb] - s_logL[olda]) * ((heat2 - heat1) / (heat2 * heat1));
+            const double lalpha = (s_logL[oldb] - s_logL[olda]) * s_dbeta[b];
             if (lalpha >= s_beta[s]) {
                 s_idx[a] = oldb;
                 s_idx[b] = olda;
