@@ -1,0 +1,70 @@
+"""C-ABI behaviour at the edges: state errors, empty batches, non-finite parameters, re-used contexts."""
+import numpy as np
+import pytest
+
+import hb_mcmc_b200 as hb
+from hb_mcmc_b200 import workload as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def test_calls_before_data_fail_loudly():
+    c = hb.Context(0)
+    try:
+        with pytest.raises(hb.HBError):
+            c.loglikelihood(wl.TRUTH_A[None])
+        with pytest.raises(hb.HBError):
+            c.light_curves(wl.TRUTH_A[None])
+        # entry points that carry their own time grid need no data set
+        lc = c.calc_light_curve(wl.time_grid(100), wl.TRUTH_A)
+        assert lc.shape == (100,) and np.isfinite(lc).all()
+        with pytest.raises((hb.HBError, ValueError)):
+            c.set_data(np.zeros(3), np.zeros(4), np.zeros(3))  # ragged arrays
+        with pytest.raises(hb.HBError):
+            c.set_bracket_sigma(-1.0)
+        with pytest.raises((hb.HBError, ValueError)):
+            c.loglikelihood(np.zeros((2, 20)))  # wrong parameter count
+    finally:
+        c.close()
+
+
+def test_non_finite_parameters_give_nan_not_garbage(ctx, orc):
+    t, flux, err = wl.make_dataset(3000, wl.TRUTH_A, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    # a NaN in any one parameter: same verdict as the reference (NaN logL -- the sampler rejects such
+    # proposals, mcmc_wrapper2.c:495,505 -- or a finite value where the parameter is unused)
+    P = np.tile(wl.TRUTH_A, (22, 1))
+    for i in range(21):
+        P[1 + i, i] = np.nan
+    got = ctx.loglikelihood(P)
+    want = orc.loglikelihood_batch(t, flux, err, P)
+    assert np.isfinite(got[0])
+    assert np.array_equal(np.isnan(got), np.isnan(want)), np.flatnonzero(np.isnan(got) != np.isnan(want))
+    fin = np.isfinite(want)
+    assert np.allclose(got[fin], want[fin], rtol=1e-10)
+    # infinities (unreachable through the prior box; some are degenerate-but-finite in the reference):
+    # no crash, and a poisoned chain does not disturb its neighbours in the batch
+    Q = np.tile(wl.TRUTH_A, (43, 1))
+    k = 1
+    for i in range(21):
+        for v in (np.inf, -np.inf):
+            Q[k, i] = v
+            k += 1
+    gq = ctx.loglikelihood(Q)
+    assert gq[0] == got[0] and gq.shape == (43,)
+    clean = ctx.loglikelihood(np.tile(wl.TRUTH_A, (4, 1)))
+    assert np.all(clean == got[0])
+
+
+def test_context_reuse_across_data_sets(ctx, orc):
+    """Buffers are re-sized and re-padded on every hb_set_data: alternate long and short light curves."""
+    rng = np.random.default_rng(3)
+    P = wl.draw_chains(16, wl.TRUTH_A, lambda P: ctx.roche_overflow(P), seed=2)
+    for N in (9000, 40, 20000, 700, 9000):
+        t = np.sort(rng.uniform(0, 25, N))
+        flux = 1 + 1e-3 * rng.standard_normal(N)
+        err = np.full(N, 5e-4)
+        ctx.set_data(t, flux, err)
+        got = ctx.loglikelihood(P)
+        want = orc.loglikelihood_batch(t, flux, err, P)
+        assert np.allclose(got, want, rtol=1e-10), N

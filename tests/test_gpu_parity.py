@@ -129,12 +129,20 @@ def test_nan_roche_clamp(ctx, golden):
 def test_edge_sizes_against_oracle(ctx, orc):
     rng = np.random.default_rng(5)
     P = wl.draw_chains(8, wl.TRUTH_A, lambda P: ctx.roche_overflow(P), seed=21)
-    for N in (1, 2, 3, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 4097):
+    # the sizes straddle every switch of the kernel: one tile (256), the small-N direct path (<= 1024), the
+    # starter table (>= 4108), candidates in shared memory (<= ~7690) or in global scratch
+    for N in (1, 2, 3, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2049, 4097, 4107, 4108, 4109,
+              7600, 7700, 7800, 12001):
         t = np.sort(rng.uniform(0, 30, N))  # ragged, non-uniform sampling
         flux = 1 + 1e-3 * rng.standard_normal(N)
         err = rng.uniform(1e-4, 1e-3, N)
         ctx.set_data(t, flux, err)
         check_logL(ctx.loglikelihood(P), orc.loglikelihood_batch(t, flux, err, P))
+        if N in (3, 257, 1025, 4108, 7700):  # the light-curve output variant of the pass at the same sizes
+            lc = ctx.light_curves(P[:2])
+            for k in range(2):
+                want = orc.calc_light_curve(t, P[k])
+                assert np.nanmax(np.abs(lc[k] - want)) < 1e-11, (N, k)
     # empty data set: chi^2 is the Gaia term alone
     ctx.set_data(np.empty(0), np.empty(0), np.empty(0))
     ctx.set_mags([100, 4.5, 0.1, 0, -0.05], [0.05, 0.1, 0.1, 0.1], 1, 0)
