@@ -335,7 +335,10 @@ def gpu_arm(args, cfg, rank, local_rank, world):
     logL_dev = d_logL.cpu().numpy()
 
     # ---- end to end through the host-buffer C ABI ("e2e") ----
-    out = np.empty(n)
+    # page-locked host buffers, as the contract asks: the library DMAs them in place
+    P_pin = torch.from_numpy(P).clone().pin_memory()
+    out_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    P, out = P_pin.numpy(), out_pin.numpy()
     for _ in range(2):
         ctx.loglikelihood_into(P, out)
     barrier()

@@ -161,6 +161,17 @@ int ensure_scratch(hb_ctx* ctx, long n_points)
     return HB_OK;
 }
 
+// true when p points into page-locked host memory the device can DMA from / to directly
+bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();  // pageable memory reports an error on old drivers: clear it
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // host -> device through the pinned staging buffer, on the context stream
 int upload(hb_ctx* ctx, double* dst, const double* src, size_t n)
 {
@@ -404,15 +415,33 @@ int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, dou
     int rc;
     if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
     const size_t np = (size_t)n_chains * NPARS;
-    CK(grow_pin(ctx, np));
-    std::memcpy(ctx->h_pin, params, np * sizeof(double));
-    CK(cudaMemcpyAsync(ctx->d_params, ctx->h_pin, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are DMA'd in place;
+    // pageable ones go through the context's pinned staging buffer in chunks, so that the host copy of
+    // chunk k+1 overlaps the transfer of chunk k.
+    const bool in_pinned = is_pinned_host(params), out_pinned = is_pinned_host(logL);
+    if (in_pinned) {
+        CK(cudaMemcpyAsync(ctx->d_params, params, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CK(grow_pin(ctx, np));
+        const long n_chunks = n_chains >= 1024 ? 4 : 1;
+        for (long k = 0; k < n_chunks; k++) {
+            const size_t a = (size_t)(n_chains * k / n_chunks) * NPARS, b = (size_t)(n_chains * (k + 1) / n_chunks) * NPARS;
+            std::memcpy(ctx->h_pin + a, params + a, (b - a) * sizeof(double));
+            CK(cudaMemcpyAsync(ctx->d_params + a, ctx->h_pin + a, (b - a) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
     if ((rc = run_eval(ctx, ctx->d_params, n_chains, ctx->d_t, ctx->d_fw, ctx->N, ctx->d_logL, nullptr)) != HB_OK)
         return rc;
-    // the D2H lands in the head of the pinned buffer; stream order keeps it after the H2D read
-    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_logL, (size_t)n_chains * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(logL, ctx->h_pin, (size_t)n_chains * sizeof(double));
+    if (out_pinned) {
+        CK(cudaMemcpyAsync(logL, ctx->d_logL, (size_t)n_chains * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        // the D2H lands in the head of the pinned buffer; stream order keeps it after the H2D reads
+        CK(grow_pin(ctx, (size_t)n_chains));
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_logL, (size_t)n_chains * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(logL, ctx->h_pin, (size_t)n_chains * sizeof(double));
+    }
     return HB_OK;
 }
 

@@ -68,3 +68,20 @@ def test_context_reuse_across_data_sets(ctx, orc):
         got = ctx.loglikelihood(P)
         want = orc.loglikelihood_batch(t, flux, err, P)
         assert np.allclose(got, want, rtol=1e-10), N
+
+
+def test_pinned_and_pageable_host_buffers_agree(ctx):
+    """hb_loglikelihood_batch DMAs page-locked caller buffers in place and stages pageable ones in chunks."""
+    import torch
+    t, flux, err = wl.make_dataset(2000, wl.TRUTH_A, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    for n in (1, 7, 1023, 1024, 3001):
+        P = wl.draw_chains(n, wl.TRUTH_A, lambda P: ctx.roche_overflow(P), seed=n)
+        want = ctx.loglikelihood(P)  # pageable in, pageable out
+        Pp = torch.from_numpy(P).clone().pin_memory()
+        op = torch.empty(n, dtype=torch.float64).pin_memory()
+        ctx.loglikelihood_into(Pp.numpy(), op.numpy())  # pinned in, pinned out
+        assert np.array_equal(op.numpy(), want)
+        out = np.empty(n)
+        ctx.loglikelihood_into(Pp.numpy(), out)  # pinned in, pageable out
+        assert np.array_equal(out, want)
