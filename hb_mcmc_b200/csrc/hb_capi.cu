@@ -70,6 +70,9 @@ struct hb_ctx {
 
     // half-width, in binomial sigmas, of the median bracket taken from the pre-sample (hb_set_bracket_sigma)
     float bracket_sigma = 2.5f;
+    // largest exponent word of a Newton iterate the logL-only pass accepts before it re-evaluates the chain
+    // with the per-sample library fallback (hb_set_sincos_range)
+    int hot_hi_limit = kSincosTabHiLimit;
 };
 
 namespace {
@@ -198,7 +201,7 @@ int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, con
     CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->stream));
     if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_fw, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
-                         d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->d_sctab, ctx->stream));
+                         d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->d_sctab, ctx->hot_hi_limit, ctx->stream));
     if (ctx->time_kernels) {
         CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
         ctx->ev_valid = true;
@@ -627,6 +630,18 @@ int hb_set_bracket_sigma(hb_ctx* ctx, double sigma)
     if (!(sigma >= 0.0) || sigma > 100.0) return fail_arg(ctx, "hb_set_bracket_sigma: need 0 <= sigma <= 100");
     ctx->bracket_sigma = (float)sigma;
     ctx->generation++;  // a by-value argument of the captured step changed
+    return HB_OK;
+}
+
+int hb_set_sincos_range(hb_ctx* ctx, double max_abs)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!(max_abs > 0.0) || max_abs > 1024.0) return fail_arg(ctx, "hb_set_sincos_range: need 0 < max_abs <= 1024");
+    long long bits;
+    std::memcpy(&bits, &max_abs, sizeof bits);
+    ctx->hot_hi_limit = (int)(bits >> 32);
+    ctx->generation++;
     return HB_OK;
 }
 

@@ -806,11 +806,14 @@ __device__ __forceinline__ double kepler_table_node(int j, double e)
 // kFullWarp: all 32 lanes of the warp execute this call together (true in the model pass).
 // ktab: the chain's E(M) table (nullptr: reference starter, always valid).
 // kSinTab: use sincos_tab with the table sctab (else the polynomial sincos_lean; sctab is ignored).
-template <int V, bool kFullWarp, bool kSinTab = false>
+// kDeferRange: do not test the fast sincos' argument range per sample; the largest exponent word seen is
+// accumulated into *hi_acc and the CALLER checks it once (and redoes its work without kDeferRange if it
+// is out of range -- wild Newton iterates at e -> 1 are rare).
+template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
                                               const double rPs, const double* __restrict__ ktab,
                                               const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
-                                              double (&den)[V], double (&beta)[V])
+                                              double (&den)[V], double (&beta)[V], int* hi_acc = nullptr)
 {
     double M[V], E[V], dE[V], yr[V];
 #pragma unroll
@@ -863,7 +866,9 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
             beta[j] = rcp_fast(den[j]);
         }
     }
-    if (hi_max > (kSinTab ? kSincosTabHiLimit : kSincosHiLimit)) {  // an iterate left the fast sincos' range: library
+    if (kDeferRange) {
+        *hi_acc = max(*hi_acc, hi_max);
+    } else if (hi_max > (kSinTab ? kSincosTabHiLimit : kSincosHiLimit)) {  // an iterate left the fast sincos' range: library
 #pragma unroll
         for (int j = 0; j < V; j++) {
             kepler_point_careful(M[j], e, &cE[j], &sE[j]);
@@ -905,13 +910,14 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 
 // Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
-template <int V, bool kFullWarp, bool kSinTab = false>
+template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
 __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab,
-                                         const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V])
+                                         const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V],
+                                         int* hi_acc = nullptr)
 {
     const bool may_eclipse = (((int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
-    kepler_points<V, kFullWarp, kSinTab>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, sctab, cE, sE, den, bet);
+    kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, sctab, cE, sE, den, bet, hi_acc);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
 k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
              const double2* __restrict__ fw, int N, uint64_t* __restrict__ scratch,
              size_t scratch_stride, double* __restrict__ logL, double* __restrict__ lc_out, int* __restrict__ counter,
-             float bracket_sigma, const double2* __restrict__ sctab_g)
+             float bracket_sigma, const double2* __restrict__ sctab_g, int hot_hi_limit)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -248,8 +248,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         int nanflag = 0, c_lt = 0;
         double S0 = 0., S1 = 0., S2 = 0.;
         constexpr int V = kPointsPerThread;
+        int hi_acc = 0;  // largest sincos argument exponent of the hot pass (checked once, below)
         auto model_pass = [&](auto store_tag, auto data_tag) {
         constexpr bool kStore = decltype(store_tag)::value;
+        constexpr bool kHot = !kStore;  // the logL-only pass defers the sincos range check to the end of the chain
         constexpr bool kData = decltype(data_tag)::value;  // fw != nullptr, known at compile time in the hot variant
         nanflag = 0;
         c_lt = 0;
@@ -308,7 +310,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
 #endif
-            raw_flux<V, true, true>(cc, ktab, sctab, ts, u);
+            raw_flux<V, true, true, kHot>(cc, ktab, sctab, ts, u, &hi_acc);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -349,8 +351,20 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             if (fw != nullptr) model_pass(std::true_type{}, std::true_type{});
             else model_pass(std::true_type{}, std::false_type{});
         };
-        if (store_template) general_pass();
-        else model_pass(std::false_type{}, std::true_type{});
+        bool have_template = store_template;
+        if (store_template) {
+            general_pass();
+        } else {
+            model_pass(std::false_type{}, std::true_type{});
+            // a Newton iterate left the table sincos' range somewhere in this chain (e -> 1 only): the sums are
+            // not trustworthy; evaluate the chain again with the per-sample check and the library fallback
+            if (__syncthreads_or(hi_acc > hot_hi_limit)) {
+                if (tid == 0) sm.ctl.cnt = 0;
+                __syncthreads();
+                general_pass();
+                have_template = true;
+            }
+        }
         const int any_nan = __syncthreads_or(nanflag);
         if (any_nan) {
             if (lc_out != nullptr)
@@ -371,7 +385,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         else {
             // the bracket missed (or overflowed; ~1 % of chains by construction of the 2.5 sigma bracket):
             // evaluate the chain once more, this time storing the template, and select on that
-            if (!store_template) {
+            if (!have_template) {
                 if (tid == 0) sm.ctl.cnt = 0;
                 __syncthreads();
                 general_pass();
@@ -623,14 +637,14 @@ cudaError_t configure_eval()
 
 cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
                               int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
-                              int* counter, float bracket_sigma, const double2* sctab, cudaStream_t s)
+                              int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s)
 {
     if (n_chains <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     if (grid > n_chains) grid = n_chains;
     k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, fw, N, scratch,
-                                                                               scratch_stride, logL, lc_out, counter, bracket_sigma, sctab);
+                                                                               scratch_stride, logL, lc_out, counter, bracket_sigma, sctab, hot_hi_limit);
     return cudaGetLastError();
 }
 

@@ -37,7 +37,7 @@ cudaError_t configure_eval();
 cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, cudaStream_t s);
 cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
                               int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
-                              int* counter, float bracket_sigma, const double2* sctab, cudaStream_t s);
+                              int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s);
 cudaError_t launch_order_stat(const double* x, int n, int k, uint64_t* scratch, size_t stride, double* out,
                               cudaStream_t s);
 cudaError_t launch_subtract(double* arr, int n, const double* value, cudaStream_t s);

@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "hb_create", "hb_destroy", "hb_last_error", "hb_global_error", "hb_device_info", "hb_set_stream", "hb_sync",
     "hb_set_data", "hb_set_mags", "hb_loglikelihood_batch", "hb_loglikelihood_batch_dev", "hb_light_curve_batch",
     "hb_calc_light_curve", "hb_chain_info_batch", "hb_traj", "hb_order_statistic", "hb_remove_median", "hb_scalar", "hb_gaia_batch", "hb_fp64_peak",
-    "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count", "hb_set_bracket_sigma",
+    "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count", "hb_set_bracket_sigma", "hb_set_sincos_range",
     "hb_pt_create", "hb_pt_destroy", "hb_pt_init_random", "hb_pt_set_state", "hb_pt_step", "hb_pt_iteration",
     "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
     "hb_pt_get_counters", "hb_pt_device_logL", "hb_pt_cold_logL_dev",
@@ -79,6 +79,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_gaia_batch.argtypes = [vp, _dp, l, d, _dp, _dp, _dp, _dp]
     L.hb_fp64_peak.argtypes = [vp, d, _dp]
     L.hb_set_bracket_sigma.argtypes = [vp, d]
+    L.hb_set_sincos_range.argtypes = [vp, d]
     L.hb_time_kernels.argtypes = [vp, i]
     L.hb_last_eval_kernel_ms.argtypes = [vp, _dp]
     L.hb_launch_count.argtypes = [vp]
@@ -279,6 +280,10 @@ class Context:
     def set_bracket_sigma(self, sigma: float) -> None:
         """Half-width of the pre-sample median bracket (cost knob; results do not depend on it)."""
         self._ck(self._L.hb_set_bracket_sigma(self._h, float(sigma)))
+
+    def set_sincos_range(self, max_abs: float) -> None:
+        """|E| above which the logL-only pass re-evaluates a chain with the libm fallback (test knob)."""
+        self._ck(self._L.hb_set_sincos_range(self._h, float(max_abs)))
 
     def time_kernels(self, enable: bool = True) -> None:
         self._ck(self._L.hb_time_kernels(self._h, int(enable)))

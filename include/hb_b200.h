@@ -167,6 +167,12 @@ int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);
  * and selected exactly, so the result never depends on this value -- only the cost does (0 forces every
  * chain down the miss path; the tests use that). */
 int hb_set_bracket_sigma(hb_ctx* ctx, double sigma);
+/* Second test knob.  The logL-only pass of k_chain_eval does not range-check its table sincos per sample: it
+ * records the largest |E| any Newton iterate of the chain reached and, when that exceeds max_abs (default and
+ * maximum 1024, the validity range of the table sincos), evaluates the chain again with the per-sample check
+ * and the libm fallback.  Inside the prior box the Roche test keeps e below ~0.9985, where such iterates do not
+ * occur; lowering max_abs forces the re-evaluation so that the tests can hold it to the normal path's bits. */
+int hb_set_sincos_range(hb_ctx* ctx, double max_abs);
 /* When enabled, every likelihood / light-curve call records CUDA events around its k_chain_eval
  * launch on the launching stream; hb_last_eval_kernel_ms waits for and returns that duration. */
 int hb_time_kernels(hb_ctx* ctx, int enable);

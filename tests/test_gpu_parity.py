@@ -188,3 +188,34 @@ def test_full_size_properties(ctx, orc):
     assert rel_err(g3, got[:256]).max() < 1e-12
     # blending = 0, flux_tune = 1 and a constant offset of the data: chi^2 is a quadratic in the offset
     ctx.set_data(t, flux, err)
+
+
+def test_out_of_range_iterates_rerun_the_chain(ctx, orc):
+    """The logL-only pass checks the table sincos' argument range once per chain, not per sample, and
+    re-evaluates the chain with the per-sample libm fallback when a Newton iterate left it.  Inside the
+    prior box the Roche test caps e near 0.9985 and iterates stay far below the real limit (1024), so the
+    knob lowers the limit: every chain (limit 0.5) or the eccentric ones (limit 8) take the second pass
+    and must reproduce the reference like the first."""
+    N = 6000
+    t = wl.time_grid(N)
+    P = wl.draw_chains(48, wl.TRUTH_B, lambda P: ctx.roche_overflow(P), seed=17, e_max=0.99)
+    P[:24, 3] = np.linspace(0.85, 0.99, 24)
+    P = P[ctx.roche_overflow(P) == 0]
+    flux = orc.calc_light_curve(t, wl.TRUTH_B) + 3e-4 * np.random.default_rng(0).standard_normal(N)
+    err = np.full(N, 3e-4)
+    ctx.set_data(t, flux, err)
+    want = orc.loglikelihood_batch(t, flux, err, P)
+    base = ctx.loglikelihood(P)
+    check_logL(base, want)
+    try:
+        for limit in (0.5, 8.0, 64.0):
+            ctx.set_sincos_range(limit)
+            got = ctx.loglikelihood(P)
+            check_logL(got, want)
+            # chains the table solve converges for give the same bits on either path
+            same = got == base
+            assert same.mean() > 0.5, (limit, same.mean())
+    finally:
+        ctx.set_sincos_range(1024.0)
+    with pytest.raises(Exception):
+        ctx.set_sincos_range(4096.0)
