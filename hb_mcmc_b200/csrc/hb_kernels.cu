@@ -20,7 +20,10 @@ namespace hb {
 // ---------------------------------------------------------------------------
 // One warp per chain: the lanes share out the ~50 libm calls (prologue_trans_warp), lane 0 assembles
 // and the warp stores the 47 doubles of ChainConst together.
-__global__ void __launch_bounds__(128) k_prologue(const double* __restrict__ params, int n, MagSetup ms,
+#ifndef HB_PROLOGUE_BLOCKS
+#define HB_PROLOGUE_BLOCKS 4  // 128 registers: 16 warps per SM; fewer (184 registers) leaves 4096 chains waiting in 3.5 waves
+#endif
+__global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const double* __restrict__ params, int n, MagSetup ms,
                                                   ChainConst* __restrict__ out)
 {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
