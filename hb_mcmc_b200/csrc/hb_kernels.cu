@@ -24,8 +24,10 @@ namespace hb {
 #define HB_PROLOGUE_BLOCKS 4  // 128 registers: 16 warps per SM; fewer (184 registers) leaves 4096 chains waiting in 3.5 waves
 #endif
 __global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const double* __restrict__ params, int n, MagSetup ms,
-                                                  ChainConst* __restrict__ out)
+                                                  ChainConst* __restrict__ out, int* __restrict__ eval_counter)
 {
+    // arm the chain scheduler of the k_chain_eval launch that follows on the stream (saves a memset node)
+    if (eval_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *eval_counter = 0;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= n) return;
@@ -625,10 +627,11 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 // ---------------------------------------------------------------------------
 // launchers (plain C++ so that hb_capi.cu stays free of <<< >>>)
 // ---------------------------------------------------------------------------
-cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, cudaStream_t s)
+cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, int* eval_counter,
+                            cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out);
+    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter);
     return cudaGetLastError();
 }
 
@@ -643,9 +646,7 @@ cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* 
                               int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s)
 {
     if (n_chains <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
-    if (e != cudaSuccess) return e;
-    if (grid > n_chains) grid = n_chains;
+    if (grid > n_chains) grid = n_chains;  // *counter was zeroed by the k_prologue launch in front of this one
     k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, fw, N, scratch,
                                                                                scratch_stride, logL, lc_out, counter, bracket_sigma, sctab, hot_hi_limit);
     return cudaGetLastError();
