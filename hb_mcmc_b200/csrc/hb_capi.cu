@@ -198,7 +198,7 @@ int download(hb_ctx* ctx, double* dst, const double* src, size_t n)
 int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, const double2* d_fw,
              long N, double* d_logL, double* d_lc)
 {
-    CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->d_counter, ctx->stream));
+    CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->d_counter, ctx->grid, ctx->stream));
     if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_fw, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
                          d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->d_sctab, ctx->hot_hi_limit, ctx->stream));
@@ -516,7 +516,7 @@ int hb_chain_info_batch(hb_ctx* ctx, const double* params, long n_chains, double
     if ((rc = upload(ctx, ctx->d_params, params, (size_t)n_chains * NPARS)) != HB_OK) return rc;
     MagSetup ms = ctx->ms;
     ms.mag_data[0] = D;
-    CK(launch_prologue(ctx->d_params, (int)n_chains, ms, ctx->d_cc, nullptr, ctx->stream));
+    CK(launch_prologue(ctx->d_params, (int)n_chains, ms, ctx->d_cc, nullptr, 0, ctx->stream));
     CK(launch_chain_info(ctx->d_cc, (int)n_chains, ctx->d_aux, ctx->stream));
     ctx->launches += 2;
     return download(ctx, out, ctx->d_aux, (size_t)n_chains * 9);

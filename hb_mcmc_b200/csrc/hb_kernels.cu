@@ -24,10 +24,11 @@ namespace hb {
 #define HB_PROLOGUE_BLOCKS 4  // 128 registers: 16 warps per SM; fewer (184 registers) leaves 4096 chains waiting in 3.5 waves
 #endif
 __global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const double* __restrict__ params, int n, MagSetup ms,
-                                                  ChainConst* __restrict__ out, int* __restrict__ eval_counter)
+                                                  ChainConst* __restrict__ out, int* __restrict__ eval_counter, int eval_grid)
 {
-    // arm the chain scheduler of the k_chain_eval launch that follows on the stream (saves a memset node)
-    if (eval_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *eval_counter = 0;
+    // arm the chain scheduler of the k_chain_eval launch that follows on the stream (saves a memset node):
+    // its CTAs start on chains 0 .. grid-1 and fetch the next ones from here
+    if (eval_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *eval_counter = eval_grid;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= n) return;
@@ -169,11 +170,16 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     const uint32_t tile_bytes = kTile * sizeof(double);
 #endif
 
-    for (;;) {
-        // dynamic chain scheduler: chains differ in cost (eclipse fraction, Roche early-out)
-        if (tid == 0) s_chain = atomicAdd(counter, 1);
-        __syncthreads();
-        const int chain = s_chain;
+    for (int round = 0;; round++) {
+        // dynamic chain scheduler: chains differ in cost (eclipse fraction, Roche early-out).  The first chain of
+        // a CTA is its own index (the counter starts at gridDim.x), so a batch that fits one wave -- a PT step
+        // at the reference's size -- runs without a single atomic round trip.
+        if (round > 0) {
+            if (n_chains <= (int)gridDim.x) break;
+            if (tid == 0) s_chain = atomicAdd(counter, 1);
+            __syncthreads();
+        }
+        const int chain = round == 0 ? (int)blockIdx.x : s_chain;
         if (chain >= n_chains) break;
         {
             const double* src = reinterpret_cast<const double*>(cc_all + chain);
@@ -628,10 +634,10 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 // launchers (plain C++ so that hb_capi.cu stays free of <<< >>>)
 // ---------------------------------------------------------------------------
 cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, int* eval_counter,
-                            cudaStream_t s)
+                            int eval_grid, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter);
+    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter, eval_grid < n ? eval_grid : n);
     return cudaGetLastError();
 }
 
@@ -646,7 +652,7 @@ cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* 
                               int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s)
 {
     if (n_chains <= 0) return cudaSuccess;
-    if (grid > n_chains) grid = n_chains;  // *counter was zeroed by the k_prologue launch in front of this one
+    if (grid > n_chains) grid = n_chains;  // *counter was set to this grid by the k_prologue launch in front of this one
     k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, fw, N, scratch,
                                                                                scratch_stride, logL, lc_out, counter, bracket_sigma, sctab, hot_hi_limit);
     return cudaGetLastError();

@@ -35,7 +35,7 @@ size_t eval_smem_bytes();
 int eval_tile();  // samples per TMA tile: device time / flux / weight arrays are padded to a multiple of it
 cudaError_t configure_eval();
 cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, int* eval_counter,
-                            cudaStream_t s);
+                            int eval_grid, cudaStream_t s);
 cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
                               int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
                               int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s);
