@@ -588,11 +588,11 @@ __constant__ double kSinC[6] = {-1.66666666666666324348e-01, 8.33333333332248946
                                 2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
 __constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                 -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
-// Scalar constants of the per-sample code as constant-bank operands (a literal double costs two
-// UMOV per use): 0 fl(2 pi)  1 1/fl(2 pi)  2 magic - 0.5  3 magic = 1.5 * 2^52  4 table nodes per
-// radian  5 -1/6  6 1/6  7 fl(pi)
-__constant__ double kMisc[8] = {6.283185307179586476925, 0.15915494309189534561, 6755399441055743.5, 6755399441055744.0,
-                                162.97466172610083, -1.0 / 6.0, 1.0 / 6.0, 3.14159265358979323846};
+// Scalar constants of the per-sample code as constant-bank operands (a literal double with a non-zero
+// low word costs two moves per use): 0 fl(2 pi)  1 1/fl(2 pi)  4 E(M)-table nodes per radian  6 1/6
+// 7 fl(pi)  (2, 3, 5: unused since the magic number became an instruction immediate)
+__constant__ double kMisc[8] = {6.283185307179586476925, 0.15915494309189534561, 0.0, 0.0,
+                                162.97466172610083, 0.0, 1.0 / 6.0, 3.14159265358979323846};
 // pi/2 split in three (Cody-Waite), 2/pi, and the round-to-integer magic number 1.5 * 2^52
 __constant__ double kRed[5] = {1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983880e-33,
                                6.36619772367581382433e-01, 6755399441055744.0};
@@ -708,7 +708,7 @@ __device__ __forceinline__ double fmod_twopi(double M)
     const double am = fabs(M);
     // floor(am / y): the magic-number trick with the FMA rounding toward -inf (at 1.5 * 2^52 one ulp is 1).
     // Adding `magic - 0.5` in round-to-nearest does NOT work: that constant is not representable.
-    const double q = __fma_rd(am, kMisc[1], 6755399441055744.0) - 6755399441055744.0;
+    const double q = __fma_rd(am, kMisc[1], kMagic) - kMagic;
     double r = fma(-q, kMisc[0], am);
     if (!(r >= 0.0 && r < kMisc[0])) r = fmod_twopi_fix(q, r, am);
     return copysign(r, M);

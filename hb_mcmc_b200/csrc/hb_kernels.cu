@@ -304,13 +304,16 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         double ts_next[V];
 #pragma unroll
         for (int j = 0; j < V; j++) ts_next[j] = tsec[j * kThreads + tid];
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const int base = tile * kTile;
+        // this thread's first sample of the tile, carried in a register the compiler cannot re-derive
+        // (it would otherwise rebuild it from the tile counter and SR_TID twice per iteration)
+        int i0 = tid;
+        for (int tile = 0; tile < n_tiles; tile++, i0 += kTile) {
+            asm volatile("" : "+r"(i0));
             int idx[V];
             double ts[V], u[V], fl[V], wv[V];
 #pragma unroll
             for (int j = 0; j < V; j++) {
-                idx[j] = base + j * kThreads + tid;
+                idx[j] = i0 + j * kThreads;
                 ts[j] = ts_next[j];
                 if (tile + 1 < n_tiles) ts_next[j] = tsec[idx[j] + kTile];
                 fl[j] = wv[j] = 0.0;
