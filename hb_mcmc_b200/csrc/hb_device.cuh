@@ -52,7 +52,8 @@ struct ChainConst {
     //   c1 s + c3 s3 = s (q1 + q3 c2),          q1 = c1 + c3,  q3 = 2 c3
     //   d0 + d2 c2 + d4 c4 = r0 + c2 (d2 + r4 c2),  r0 = d0 - d4,  r4 = 2 d4
     double K0, K1, a0, a1, a2, b0, b1, q1, q3, r0, d2, r4;
-    // eclipse pre-test on squared quantities: (1 - e cos E)^2 (ci^2 + si^2 c^2) < thr, thr = ((R1 + R2)/ar)^2 (1 + 1e-9)
+    // eclipse pre-test on squared quantities: (1 - e cos E)^2 (cos^2 i + sin^2 i c^2) < thr with
+    // c^2 = (1 + c2)/2: si2 = sin^2 i / 2, ci2 = cos^2 i + sin^2 i / 2, thr = ((R1 + R2)/ar)^2 (1 + 1e-9)
     double si2, ci2, thr;
     // eclipse (radii in Rsun, sorted big/small as eclipse_area does)
     double Rb, Rs, ecl1, ecl2;  // ecl_k = Norm_k / (pi R_k^2)
@@ -450,8 +451,8 @@ __device__ inline void prologue_assemble(const double* __restrict__ p, const Mag
 
     cc.Rb = fmax(R[0], R[1]);
     cc.Rs = fmin(R[0], R[1]);
-    cc.si2 = si * si;
-    cc.ci2 = ci * ci;
+    cc.si2 = 0.5 * si * si;
+    cc.ci2 = ci * ci + 0.5 * si * si;
     {
         const double lim = (cc.Rb + cc.Rs) / cc.ar;
         cc.thr = lim * lim * (1.0 + 1e-9);
@@ -656,19 +657,18 @@ constexpr int kSinTabN = 1024;
 // Doubles whose low 32 bits are zero are encoded as immediates in FP64 SASS instructions (no constant
 // load, no register).  Used where 20 mantissa bits are enough:
 //   kMagic   1.5 * 2^52, exact
-//   kNodesA  1024 / (2 pi) to 20 bits: only picks the nearest table node, the reduction r = x - k h is exact
 //   kT5, kT4 1/120 and 1/24 to 20 bits: the Taylor terms they scale are below 1e-11 and 4e-12
-// With the 20-bit node constant the nearest-node pick drifts by |x| * 2^-20 nodes: negligible for
-// |x| <= 1024 (0.16 % of a node), so that is the validity range; beyond it (wild Newton iterates at
-// e -> 1) the caller falls back to the library path like sincos_lean does at 1e5.
+// Validity range |x| <= 1024 (checked by the caller, who falls back to the library path beyond it,
+// like sincos_lean does at 1e5): Kepler iterates are O(10), and the two-term reduction is exact to
+// 1e-19 there.
 constexpr int kSincosTabHiLimit = 0x40900000;  // high word of 1024.0
 constexpr double kMagic = 6755399441055744.0;
-constexpr double kNodesA = 0x1.45F30p+7;
 constexpr double kT5 = 0x1.11111p-7;
 constexpr double kT4 = 0x1.55555p-5;
-// 0 nodes per radian  1, 2 h = pi/512 as (pi/2 hi, lo of kRed) / 256  3-5 Taylor coefficients
+// 0 nodes per radian  1, 2 h = pi/512 as (pi/2 hi, lo of kRed) / 256  3 -1/2  4 -1/6
+// (an FMA takes one immediate at most: where two constants meet, one comes from here)
 __constant__ double kTabC[6] = {162.97466172610082624, 1.57079632679489655800e+00 / 256.0, 6.12323399573676603587e-17 / 256.0,
-                                1.0 / 120.0, -1.0 / 6.0, 1.0 / 24.0};
+                                -0.5, -1.0 / 6.0, 0.0};
 template <int V>
 __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* __restrict__ tab, double (&s_out)[V],
                                            double (&c_out)[V], int& hi_max)
@@ -676,7 +676,7 @@ __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* 
 #pragma unroll
     for (int j = 0; j < V; j++) {
         hi_max = max(hi_max, __double2hiint(x[j]) & 0x7fffffff);
-        const double t = fma(x[j], kNodesA, kMagic);
+        const double t = fma(x[j], kTabC[0], kMagic);
         const int k = __double2loint(t) & (kSinTabN - 1);  // nearest node, periodic (two's complement for x < 0)
         const double kd = t - kMagic;
         double r = fma(-kd, kTabC[1], x[j]);
@@ -684,7 +684,7 @@ __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* 
         const double2 sc = tab[k];  // {sin, cos}(k h)
         const double z = r * r;
         const double sd = fma(r * z, fma(z, kT5, kTabC[4]), r);
-        const double cd = fma(z, fma(z, kT4, -0.5), 1.0);
+        const double cd = fma(z, fma(z, kT4, kTabC[3]), 1.0);
         s_out[j] = fma(sc.y, sd, sc.x * cd);
         c_out[j] = fma(-sc.x, sd, sc.y * cd);
     }
@@ -786,7 +786,9 @@ __device__ __forceinline__ double kepler_table_guess(const double* __restrict__ 
     const double a = fma(t, t, -t);
     const double p = fma(t, y3 - y0, fma(2.0, y0, y3));
     const double q = fma(t, y1 - y2, -y1);
-    const double E = fma(fma(a, 0.5, -1.0), q, (a * kMisc[6]) * p);
+    // (a/2 - 1) q + (a/6) p, arranged so that no FMA carries two constant operands (one of them would
+    // have to be built in registers with two moves)
+    const double E = fma(a, 0.5 * q, fma(a * kMisc[6], p, -q));
     return copysign(E, m);
 }
 
@@ -925,8 +927,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
         const double X = cE[j] - cc.e;
         const double c = fma(-cc.swq, sE[j], cc.cw * X) * beta;  // cos(omega0 + nu)
         const double s = fma(cc.cwq, sE[j], cc.sw * X) * beta;   // sin(omega0 + nu)
-        const double cc2 = c * c;
-        const double c2 = fma(2.0, cc2, -1.0);                   // cos 2x
+        const double c2 = fma(c + c, c, -1.0);                   // cos 2x
 
         const double P5 = fma(fma(cc.r4, c2, cc.d2), c2, cc.r0);
         const double P4 = s * fma(cc.q3, c2, cc.q1);
@@ -938,7 +939,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
         // eclipse: the squared projected separation over a^2 against the chain's threshold (s^2 = 1 - c^2 to
         // rounding; the 1e-9 slack of thr absorbs that); the rare in-eclipse sample then forms the
         // separation exactly as the reference does (likelihood3.c:173-176, 365)
-        if (may_eclipse && den[j] * den[j] * fma(cc2, cc.si2, cc.ci2) < cc.thr) {
+        if (may_eclipse && den[j] * den[j] * fma(c2, cc.si2, cc.ci2) < cc.thr) {
             const double sc = s * cc.ci;
             const double proj2 = fma(c, c, sc * sc);
             const double rr = cc.ar * den[j];

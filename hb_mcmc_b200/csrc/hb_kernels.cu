@@ -47,16 +47,15 @@ __global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const doub
 // ---- staging of the data stream ---------------------------------------------------------------
 // The observed light curve (t, flux, 1/sigma: 24 B per sample) is read by every chain and stays
 // L2-resident.  Two ways to bring it to the math were built and measured on B200 (C2, 4096 x 20k):
-//   HB_TMA_STAGING = 0 (default)  coalesced LDG, software-pipelined one iteration ahead in registers:
-//                                 1.490 ms
+//   HB_TMA_STAGING = 0 (default)  coalesced LDG (8 B of t one iteration ahead, 16 B of {flux, 1/sigma}),
+//                                 software-pipelined in registers: 0.89 ms per call
 //   HB_TMA_STAGING = 1            TMA bulk copies (cp.async.bulk -> SASS UBLKCP) of whole 256-sample
 //                                 tiles into a 2-stage shared-memory ring, completion by mbarrier
 //                                 expect_tx/complete_tx, stage reuse by a second mbarrier the warps
-//                                 arrive on: 1.570 ms (the ring couples the warps to within one
-//                                 iteration of each other); a per-warp variant with 256-byte slices
-//                                 was 1.733 ms.
-// At ~2000 cycles of FP64 work per 24 bytes the stream is far from any bandwidth limit, so the
-// variant with the least synchronisation wins; the TMA path is kept selectable.
+//                                 arrive on: 1.09 ms (the 12 KB ring costs the fourth CTA per SM and
+//                                 couples the warps to within one iteration of each other); same bits.
+// At ~1000 cycles of FP64 work per 24 bytes the stream is far from any bandwidth limit, so the
+// variant with the least synchronisation and the smallest footprint wins; the TMA path stays selectable.
 #ifndef HB_TMA_STAGING
 #define HB_TMA_STAGING 0
 #endif
