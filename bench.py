@@ -505,6 +505,16 @@ def pt_reference_size_leg(ctx):
         if r.returncode == 0 and re.search(r"Begining main mcmc loop", r.stdout):
             out.update({"cpu_steps_per_sec": ref_iters / dt, "cpu_iterations": ref_iters, "cpu_kind": "reference",
                         "cpu_threads": 8, "cpu_note": "unmodified mcmc_wrapper2.c driver, 2 likelihood evaluations per rung per step"})
+        # the same unmodified driver with likelihood3.c replaced by libhb_likelihood3.so on the link line
+        # (25 OpenMP threads as in the reference; their concurrent calls are combined into device batches)
+        shim_exe = os.path.join(ROOT, "oracle", "_ref", "hb_mcmc_ref_shim")
+        if os.path.exists(shim_exe):
+            t0 = time.perf_counter()
+            r = subprocess.run([shim_exe, str(ref_iters), "102289966", repr(logp), "9"], capture_output=True, text=True, cwd=scr)
+            dt = time.perf_counter() - t0
+            if r.returncode == 0 and re.search(r"Begining main mcmc loop", r.stdout):
+                out.update({"shim_steps_per_sec": ref_iters / dt,
+                            "shim_note": "unmodified mcmc_wrapper2.c linked against libhb_likelihood3.so (link-level drop-in)"})
     return out
 
 

@@ -15,11 +15,14 @@
  * device model never sorts) are plain host C.
  *
  * Threading: the reference calls loglikelihood from up to 25 OpenMP threads on shared arrays
- * (mcmc_wrapper2.c:383,488-489).  All calls funnel into one context whose C ABI serialises
- * them; correctness is preserved, the batched entry point hb_loglikelihood_batch is the fast path.
+ * (mcmc_wrapper2.c:383,488-489).  Concurrent calls are COMBINED into one batched device call (see
+ * loglikelihood below); everything else funnels into one context whose C ABI serialises it.
  */
+#define _POSIX_C_SOURCE 200809L /* clock_gettime, sched_yield under -std=c99 */
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -188,28 +191,153 @@ int RocheOverflow(double *pars)
     return (int)o[8];
 }
 
+/*
+ * loglikelihood() with combining.  The reference's rung loop calls it from many OpenMP threads at once
+ * (mcmc_wrapper2.c:383,488-489), one chain per call; one device launch per call would be all latency.
+ * Concurrent callers therefore queue their request; the first one to find no leader becomes the leader,
+ * waits a few tens of microseconds for the other threads of the team to arrive (adaptively: until the
+ * queue reaches the size of the previous batch, or stops growing), evaluates the whole queue with ONE
+ * hb_loglikelihood_batch call and hands every caller its value.  A single-threaded caller pays one short
+ * wait at most (the expected batch size decays to 1).  Requests that differ in data arrays or magnitudes
+ * are evaluated group by group.
+ */
+#define SHIM_QMAX 256
+/* patience of the collecting leader: a woken OpenMP team takes some tens of microseconds to come back with its
+ * next call, and one device call costs ~50 us whatever its size -- waiting for the team pays */
+#define SHIM_IDLE_US 50.0
+#define SHIM_MAX_US 300.0
+typedef struct {
+    const double *time, *flux, *noise, *params, *mag_data, *magerr;
+    long N;
+    double out;
+    int done;
+} shim_req;
+
+static pthread_mutex_t q_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t q_cv = PTHREAD_COND_INITIALIZER;
+static shim_req *q_items[SHIM_QMAX];
+static int q_len = 0, q_leader = 0, q_expect = 1;
+/* HB_SHIM_STATS=1: batches, requests and the time spent collecting / evaluating are printed at exit */
+static long st_batches = 0, st_reqs = 0;
+static double st_collect_us = 0., st_eval_us = 0.;
+static int st_on = -1;
+static void st_print(void)
+{
+    if (st_batches > 0)
+        fprintf(stderr, "libhb_likelihood3: %ld loglikelihood calls in %ld batches (%.1f per batch), %.1f us collecting and %.1f us evaluating per batch\n",
+                st_reqs, st_batches, (double)st_reqs / st_batches, st_collect_us / st_batches, st_eval_us / st_batches);
+}
+
+static double now_us(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+static int same_group(const shim_req *a, const shim_req *b)
+{
+    return a->time == b->time && a->flux == b->flux && a->noise == b->noise && a->N == b->N &&
+           memcmp(a->mag_data, b->mag_data, 5 * sizeof(double)) == 0 && memcmp(a->magerr, b->magerr, 4 * sizeof(double)) == 0;
+}
+
+/* evaluate items[0..n) (all of one group) in one device call; g_mu serialises the context's data set */
+static void eval_group(hb_ctx *c, shim_req **items, int n)
+{
+    static double *pbuf = NULL, *obuf = NULL;
+    static int cap = 0;
+    pthread_mutex_lock(&g_mu);
+    if (n > cap) {
+        cap = n + 64;
+        pbuf = (double *)realloc(pbuf, (size_t)cap * NPARS * sizeof(double));
+        obuf = (double *)realloc(obuf, (size_t)cap * sizeof(double));
+    }
+    const shim_req *r0 = items[0];
+    const long N = r0->N;
+    size_t bytes = (size_t)(N > 0 ? N : 0) * sizeof(double);
+    if (N != g_n || memcmp(r0->time, g_t, bytes) || memcmp(r0->flux, g_f, bytes) || memcmp(r0->noise, g_e, bytes)) {
+        g_t = (double *)realloc(g_t, bytes + 8);
+        g_f = (double *)realloc(g_f, bytes + 8);
+        g_e = (double *)realloc(g_e, bytes + 8);
+        memcpy(g_t, r0->time, bytes); memcpy(g_f, r0->flux, bytes); memcpy(g_e, r0->noise, bytes);
+        g_n = N;
+        CK(hb_set_data(c, r0->time, r0->flux, r0->noise, N));
+    }
+    CK(hb_set_mags(c, r0->mag_data, r0->magerr, g_use_gmag, g_use_color));
+    for (int i = 0; i < n; i++) memcpy(pbuf + (size_t)i * NPARS, items[i]->params, NPARS * sizeof(double));
+    CK(hb_loglikelihood_batch(c, pbuf, n, obuf));
+    for (int i = 0; i < n; i++) items[i]->out = obuf[i];
+    pthread_mutex_unlock(&g_mu);
+}
+
 double loglikelihood(double time[], double lightcurve[], double noise[], long N, double params[], double mag_data[],
                      double magerr[])
 {
     hb_ctx *c = ctx();
-    double out = 0.;
-    pthread_mutex_lock(&g_mu);
     /* side effect of likelihood3.c:824-827: the caller's noise[] is clamped in place (quirk Q2) */
     for (long i = 0; i < N; i++)
         if (noise[i] < 1.e-5) noise[i] = 1.e-5;
-    size_t bytes = (size_t)(N > 0 ? N : 0) * sizeof(double);
-    if (N != g_n || memcmp(time, g_t, bytes) || memcmp(lightcurve, g_f, bytes) || memcmp(noise, g_e, bytes)) {
-        g_t = (double *)realloc(g_t, bytes + 8);
-        g_f = (double *)realloc(g_f, bytes + 8);
-        g_e = (double *)realloc(g_e, bytes + 8);
-        memcpy(g_t, time, bytes); memcpy(g_f, lightcurve, bytes); memcpy(g_e, noise, bytes);
-        g_n = N;
-        CK(hb_set_data(c, time, lightcurve, noise, N));
+    shim_req me = {time, lightcurve, noise, params, mag_data, magerr, N, 0., 0};
+
+    pthread_mutex_lock(&q_mu);
+    while (q_len >= SHIM_QMAX) pthread_cond_wait(&q_cv, &q_mu);
+    q_items[q_len++] = &me;
+    while (!me.done) {
+        if (q_leader) { /* someone is collecting or evaluating: wait for my value, or for the leadership */
+            pthread_cond_wait(&q_cv, &q_mu);
+            continue;
+        }
+        q_leader = 1; /* lead ONE batch; my own request is still queued, so it is part of it */
+        if (st_on < 0) {
+            st_on = getenv("HB_SHIM_STATS") != NULL;
+            if (st_on) atexit(st_print);
+        }
+        const double st_t0 = st_on ? now_us() : 0.;
+        /* collect: wait until the queue holds as many requests as the previous batch did, or stops growing */
+        if (q_expect > 1 || q_len > 1) {
+            const double t0 = now_us();
+            int last = q_len;
+            double t_last = t0;
+            while (q_len < q_expect) {
+                pthread_mutex_unlock(&q_mu);
+                sched_yield();
+                pthread_mutex_lock(&q_mu);
+                const double t = now_us();
+                if (q_len != last) { last = q_len; t_last = t; }
+                if (t - t_last > SHIM_IDLE_US || t - t0 > SHIM_MAX_US) break;
+            }
+        }
+        shim_req *batch[SHIM_QMAX];
+        const int n = q_len;
+        memcpy(batch, q_items, (size_t)n * sizeof(batch[0]));
+        q_len = 0;
+        q_expect = n >= q_expect ? n : q_expect - 1; /* follows the team size up at once, down slowly */
+        pthread_cond_broadcast(&q_cv);                          /* room in the queue again */
+        pthread_mutex_unlock(&q_mu);
+        const double st_t1 = st_on ? now_us() : 0.;
+        /* evaluate group by group (normally one group) */
+        int used[SHIM_QMAX] = {0};
+        for (int i = 0; i < n; i++) {
+            if (used[i]) continue;
+            shim_req *grp[SHIM_QMAX];
+            int m = 0;
+            for (int j = i; j < n; j++)
+                if (!used[j] && same_group(batch[i], batch[j])) { grp[m++] = batch[j]; used[j] = 1; }
+            eval_group(c, grp, m);
+        }
+        pthread_mutex_lock(&q_mu);
+        if (st_on) {
+            st_batches++;
+            st_reqs += n;
+            st_collect_us += st_t1 - st_t0;
+            st_eval_us += now_us() - st_t1;
+        }
+        for (int i = 0; i < n; i++) batch[i]->done = 1;
+        q_leader = 0;
+        pthread_cond_broadcast(&q_cv); /* results are in; whoever is still queued may lead the next batch */
     }
-    CK(hb_set_mags(c, mag_data, magerr, g_use_gmag, g_use_color));
-    CK(hb_loglikelihood_batch(c, params, 1, &out));
-    pthread_mutex_unlock(&g_mu);
-    return out;
+    pthread_mutex_unlock(&q_mu);
+    return me.out;
 }
 
 /* ---- likelihood3.h:88-89: constant tables (likelihood3.c:986-1211) ------------------------ */

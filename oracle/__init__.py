@@ -39,6 +39,13 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True, stdout=sys.stderr)
     if ref:
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True, stdout=sys.stderr)
+        if os.path.exists("/root/reference/src/mcmc_wrapper2.c"):
+            # the unmodified driver, stand-alone (statistical goldens, the PT baseline of bench.py) and linked
+            # against the product's link-level drop-in libhb_likelihood3.so when that has been built
+            targets = ["ref_driver"]
+            if os.path.exists(os.path.join(os.path.dirname(HERE), "hb_mcmc_b200", "csrc", "libhb_likelihood3.so")):
+                targets.append("ref_driver_shim")
+            subprocess.run(["make", "-s", "-C", HERE] + targets, check=True, stdout=sys.stderr)
 
 
 def have_reference() -> bool:

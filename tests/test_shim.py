@@ -127,3 +127,74 @@ def test_shim_matches_golden(shim, golden):
     tp = golden["kat_traj_pars"].copy()
     shim.traj(p(t), p(tp), *[p(o) for o in outs], 1000)
     assert np.abs(outs[3] / golden["kat_traj_r"] - 1).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_are_combined_and_correct(shim, golden):
+    """The reference's OpenMP rung loop calls loglikelihood from many threads at once (mcmc_wrapper2.c:383,
+    488-489).  The shim combines concurrent calls into one batched device call: every caller must get the
+    value a lone call gets, whatever the interleaving, including callers with another data set."""
+    import threading
+    t = wl.time_grid(1000)
+    fl = golden["n1000_flux"].copy()
+    er = np.full(1000, 3e-4)
+    md0, me0 = np.array([1000.0, 1, 1, 1, 1]), np.full(4, 1e15)
+    P = golden["n1000_params"][:48].copy()
+    t2 = wl.time_grid(777)
+    fl2, er2 = fl[:777].copy(), er[:777].copy()
+    want = np.array([shim.loglikelihood(p(t), p(fl), p(er), 1000, p(P[k].copy()), p(md0), p(me0)) for k in range(48)])
+    want2 = np.array([shim.loglikelihood(p(t2), p(fl2), p(er2), 777, p(P[k].copy()), p(md0), p(me0)) for k in range(8)])
+    got = np.full((3, 48), np.nan)
+    got2 = np.full(8, np.nan)
+
+    def worker(tid, nthreads):
+        for rep in range(3):
+            for k in range(tid, 48, nthreads):
+                pk = P[k].copy()
+                got[rep, k] = shim.loglikelihood(p(t), p(fl), p(er), 1000, p(pk), p(md0), p(me0))
+        if tid < 8:  # a second data set mixed into the same stream of calls
+            pk = P[tid].copy()
+            got2[tid] = shim.loglikelihood(p(t2), p(fl2), p(er2), 777, p(pk), p(md0), p(me0))
+
+    for nthreads in (2, 8, 16):
+        got[:] = np.nan
+        got2[:] = np.nan
+        ths = [threading.Thread(target=worker, args=(i, nthreads)) for i in range(nthreads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join(timeout=120)
+            assert not th.is_alive(), "a caller never got its value"
+        for rep in range(3):
+            assert np.array_equal(got[rep], want, equal_nan=True), nthreads
+        nmix = min(8, nthreads)
+        assert np.array_equal(got2[:nmix], want2[:nmix], equal_nan=True), nthreads
+
+
+@pytest.mark.gpu
+def test_unmodified_driver_on_the_shim_walks_the_reference_chain(tmp_path):
+    """End to end at link level: the UNMODIFIED mcmc_wrapper2.c (oracle/_ref/hb_mcmc_ref_shim: only its
+    /scratch prefix moved, likelihood3.c replaced by libhb_likelihood3.so on the link line) against the same
+    file compiled with the reference's own likelihood3.c (oracle/_ref/hb_mcmc_ref).  Same seeds, same ran2
+    streams: as long as the likelihoods agree to far more digits than any accept decision needs, the two
+    runs walk the same chain, so their chain files agree line by line."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    cpu, gpu = os.path.join(ref_dir, "hb_mcmc_ref"), os.path.join(ref_dir, "hb_mcmc_ref_shim")
+    lc = os.path.join(ref_dir, "scratch", "data", "lightcurves", "folded_lightcurves", "102289966_new.txt")
+    if not (os.path.exists(cpu) and os.path.exists(gpu) and os.path.exists(lc)):
+        pytest.skip("oracle/_ref drivers not built (make -C oracle ref_driver ref_driver_shim)")
+    build.build_lib()
+    build.build_shim()
+    chain_file = os.path.join(ref_dir, "scratch", "data", "chains", "chain.102289966_gmag_OMP_71.dat")
+    rows = []
+    for exe in (cpu, gpu):  # same run id = same seeds (mcmc_wrapper2.c:91); the second run rewrites the file
+        r = subprocess.run([exe, "400", "102289966", "0.7960497", "71"], cwd=ref_dir, capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, HB_SHIM_STATS="1"))
+        assert "logL=" in r.stdout, r.stdout[-400:] + r.stderr[-400:]
+        rows.append(np.loadtxt(chain_file, ndmin=2))
+        if exe == gpu:
+            m = re.search(r"(\d+) loglikelihood calls in (\d+) batches", r.stderr)
+            assert m and int(m.group(1)) > 8 * int(m.group(2)), r.stderr[-300:]  # the team's calls were combined
+    a, b = rows
+    assert a.shape == b.shape and a.shape[0] >= 4
+    assert np.allclose(a, b, rtol=1e-9, atol=1e-12), np.abs(a - b).max()
