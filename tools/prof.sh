@@ -7,4 +7,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 $CMD > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_chain_eval -s 4 -c 1 -o gpurun_out/prof_chain_eval -f $CMD > gpurun_out/ncu_full.log 2>&1
 tail -1 gpurun_out/ncu_full.log
-python tools/configs.py > gpurun_out/configs.txt 2>&1; cat gpurun_out/configs.txt
+python tests/tools/configs.py > gpurun_out/configs.txt 2>&1; cat gpurun_out/configs.txt
