@@ -10,7 +10,12 @@ if os.environ.get("HB_LIB"):
     hblib._lib = hblib.load_library(os.environ["HB_LIB"])
 ctx = hb.Context(0)
 worst = 0
-for truth, N, emax, n, seed in ((wl.TRUTH_A, 20000, 0.95, 512, 1), (wl.TRUTH_B, 20000, 0.99, 512, 2), (wl.TRUTH_A, 1001, 0.99, 1024, 3), (wl.TRUTH_B, 50000, 0.97, 128, 4), (wl.TRUTH_A, 375, 0.9, 2048, 5)):
+REPS = int(os.environ.get("REPS", "1"))
+over = 0
+total = 0
+for rep in range(REPS):
+  for truth, N, emax, n, seed0 in ((wl.TRUTH_A, 20000, 0.95, 512, 1), (wl.TRUTH_B, 20000, 0.99, 512, 2), (wl.TRUTH_A, 1001, 0.99, 1024, 3), (wl.TRUTH_B, 50000, 0.97, 128, 4), (wl.TRUTH_A, 375, 0.9, 2048, 5)):
+    seed = seed0 + 100 * rep
     t, fl, er = wl.make_dataset(N, truth, R.calc_light_curve)
     ctx.set_data(t, fl, er)
     P = wl.draw_chains(n, truth, ctx.roche_overflow, seed=seed, e_max=emax)
@@ -27,4 +32,6 @@ for truth, N, emax, n, seed in ((wl.TRUTH_A, 20000, 0.95, 512, 1), (wl.TRUTH_B, 
     i = np.nanargmax(rel)
     print(f"truth e={truth[3]:.3f} N={N:6d} n={len(P):5d} emax={emax}: max rel {np.nanmax(rel):.3e} (e={P[i,3]:.3f}, logL={o[i]:.4g})  median {np.nanmedian(rel):.2e}  nan {np.isnan(o).sum()}")
     worst = max(worst, np.nanmax(rel))
-print("WORST", worst)
+    over += int(np.nansum(rel > 1e-10))
+    total += len(P)
+print("WORST", worst, "chains", total, "above 1e-10:", over)
