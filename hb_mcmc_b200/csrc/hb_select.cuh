@@ -192,22 +192,35 @@ __device__ __noinline__ uint64_t block_select_key(const uint64_t* keys, int n, i
         const int cap = bufs[pick].cap;
 
         // ---- count + compact pass ----
+        // The keys usually sit in the CTA's global scratch (L2): a thread's loads are issued eight at a time,
+        // so the pass costs a few memory latencies instead of one per key.
         int c_lt = 0;
-        for (int base = 0; base < cur_n; base += kThreads) {
-            const int i = base + tid;
-            const bool valid = i < cur_n;
-            const uint64_t x = valid ? cur[i] : 0ull;
-            c_lt += (valid & (x < lo));
-            const bool inr = valid & (x >= lo) & (x <= hi);
-            const unsigned mask = __ballot_sync(0xffffffffu, inr);
-            if (mask) {
-                const int leader = __ffs(mask) - 1;
-                int basepos = 0;
-                if (lane == leader) basepos = atomicAdd(&ctl.cnt, __popc(mask));
-                basepos = __shfl_sync(0xffffffffu, basepos, leader);
-                if (inr) {
-                    const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
-                    if (pos < cap) out[pos] = x;
+        constexpr int kBatch = 8;
+        for (int base = 0; base < cur_n; base += kBatch * kThreads) {
+            uint64_t xs[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; u++) {
+                const int i = base + u * kThreads + tid;
+                xs[u] = (i < cur_n) ? cur[i] : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; u++) {
+                const int i = base + u * kThreads + tid;
+                if (base + u * kThreads >= cur_n) break;  // uniform: no lane of the block has work left
+                const bool valid = i < cur_n;
+                const uint64_t x = xs[u];
+                c_lt += (valid & (x < lo));
+                const bool inr = valid & (x >= lo) & (x <= hi);
+                const unsigned mask = __ballot_sync(0xffffffffu, inr);
+                if (mask) {
+                    const int leader = __ffs(mask) - 1;
+                    int basepos = 0;
+                    if (lane == leader) basepos = atomicAdd(&ctl.cnt, __popc(mask));
+                    basepos = __shfl_sync(0xffffffffu, basepos, leader);
+                    if (inr) {
+                        const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
+                        if (pos < cap) out[pos] = x;
+                    }
                 }
             }
         }
