@@ -150,6 +150,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     uint64_t* gbufB = tmpl + scratch_stride;
     uint64_t* gbufC = tmpl + 2 * scratch_stride;
     const SelectBuf bufs[4] = {{sm.candB, kCandB}, {sm.candA, kCandA}, {gbufB, N}, {gbufC, N}};
+    static_assert(kCandB >= 2 * kThreads, "candB doubles as the work area of block_select_hist");
     __shared__ int s_chain;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int krank = median_rank(N);
@@ -393,8 +394,13 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         __syncthreads();
         const uint32_t seed2 = (uint32_t)cc.seed ^ 0x9e3779b9u;
         uint64_t mkey;
-        if (krank >= c_lt && krank < c_lt + c_in && c_in <= cand_cap)
-            mkey = block_select_key<kThreads>(cand, c_in, krank - c_lt, sm.ctl, bufs, 4, seed2);
+        if (krank >= c_lt && krank < c_lt + c_in && c_in <= cand_cap) {
+            // the candidates lie between two order statistics of the pre-sample: one histogram pass finds the
+            // bin of the median (hb_select.cuh); sampling rounds only when that fails (ties) or there is no bracket
+            if (!(bracketed && c_in > kThreads &&
+                  block_select_hist<kThreads>(cand, c_in, krank - c_lt, lo, hi, sm.ctl, sm.candB, &mkey)))
+                mkey = block_select_key<kThreads>(cand, c_in, krank - c_lt, sm.ctl, bufs, 4, seed2);
+        }
         else {
             // the bracket missed (or overflowed; ~1 % of chains by construction of the 2.5 sigma bracket):
             // evaluate the chain once more, this time storing the template, and select on that

@@ -140,6 +140,84 @@ __device__ __noinline__ uint64_t select_bisect(const uint64_t* keys, int n, int 
     return lo;
 }
 
+// One-shot select for keys known to lie in [lo, hi] with a roughly uniform density -- the candidates the
+// model pass of k_chain_eval collects between two order statistics of its pre-sample.  Instead of two
+// more sample / sort / compact rounds: histogram the keys over kThreads equal bins of [lo, hi] (pass A),
+// find the bin holding rank k by a block scan, gather that bin (pass B) and sort it.  Both passes read
+// the keys eight loads at a time.  Returns false -- nothing decided, the caller falls back to
+// block_select_key -- when the bin holds more than kThreads keys (ties, a plateau) or [lo, hi] is degenerate.
+// `work` is scratch shared memory of at least 2 * kThreads 64-bit words.
+template <int kThreads>
+__device__ __noinline__ bool block_select_hist(const uint64_t* keys, int n, int k, double lo, double hi,
+                                               SelectCtl<kThreads>& ctl, uint64_t* work, uint64_t* result)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int* hist = reinterpret_cast<int*>(work);  // kThreads bins
+    uint64_t* surv = work + kThreads;          // kThreads keys
+    const double scale = (double)kThreads / (hi - lo);
+    if (!(scale > 0.0) || !(scale < 1e300)) return false;  // hi == lo, or a non-finite bound (uniform decision)
+    hist[tid] = 0;
+    if (tid == 0) ctl.cnt = 0;
+    __syncthreads();
+    constexpr int kBatch = 8;
+    auto bin_of = [&](uint64_t x) {
+        const int b = (int)((dunkey(x) - lo) * scale);  // monotone in x; the same value in both passes
+        return min(max(b, 0), kThreads - 1);
+    };
+    for (int base = 0; base < n; base += kBatch * kThreads) {  // pass A: histogram
+        uint64_t xs[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+            const int i = base + u * kThreads + tid;
+            xs[u] = (i < n) ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+            if (base + u * kThreads + tid < n) atomicAdd(&hist[bin_of(xs[u])], 1);
+    }
+    __syncthreads();
+    // block-wide inclusive scan of the bins (one per thread)
+    const int h = hist[tid];
+    int incl = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) ctl.ired[wid] = incl;
+    __syncthreads();
+    int offset = 0;
+    for (int w = 0; w < wid; w++) offset += ctl.ired[w];
+    incl += offset;
+    const int excl = incl - h;
+    if (excl <= k && k < incl) {  // exactly one thread: its bin holds rank k
+        ctl.result = (uint64_t)tid;
+        ctl.lo = (uint64_t)excl;
+        ctl.hi = (uint64_t)h;
+    }
+    __syncthreads();
+    const int bin = (int)ctl.result, below = (int)ctl.lo, count = (int)ctl.hi;
+    if (count > kThreads) return false;
+    for (int base = 0; base < n; base += kBatch * kThreads) {  // pass B: gather the bin
+        uint64_t xs[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+            const int i = base + u * kThreads + tid;
+            xs[u] = (i < n) ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+            if (base + u * kThreads + tid < n && bin_of(xs[u]) == bin) surv[atomicAdd(&ctl.cnt, 1)] = xs[u];
+    }
+    __syncthreads();
+    const uint64_t mine = (tid < count) ? surv[tid] : ~0ull;
+    const uint64_t srt = block_sort<kThreads>(mine, ctl.xch);
+    if (tid == k - below) ctl.result = srt;
+    __syncthreads();
+    *result = ctl.result;
+    return true;
+}
+
 // Exact k-th smallest (0-based) of keys[0..n).  `keys` may live in global or shared memory and
 // is not modified.  `bufs` are nb scratch key buffers (any mix of shared / global) that must not
 // alias `keys`; at least two, and the largest must hold n keys.  Returns the key to every thread.
