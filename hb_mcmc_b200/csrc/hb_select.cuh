@@ -159,13 +159,14 @@ __device__ __noinline__ bool block_select_hist(const uint64_t* keys, int n, int 
     hist[tid] = 0;
     if (tid == 0) ctl.cnt = 0;
     __syncthreads();
-    constexpr int kBatch = 8;
+    constexpr int kBatch = 16;  // one batch covers 16 * kThreads keys: the usual candidate count, read ONCE
     auto bin_of = [&](uint64_t x) {
         const int b = (int)((dunkey(x) - lo) * scale);  // monotone in x; the same value in both passes
         return min(max(b, 0), kThreads - 1);
     };
+    const bool one_batch = n <= kBatch * kThreads;
+    uint64_t xs[kBatch];
     for (int base = 0; base < n; base += kBatch * kThreads) {  // pass A: histogram
-        uint64_t xs[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; u++) {
             const int i = base + u * kThreads + tid;
@@ -198,21 +199,43 @@ __device__ __noinline__ bool block_select_hist(const uint64_t* keys, int n, int 
     __syncthreads();
     const int bin = (int)ctl.result, below = (int)ctl.lo, count = (int)ctl.hi;
     if (count > kThreads) return false;
-    for (int base = 0; base < n; base += kBatch * kThreads) {  // pass B: gather the bin
-        uint64_t xs[kBatch];
+    // pass B: gather the bin (from the registers of pass A when one batch held everything)
+    for (int base = 0; base < n; base += kBatch * kThreads) {
+        if (!one_batch) {
 #pragma unroll
-        for (int u = 0; u < kBatch; u++) {
-            const int i = base + u * kThreads + tid;
-            xs[u] = (i < n) ? keys[i] : 0ull;
+            for (int u = 0; u < kBatch; u++) {
+                const int i = base + u * kThreads + tid;
+                xs[u] = (i < n) ? keys[i] : 0ull;
+            }
         }
 #pragma unroll
         for (int u = 0; u < kBatch; u++)
             if (base + u * kThreads + tid < n && bin_of(xs[u]) == bin) surv[atomicAdd(&ctl.cnt, 1)] = xs[u];
     }
     __syncthreads();
-    const uint64_t mine = (tid < count) ? surv[tid] : ~0ull;
-    const uint64_t srt = block_sort<kThreads>(mine, ctl.xch);
-    if (tid == k - below) ctl.result = srt;
+    if (count <= 32) {
+        // a handful of keys (the usual case): warp 0 sorts them with shuffles alone
+        if (wid == 0) {
+            uint64_t key = (lane < count) ? surv[lane] : ~0ull;
+#pragma unroll
+            for (int kk = 2; kk <= 32; kk <<= 1) {
+                const bool descending = (lane & kk) != 0;
+#pragma unroll
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const uint32_t olo = __shfl_xor_sync(0xffffffffu, (uint32_t)key, j);
+                    const uint32_t ohi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
+                    const uint64_t other = ((uint64_t)ohi << 32) | olo;
+                    const bool take_min = descending == ((lane & j) != 0);
+                    key = ((other < key) == take_min) ? other : key;
+                }
+            }
+            if (lane == k - below) ctl.result = key;
+        }
+    } else {
+        const uint64_t mine = (tid < count) ? surv[tid] : ~0ull;
+        const uint64_t srt = block_sort<kThreads>(mine, ctl.xch);
+        if (tid == k - below) ctl.result = srt;
+    }
     __syncthreads();
     *result = ctl.result;
     return true;
