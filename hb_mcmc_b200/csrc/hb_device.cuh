@@ -804,6 +804,35 @@ __device__ __forceinline__ double kepler_table_node(int j, double e)
     return E[0];
 }
 
+// The whole table of one chain, built by the CTA (blockDim.x = kThreads threads, all of them call).  Entry j
+// holds node j - 1.  Nodes 1 .. N/2 are solved, two per thread as ONE interleaved latency chain (entries
+// 2 + tid and 2 + kThreads + tid); node 0 is E = 0, node -1 mirrors node 1, nodes above N/2 mirror N - n.
+// Out of line: it runs once per chain and must not weigh on the register allocation of the sample loop.
+#ifndef HB_HOST_EMUL  // (the host emulation fills its table node by node with kepler_table_node)
+template <int kThreads>
+static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab, double e)
+{
+    static_assert(2 + 2 * kThreads >= kTableSolved, "two table entries per thread must cover the solved half");
+    const int tid = threadIdx.x;
+    const int j[2] = {2 + tid, min(2 + kThreads + tid, kTableSolved - 1)};
+    const double m[2] = {(double)(j[0] - 1) * (kTwoPi / (double)kTableN), (double)(j[1] - 1) * (kTwoPi / (double)kTableN)};
+    double E[2] = {kepler_starter(m[0], e), kepler_starter(m[1], e)}, s[2], c[2];
+    int hi = 0;
+    for (int k = 0; k < 6; k++) {  // quadratic convergence: a starter only needs ~1e-10
+        sincos_lean<2>(E, s, c, hi);
+#pragma unroll
+        for (int i = 0; i < 2; i++) E[i] -= div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
+    }
+    ktab[j[0]] = E[0];
+    ktab[j[1]] = E[1];
+    if (tid == 0) ktab[1] = 0.0;
+    __syncthreads();
+    if (tid == 0) ktab[0] = -ktab[2];
+    for (int i = kTableSolved + tid; i < kTableSize; i += kThreads) ktab[i] = kTwoPi - ktab[kTableN + 2 - i];
+    __syncthreads();
+}
+#endif
+
 // likelihood3.c:149-160 for V samples: outputs cos E, sin E, den = 1 - e cos E and beta = 1/den.
 // kFullWarp: all 32 lanes of the warp execute this call together (true in the model pass).
 // ktab: the chain's E(M) table (nullptr: reference starter, always valid).

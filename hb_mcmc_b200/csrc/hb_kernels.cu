@@ -205,12 +205,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= 4 * kTableSize);
         const double* ktab = use_table ? sm.ktab : nullptr;
         if (use_table) {
-            const double e = cc.e;
-            for (int j = tid; j < kTableSolved; j += kThreads) sm.ktab[j] = kepler_table_node(j, e);
-            __syncthreads();
-            // entry j holds node j - 1; node n > N/2 mirrors node N - n: entry j <- 2 pi - entry (N + 2 - j)
-            for (int j = kTableSolved + tid; j < kTableSize; j += kThreads) sm.ktab[j] = kTwoPi - sm.ktab[kTableN + 2 - j];
-            __syncthreads();
+            build_kepler_table<kThreads>(sm.ktab, cc.e);
         }
 
         // ---- pre-sample: bracket of the median rank + expansion point ----
