@@ -49,13 +49,13 @@ NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
 CHAIN_CONST_BYTES = 47 * 8  # sizeof(ChainConst): what k_chain_eval reads per chain
 # From the committed `ncu --set full` capture of one k_chain_eval launch on C2
 # (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload:
-NCU_TRAFFIC_C2_BYTES = 2.106112e6 + 3.046144e6  # dram__bytes_read.sum + dram__bytes_write.sum
+NCU_TRAFFIC_C2_BYTES = 2.742784e6 + 5.529344e6  # dram__bytes_read.sum + dram__bytes_write.sum
 NCU_EXECUTED = {
-    "fp64_instr_per_point": 92.9,   # DFMA 55.1 + DMUL 18.7 + DADD 13.6 + DSETP 5.5 (warp instructions / 32 samples)
-    "flop_per_point": 142.5,        # 2 x DFMA + DMUL + DADD
-    "all_instr_per_point": 235.0,
-    "fp64_pipe_active": 0.542,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
-    "issue_active": 0.686,          # smsp__issue_active.avg.pct_of_peak_sustained_active
+    "fp64_instr_per_point": 93.4,   # DFMA 55.0 + DMUL 19.0 + DADD 13.9 + DSETP 5.5 (warp instructions / 32 samples)
+    "flop_per_point": 142.9,        # 2 x DFMA + DMUL + DADD
+    "all_instr_per_point": 218.3,
+    "fp64_pipe_active": 0.595,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "issue_active": 0.696,          # smsp__issue_active.avg.pct_of_peak_sustained_active
     "source": "profiles/r1_chain_eval_ncu_summary.txt",
 }
 
