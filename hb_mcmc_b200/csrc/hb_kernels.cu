@@ -124,18 +124,26 @@ __device__ __forceinline__ int median_rank(int N)
     return r < N ? r : N - 1;
 }
 
-// One chain at a time per CTA (persistent CTAs, atomic chain scheduler).  Per chain:
+// One chain at a time per CTA (persistent CTAs; first chain = block index, further ones from an atomic
+// counter).  Per chain:
+//   table       E(M) starter table of the chain in shared memory (e <= 0.8, build_kepler_table)
 //   pre-sample  every thread evaluates the model at one jittered-stride sample; the block sorts
 //               the kThreads values; sample order statistics give a bracket [lo, hi] around the
 //               reference's median rank and the expansion point u0 of the chi^2.
-//   model pass  u_i at every sample (the FP64-bound part): key stored to scratch, #(u < lo)
-//               counted, u in [lo, hi] appended to a shared-memory candidate list, and the three
-//               sums of   chi^2(m) = S0 + 2 d S1 + d^2 S2,   d = -A (m - u0),
+//   model pass  u_i at every sample (the FP64-bound part): #(u < lo) counted, u in [lo, hi] appended to a
+//               candidate list (shared memory, or the CTA's global scratch for long light curves), and the
+//               three sums of   chi^2(m) = S0 + 2 d S1 + d^2 S2,   d = -A (m - u0),
 //               S0 = sum ((A (u_i - u0) + ft - f_i) w_i)^2,  S1 = sum (A (u_i - u0) + ft - f_i) w_i^2,
-//               S2 = sum w_i^2   (model_i = A (u_i - m) + ft, A = ft (1 - blending), likelihood3.c:681-685)
-//   select      exact order statistic among the candidates (hb_select.cuh); the stored template
-//               is only re-read when the bracket missed (rare) or when the caller wants the
-//               light curve itself (lc_out).
+//               S2 = sum w_i^2   (model_i = A (u_i - m) + ft, A = ft (1 - blending), likelihood3.c:681-685).
+//               Two compile-time variants: the logL-only pass keeps everything on chip; the general one
+//               also stores the template keys (light-curve output, small N, re-runs) and checks per sample
+//               what the hot one checks per chain (sincos range, NaN).
+//   select      exact order statistic among the candidates: one histogram pass (block_select_hist), else
+//               sampling rounds (block_select_key); a chain whose bracket missed or whose Newton iterates
+//               left the table sincos' range is evaluated once more with the general pass.
+// Between chains a CTA sits at barriers while its latency-bound neighbours on the SM cannot speed up, so
+// the per-chain phases count in full: clock64 gives table 3 k, pre-sample 6-8 k, pass 120-220 k, select
+// 8-13 k, final 2 k cycles at N = 20 000.
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
 k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
