@@ -26,6 +26,16 @@ namespace hb {
 constexpr int NPARS = 21;  // likelihood3.h:20
 constexpr int kNewtonUnroll = HB_NEWTON_UNROLL;  // 1 = rolled Newton loop (small I-cache footprint)
 
+// Which samples may start Newton from the per-chain E(M) table (see the table section below).
+// Chains up to kTableAllE use the table at every sample.  Between kTableAllE and kTableMaxE the reference's
+// five steps still converge to rounding EXCEPT within |M| <= 0.0493 of periastron (largest at e = 0.91;
+// tests/tools/kepler_convergence_scan.c, M on a log + uniform grid, e = 0.80 .. 0.99): such chains take the
+// table starter only for samples at least kTableMinM = 0.1 rad of mean anomaly away from periastron and
+// the reference's own starter -- hence its exact, un-converged iterates -- inside that window.
+constexpr double kTableAllE = 0.8;
+constexpr double kTableMaxE = 0.99;
+constexpr double kTableMinM = 0.1;
+
 // physical constants, likelihood3.h:4-10,31
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 2.0 * 3.14159265358979323846;  // == fl(2*PI) used by fmod(M, 2*PI)
@@ -45,6 +55,7 @@ struct ChainConst {
     double rPs;        // RN(1/Ps): seed of the exact phase division
     double cw, sw;     // cos/sin omega0
     double cwq, swq;   // cos/sin omega0 times sqrt(1 - e^2)
+    double tab_min_m;  // 0: the E(M) table serves every sample; > 0: only samples this far (rad) from periastron
     double ci, si;     // cos/sin inc
     double ar;         // a / RSUN
     // raw flux u = K0 + K1 c + b^2 (a0 + a1 s + a2 c2 + b (b0 + b1 c2 + b (c1 s + c3 s3 + b (d0 + d2 c2 + d4 c4))))
@@ -391,6 +402,7 @@ __device__ inline void prologue_assemble(const double* __restrict__ p, const Mag
     cc.rPs = __drcp_rn(cc.Ps);
     cc.cw = T.cw;
     cc.sw = T.sw;
+    cc.tab_min_m = (e > kTableAllE) ? kTableMinM : 0.0;
     cc.cwq = T.cw * T.sq1me2;
     cc.swq = T.sw * T.sq1me2;
     cc.ci = ci;
@@ -769,7 +781,7 @@ static __device__ __noinline__ void kepler_point_careful(double m, double e, dou
 constexpr int kTableN = 1024;              // intervals on [0, 2 pi]  (h = pi / 512)
 constexpr int kTableSize = kTableN + 3;    // nodes -1 .. kTableN+1
 constexpr int kTableSolved = kTableN / 2 + 2;  // entries 0 .. kTableN/2+1 are solved, the rest mirrored
-constexpr double kTableMaxE = 0.8;
+// (kTableAllE, kTableMaxE, kTableMinM: see the top of this file)
 
 __device__ __forceinline__ double kepler_table_node(int j, double e);
 
@@ -842,7 +854,7 @@ static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab
 // is out of range -- wild Newton iterates at e -> 1 are rare).
 template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
-                                              const double rPs, const double* __restrict__ ktab,
+                                              const double rPs, const double* __restrict__ ktab, const double tab_min_m,
                                               const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
                                               double (&den)[V], double (&beta)[V], int* hi_acc = nullptr)
 {
@@ -850,7 +862,15 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
 #pragma unroll
     for (int j = 0; j < V; j++) {
         M[j] = mean_anomaly(tsec[j], T0s, Ps, rPs);
-        E[j] = (ktab != nullptr) ? kepler_table_guess(ktab, M[j]) : kepler_starter(M[j], e);
+        if (ktab == nullptr) {
+            E[j] = kepler_starter(M[j], e);
+        } else if (tab_min_m > 0.0) {  // eccentric chain: the reference's own path inside the periastron window
+            const double am = fabs(M[j]);
+            const bool far = fmin(am, kTwoPi - am) >= tab_min_m;
+            E[j] = far ? kepler_table_guess(ktab, M[j]) : kepler_starter(M[j], e);
+        } else {
+            E[j] = kepler_table_guess(ktab, M[j]);
+        }
     }
     // The reference always takes five Newton steps.  Once a step is below 2^-27 the next iterate
     // is the root to rounding (quadratic convergence: the following step is ~C step^2 < 1e-16) and
@@ -948,7 +968,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
 {
     const bool may_eclipse = (((int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
-    kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, sctab, cE, sE, den, bet, hi_acc);
+    kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cc.tab_min_m, sctab, cE, sE, den, bet, hi_acc);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)

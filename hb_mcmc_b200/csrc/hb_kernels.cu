@@ -520,7 +520,7 @@ __global__ void k_traj(const double* __restrict__ times, int Nt, const double* _
     const double a = pow(kG * Mtot * sq(P) / sq(2 * kPi), 1. / 3.);
     const double ts[1] = {__dmul_rn(times[i], kSecDay)};
     double cE[1], sE[1], den[1], bet[1];
-    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), nullptr, nullptr, cE, sE, den, bet);
+    kepler_points<1, false>(ts, e, T0, P, __drcp_rn(P), nullptr, 0.0, nullptr, cE, sE, den, bet);
     const double r = a * den[0];
     const double sq1 = sqrt(1 - e * e);
     const double nu = atan2(sq1 * sE[0], cE[0] - e);

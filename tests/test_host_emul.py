@@ -159,6 +159,24 @@ def test_table_starter_equals_reference_starter(emul, orc):
     assert worst < 2e-13, worst
 
 
+def test_table_starter_eccentric_chains(emul, orc):
+    """0.8 < e <= 0.99: the table serves the samples at least 0.1 rad of mean anomaly away from periastron
+    (where the reference's five steps converge, tests/tools/kepler_convergence_scan.c); inside the window the
+    reference's own starter and un-converged iterates are followed.  Both must reproduce the oracle."""
+    t = wl.time_grid(6000) * 3.0 - 4.0
+    P = wl.draw_chains(40, wl.TRUTH_B, lambda P: np.zeros(len(P)), seed=21, e_max=0.99)
+    P[:, 3] = np.linspace(0.801, 0.99, len(P))
+    P[:20, 2] = np.log10(np.linspace(0.7, 9.0, 20))  # short periods: many periastron passages in the data
+    worst = 0.0
+    for p in P:
+        _, want = orc.calc_light_curve(t, p, raw=True)
+        for mode in (1, 3):  # table starter with the polynomial sincos / with the table sincos (the kernel)
+            got = raw(emul, p, t, mode)
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            worst = max(worst, np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), 1.0)))
+    assert worst < 1e-11, worst
+
+
 def test_table_sincos_high_e(emul, orc):
     """The table sincos in the un-converged Newton tail (e up to 0.99, reference starter)."""
     t = wl.time_grid(3000) * 7.0 - 5.0
