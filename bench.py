@@ -49,12 +49,12 @@ NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
 CHAIN_CONST_BYTES = 47 * 8  # sizeof(ChainConst): what k_chain_eval reads per chain
 # From the committed `ncu --set full` capture of one k_chain_eval launch on C2
 # (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload:
-NCU_TRAFFIC_C2_BYTES = 2.742784e6 + 5.529344e6  # dram__bytes_read.sum + dram__bytes_write.sum
+NCU_TRAFFIC_C2_BYTES = 2.778112e6 + 5.378816e6  # dram__bytes_read.sum + dram__bytes_write.sum
 NCU_EXECUTED = {
-    "fp64_instr_per_point": 93.4,   # DFMA 55.0 + DMUL 19.0 + DADD 13.9 + DSETP 5.5 (warp instructions / 32 samples)
-    "flop_per_point": 142.9,        # 2 x DFMA + DMUL + DADD
-    "all_instr_per_point": 218.3,
-    "fp64_pipe_active": 0.595,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "fp64_instr_per_point": 92.6,   # DFMA 53.7 + DMUL 18.6 + DADD 13.7 + DSETP 6.6 (warp instructions / 32 samples)
+    "flop_per_point": 139.7,        # 2 x DFMA + DMUL + DADD
+    "all_instr_per_point": 219.9,
+    "fp64_pipe_active": 0.586,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
     "issue_active": 0.696,          # smsp__issue_active.avg.pct_of_peak_sustained_active
     "source": "profiles/r1_chain_eval_ncu_summary.txt",
 }
