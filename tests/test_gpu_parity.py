@@ -219,3 +219,29 @@ def test_out_of_range_iterates_rerun_the_chain(ctx, orc):
         ctx.set_sincos_range(1024.0)
     with pytest.raises(Exception):
         ctx.set_sincos_range(4096.0)
+
+
+def test_degenerate_templates_ties_and_plateaus(ctx, orc):
+    """Templates with massive ties defeat the bracket and the histogram of the fused median (all candidates
+    in one bin): face-on circular orbits give an exactly constant template, face-on eccentric ones a template
+    that repeats exactly every orbit.  The tie-proof fallbacks must still deliver the reference's median."""
+    N = 20000
+    t = wl.time_grid(N)
+    P = np.tile(wl.TRUTH_A, (6, 1))
+    P[0, 3], P[0, 4] = 0.0, 0.0          # e = 0, inc = 0: constant
+    P[1, 3], P[1, 4] = 0.0, 1e-12        # nearly constant: variations at the 1e-24 level
+    P[2, 3], P[2, 4] = 0.3, 0.0          # face-on, eccentric: beta(t) only
+    P[3, 3], P[3, 4] = 0.0, np.pi / 2    # edge-on circular: long flat eclipse bottoms / tops
+    P[4, 19] = 0.999                     # almost all third light: the model is nearly flux_tune everywhere
+    P[5, 13:15] = 0.0                    # no reflection
+    keep = ctx.roche_overflow(P) == 0
+    P = P[keep]
+    flux = 1 + 3e-4 * np.random.default_rng(1).standard_normal(N)
+    err = np.full(N, 3e-4)
+    ctx.set_data(t, flux, err)
+    got = ctx.loglikelihood(P)
+    want = orc.loglikelihood_batch(t, flux, err, P)
+    check_logL(got, want)
+    lc = ctx.light_curves(P[:3])
+    for k in range(min(3, len(P))):
+        assert np.nanmax(np.abs(lc[k] - orc.calc_light_curve(t, P[k]))) < 1e-12
