@@ -52,7 +52,7 @@ void calc_radii_and_Teffs(double params[], double *R1, double *R2, double *Teff1
 int RocheOverflow(double *pars);
 double loglikelihood(double time[], double lightcurve[], double noise[], long N, double params[], double mag_data[],
                      double magerr[]);
-void set_limits(struct bounds limited[], struct bounds limits[], struct gauss_bounds gauss_pars[], double LC_PERIOD);
+void set_limits(struct bounds *limited, struct bounds *limits, struct gauss_bounds *gauss_pars, double LC_PERIOD);
 void initialize_proposals(double *sigma, double ***history);
 double _getT(double logM);
 double _getR(double logM);

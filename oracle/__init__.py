@@ -45,6 +45,8 @@ def build(ref: bool = True) -> None:
             targets = ["ref_driver"]
             if os.path.exists(os.path.join(os.path.dirname(HERE), "hb_mcmc_b200", "csrc", "libhb_likelihood3.so")):
                 targets.append("ref_driver_shim")
+                if os.path.exists("/root/reference/src/pyHB.pyx"):
+                    targets.append("pyhb")  # the unmodified Cython binding on the reference's C and on the drop-in
             subprocess.run(["make", "-s", "-C", HERE] + targets, check=True, stdout=sys.stderr)
 
 

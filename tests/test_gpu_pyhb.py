@@ -37,3 +37,39 @@ def test_pyhb_functions(golden, orc):
     assert pyHB.test_roche_lobe(list(kat) + [0.0], "Eggleton") > 0 and pyHB.test_roche_lobe(list(kat) + [0.0]) > 0
     lcs = pyHB.lightcurve3_batch(golden["kat_times"], np.stack([kat, kat]))
     assert np.abs(lcs - golden["kat_lc"]).max() < 2e-12
+
+
+def _load_ext(sub):
+    """The UNMODIFIED pyHB.pyx compiled by `make -C oracle pyhb` (oracle/_ref, built where the reference sources
+    exist; the .so travels)."""
+    import glob, importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = glob.glob(os.path.join(here, "..", "oracle", "_ref", sub, "pyHB*.so"))
+    if not so:
+        pytest.skip(f"oracle/_ref/{sub} not built (make -C oracle pyhb)")
+    spec = importlib.util.spec_from_file_location("pyHB", so[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_cython_binding_on_the_shim(golden):
+    """pyHB.pyx itself (not our Python mirror) linked against libhb_likelihood3.so through the .pxd of
+    INTEGRATION.md section 3, next to the same .pyx on the reference's likelihood3.c: same answers through the
+    binding's own marshalling (22-slot Q9 layout included), so a user of `import pyHB` sees no change."""
+    ref, dev = _load_ext("pyhb_ref"), _load_ext("pyhb_shim")
+    kat = list(golden["kat_params"])
+    t = golden["kat_times"]
+    a, b = np.asarray(ref.lightcurve3(t, kat)), np.asarray(dev.lightcurve3(t, kat))
+    assert a.shape == b.shape == (len(t),) and np.isfinite(a).all()
+    assert np.abs(a - b).max() < 2e-12
+    pars22 = kat + [0.0]
+    assert np.allclose(dev.calc_radii_and_Teffs(pars22), ref.calc_radii_and_Teffs(pars22), rtol=1e-13)
+    assert np.allclose(dev.calc_mags(pars22, 100.0), ref.calc_mags(pars22, 100.0), rtol=0, atol=1e-12)
+    for m in (-1.2, -0.2, 0.0, 0.3, 1.1):
+        assert abs(dev.getT(m) - ref.getT(m)) < 1e-13 and abs(dev.getR(m) - ref.getR(m)) < 1e-13
+        assert dev.envelope_Temp(m) == ref.envelope_Temp(m)
+        assert abs(dev.envelope_Radius(m) - ref.envelope_Radius(m)) < 1e-14
+    flux, err = a + 1e-4, np.full(len(t), 3e-4)
+    la, lb = ref.likelihood(t, flux, err, pars22), dev.likelihood(t, flux, err, pars22)
+    assert abs(la - lb) <= 1e-10 * abs(la)
