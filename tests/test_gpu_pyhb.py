@@ -64,7 +64,7 @@ def test_reference_cython_binding_on_the_shim(golden):
     assert a.shape == b.shape == (len(t),) and np.isfinite(a).all()
     assert np.abs(a - b).max() < 2e-12
     pars22 = kat + [0.0]
-    assert np.allclose(dev.calc_radii_and_Teffs(pars22), ref.calc_radii_and_Teffs(pars22), rtol=1e-13)
+    assert np.allclose(dev.calc_radii_and_Teffs(kat), ref.calc_radii_and_Teffs(kat), rtol=1e-13)
     assert np.allclose(dev.calc_mags(pars22, 100.0), ref.calc_mags(pars22, 100.0), rtol=0, atol=1e-12)
     for m in (-1.2, -0.2, 0.0, 0.3, 1.1):
         assert abs(dev.getT(m) - ref.getT(m)) < 1e-13 and abs(dev.getR(m) - ref.getR(m)) < 1e-13
