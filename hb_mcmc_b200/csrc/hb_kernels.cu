@@ -48,11 +48,11 @@ __global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const doub
 // The observed light curve (t, flux, 1/sigma: 24 B per sample) is read by every chain and stays
 // L2-resident.  Two ways to bring it to the math were built and measured on B200 (C2, 4096 x 20k):
 //   HB_TMA_STAGING = 0 (default)  coalesced LDG (8 B of t one iteration ahead, 16 B of {flux, 1/sigma}),
-//                                 software-pipelined in registers: 0.89 ms per call
+//                                 software-pipelined in registers: 0.786 ms per call
 //   HB_TMA_STAGING = 1            TMA bulk copies (cp.async.bulk -> SASS UBLKCP) of whole 256-sample
 //                                 tiles into a 2-stage shared-memory ring, completion by mbarrier
 //                                 expect_tx/complete_tx, stage reuse by a second mbarrier the warps
-//                                 arrive on: 1.09 ms (the 12 KB ring costs the fourth CTA per SM and
+//                                 arrive on: 0.971 ms (the 12 KB ring costs the fourth CTA per SM and
 //                                 couples the warps to within one iteration of each other); same bits.
 // At ~1000 cycles of FP64 work per 24 bytes the stream is far from any bandwidth limit, so the
 // variant with the least synchronisation and the smallest footprint wins; the TMA path stays selectable.
