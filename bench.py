@@ -380,7 +380,9 @@ def gpu_arm(args, cfg, rank, local_rank, world):
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_chain_eval_ncu_summary.txt)",
                 "hbm": hbm_block(n, N, k_ms),
                 "flop_per_point": FLOP_PER_POINT, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-                "executed": executed_block(n, N, k_ms, peak_tf),
+                # the instruction counts come from the C2 capture: not carried over to other workloads
+                "executed": executed_block(n, N, k_ms, peak_tf)
+                            if (args.workload == "C2" and not args.chains and not args.points) else None,
                 "peak_source": "hb_fp64_peak DFMA probe on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
                 "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
