@@ -16,7 +16,8 @@
  *
  * Threading: the reference calls loglikelihood from up to 25 OpenMP threads on shared arrays
  * (mcmc_wrapper2.c:383,488-489).  Concurrent calls are COMBINED into one batched device call (see
- * loglikelihood below); everything else funnels into one context whose C ABI serialises it.
+ * loglikelihood below); a call that repeats a recent one bit for bit is answered from a memo; everything else
+ * funnels into one context whose C ABI serialises it.
  */
 #define _POSIX_C_SOURCE 200809L /* clock_gettime, sched_yield under -std=c99 */
 #include <math.h>
@@ -45,6 +46,8 @@ static int g_use_gmag = 1, g_use_color = 0; /* likelihood3.h:11-12 */
 /* cached copy of the last data set handed to loglikelihood() */
 static double *g_t = NULL, *g_f = NULL, *g_e = NULL;
 static long g_n = -1;
+static long g_gen = 0;                                        /* bumped whenever the cached data set is replaced */
+static pthread_rwlock_t g_data_rw = PTHREAD_RWLOCK_INITIALIZER; /* g_t/g_f/g_e/g_n/g_gen: readers = memo look-ups */
 
 static void die(const char *what, const char *why)
 {
@@ -84,9 +87,12 @@ void hb_shim_shutdown(void)
     pthread_mutex_lock(&g_mu);
     if (g_ctx) hb_destroy(g_ctx);
     g_ctx = NULL;
+    pthread_rwlock_wrlock(&g_data_rw);
     free(g_t); free(g_f); free(g_e);
     g_t = g_f = g_e = NULL;
     g_n = -1;
+    g_gen++;
+    pthread_rwlock_unlock(&g_data_rw);
     pthread_mutex_unlock(&g_mu);
 }
 
@@ -211,6 +217,7 @@ typedef struct {
     long N;
     double out;
     int done;
+    long gen; /* data-set generation the value belongs to (memo) */
 } shim_req;
 
 static pthread_mutex_t q_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -218,14 +225,14 @@ static pthread_cond_t q_cv = PTHREAD_COND_INITIALIZER;
 static shim_req *q_items[SHIM_QMAX];
 static int q_len = 0, q_leader = 0, q_expect = 1;
 /* HB_SHIM_STATS=1: batches, requests and the time spent collecting / evaluating are printed at exit */
-static long st_batches = 0, st_reqs = 0;
+static long st_batches = 0, st_reqs = 0, st_memo_hits = 0;
 static double st_collect_us = 0., st_eval_us = 0.;
 static int st_on = -1;
 static void st_print(void)
 {
     if (st_batches > 0)
-        fprintf(stderr, "libhb_likelihood3: %ld loglikelihood calls in %ld batches (%.1f per batch), %.1f us collecting and %.1f us evaluating per batch\n",
-                st_reqs, st_batches, (double)st_reqs / st_batches, st_collect_us / st_batches, st_eval_us / st_batches);
+        fprintf(stderr, "libhb_likelihood3: %ld loglikelihood calls in %ld batches (%.1f per batch), %.1f us collecting and %.1f us evaluating per batch; %ld more calls answered from the memo\n",
+                st_reqs, st_batches, (double)st_reqs / st_batches, st_collect_us / st_batches, st_eval_us / st_batches, st_memo_hits);
 }
 
 static double now_us(void)
@@ -256,18 +263,92 @@ static void eval_group(hb_ctx *c, shim_req **items, int n)
     const long N = r0->N;
     size_t bytes = (size_t)(N > 0 ? N : 0) * sizeof(double);
     if (N != g_n || memcmp(r0->time, g_t, bytes) || memcmp(r0->flux, g_f, bytes) || memcmp(r0->noise, g_e, bytes)) {
+        pthread_rwlock_wrlock(&g_data_rw);
         g_t = (double *)realloc(g_t, bytes + 8);
         g_f = (double *)realloc(g_f, bytes + 8);
         g_e = (double *)realloc(g_e, bytes + 8);
         memcpy(g_t, r0->time, bytes); memcpy(g_f, r0->flux, bytes); memcpy(g_e, r0->noise, bytes);
         g_n = N;
+        g_gen++;
+        pthread_rwlock_unlock(&g_data_rw);
         CK(hb_set_data(c, r0->time, r0->flux, r0->noise, N));
     }
     CK(hb_set_mags(c, r0->mag_data, r0->magerr, g_use_gmag, g_use_color));
     for (int i = 0; i < n; i++) memcpy(pbuf + (size_t)i * NPARS, items[i]->params, NPARS * sizeof(double));
     CK(hb_loglikelihood_batch(c, pbuf, n, obuf));
-    for (int i = 0; i < n; i++) items[i]->out = obuf[i];
+    for (int i = 0; i < n; i++) {
+        items[i]->out = obuf[i];
+        items[i]->gen = g_gen;
+    }
     pthread_mutex_unlock(&g_mu);
+}
+
+/*
+ * Memo of recent values.  The reference's rung loop evaluates the CURRENT state of every rung again at every
+ * step (mcmc_wrapper2.c:488) although its value is the previous step's logLx or logLy: half of the driver's
+ * calls repeat a (data, params, magnitudes) triple seen one step earlier.  loglikelihood is a pure function of
+ * those inputs, so such a call is answered from a small direct-mapped table -- after checking EVERY input bit
+ * for bit (the 21 parameters, the 9 magnitude numbers, and the caller's three data arrays against the copy the
+ * device data set was made from), never on pointers alone.  HB_SHIM_MEMO=0 switches it off.
+ */
+#define MEMO_SLOTS 1024
+typedef struct {
+    double params[NPARS], mags[9], out;
+    long gen, N;
+    int valid;
+} memo_ent;
+static memo_ent memo[MEMO_SLOTS];
+static pthread_mutex_t memo_mu = PTHREAD_MUTEX_INITIALIZER;
+static int memo_on = -1;
+
+/* management call: 0 = every call is evaluated on the device, 1 = memo on (the default; env HB_SHIM_MEMO) */
+void hb_shim_set_memo(int on) { memo_on = on != 0; }
+long hb_shim_memo_hits(void) { return st_memo_hits; }
+
+static unsigned memo_slot(const double *params)
+{
+    unsigned long long h = 1469598103934665603ULL, w;
+    for (int i = 0; i < NPARS; i++) {
+        memcpy(&w, &params[i], sizeof w);
+        h = (h ^ w) * 1099511628211ULL;
+        h ^= h >> 29;
+    }
+    return (unsigned)(h % MEMO_SLOTS);
+}
+
+static int memo_lookup(const shim_req *r, double *out)
+{
+    memo_ent e;
+    pthread_mutex_lock(&memo_mu);
+    e = memo[memo_slot(r->params)];
+    pthread_mutex_unlock(&memo_mu);
+    if (!e.valid || e.N != r->N || memcmp(e.params, r->params, sizeof e.params) ||
+        memcmp(e.mags, r->mag_data, 5 * sizeof(double)) || memcmp(e.mags + 5, r->magerr, 4 * sizeof(double)))
+        return 0;
+    int hit = 0;
+    const size_t bytes = (size_t)(r->N > 0 ? r->N : 0) * sizeof(double);
+    pthread_rwlock_rdlock(&g_data_rw);
+    if (e.gen == g_gen && r->N == g_n && !memcmp(r->time, g_t, bytes) && !memcmp(r->flux, g_f, bytes) &&
+        !memcmp(r->noise, g_e, bytes))
+        hit = 1;
+    pthread_rwlock_unlock(&g_data_rw);
+    if (hit) *out = e.out;
+    return hit;
+}
+
+static void memo_store(const shim_req *r)
+{
+    memo_ent e;
+    memcpy(e.params, r->params, sizeof e.params);
+    memcpy(e.mags, r->mag_data, 5 * sizeof(double));
+    memcpy(e.mags + 5, r->magerr, 4 * sizeof(double));
+    e.out = r->out;
+    e.gen = r->gen;
+    e.N = r->N;
+    e.valid = 1;
+    pthread_mutex_lock(&memo_mu);
+    memo[memo_slot(r->params)] = e;
+    pthread_mutex_unlock(&memo_mu);
 }
 
 double loglikelihood(double time[], double lightcurve[], double noise[], long N, double params[], double mag_data[],
@@ -277,7 +358,15 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
     /* side effect of likelihood3.c:824-827: the caller's noise[] is clamped in place (quirk Q2) */
     for (long i = 0; i < N; i++)
         if (noise[i] < 1.e-5) noise[i] = 1.e-5;
-    shim_req me = {time, lightcurve, noise, params, mag_data, magerr, N, 0., 0};
+    shim_req me = {time, lightcurve, noise, params, mag_data, magerr, N, 0., 0, 0};
+    if (memo_on < 0) {
+        const char *env = getenv("HB_SHIM_MEMO");
+        memo_on = env ? atoi(env) != 0 : 1;
+    }
+    if (memo_on && memo_lookup(&me, &me.out)) {
+        __sync_fetch_and_add(&st_memo_hits, 1);
+        return me.out;
+    }
 
     pthread_mutex_lock(&q_mu);
     while (q_len >= SHIM_QMAX) pthread_cond_wait(&q_cv, &q_mu);
@@ -337,6 +426,7 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
         pthread_cond_broadcast(&q_cv); /* results are in; whoever is still queued may lead the next batch */
     }
     pthread_mutex_unlock(&q_mu);
+    if (memo_on) memo_store(&me);
     return me.out;
 }
 

@@ -3,7 +3,7 @@
  * the reference's likelihood3.c.  The prototypes are the reference's own (likelihood3.h:68-89;
  * the last four are the un-headered helpers its Cython binding uses, likelihood3.pxd:10-13), so
  * a caller keeps including ITS likelihood3.h and only changes what it links against.  This header
- * exists so the test-suite can check the export list; it declares nothing new except the two
+ * exists so the test-suite can check the export list; it declares nothing new except the
  * hb_shim_* management calls.
  *
  *   symbol                 replaces (reference file:line)        computed
@@ -62,6 +62,11 @@ double envelope_Radius(double logM);
 /* USE_GMAG / USE_COLOR_INFO (likelihood3.h:11-12) at run time; defaults 1 / 0 */
 void hb_shim_set_flags(int use_gmag, int use_color);
 void hb_shim_shutdown(void);
+/* loglikelihood() answers a call whose inputs (parameters, magnitudes, data arrays -- compared bit for bit)
+ * repeat a recent one from a memo: the reference driver re-evaluates every rung's current state at every step
+ * (mcmc_wrapper2.c:488).  on = 0 evaluates every call on the device (also: env HB_SHIM_MEMO=0). */
+void hb_shim_set_memo(int on);
+long hb_shim_memo_hits(void);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,8 @@ def shim():
     L.set_limits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     L.initialize_proposals.argtypes = [dp, C.c_void_p]
     L.quickSort.argtypes = [dp, C.c_int, C.c_int]
+    L.hb_shim_set_memo.argtypes = [C.c_int]
+    L.hb_shim_memo_hits.restype = C.c_long
     return L
 
 
@@ -135,6 +137,7 @@ def test_concurrent_callers_are_combined_and_correct(shim, golden):
     488-489).  The shim combines concurrent calls into one batched device call: every caller must get the
     value a lone call gets, whatever the interleaving, including callers with another data set."""
     import threading
+    shim.hb_shim_set_memo(0)  # every call reaches the device: this test is about the combining
     t = wl.time_grid(1000)
     fl = golden["n1000_flux"].copy()
     er = np.full(1000, 3e-4)
@@ -169,6 +172,59 @@ def test_concurrent_callers_are_combined_and_correct(shim, golden):
             assert np.array_equal(got[rep], want, equal_nan=True), nthreads
         nmix = min(8, nthreads)
         assert np.array_equal(got2[:nmix], want2[:nmix], equal_nan=True), nthreads
+    # the same storm with the memo on: repeated triples are answered from the table, with the same bits
+    shim.hb_shim_set_memo(1)
+    h0 = shim.hb_shim_memo_hits()
+    got[:] = np.nan
+    got2[:] = np.nan
+    ths = [threading.Thread(target=worker, args=(i, 8)) for i in range(8)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join(timeout=120)
+        assert not th.is_alive()
+    for rep in range(3):
+        assert np.array_equal(got[rep], want, equal_nan=True)
+    assert np.array_equal(got2, want2, equal_nan=True)
+    assert shim.hb_shim_memo_hits() > h0
+
+
+@pytest.mark.gpu
+def test_memo_checks_every_input(shim, golden):
+    """A repeated (data, parameters, magnitudes) triple is answered from the memo (the reference driver repeats
+    the current state of every rung at every step, mcmc_wrapper2.c:488); anything that changes -- a parameter
+    bit, a magnitude, the data arrays modified IN PLACE behind the same pointers -- is evaluated afresh."""
+    t = wl.time_grid(1000)
+    fl = golden["n1000_flux"].copy()
+    er = np.full(1000, 3e-4)
+    md, me = np.array([100.0, 9.0, 1, 1, 1]), np.array([0.05, 1e15, 1e15, 1e15])
+    pk = golden["n1000_params"][3].copy()
+
+    def call():
+        return shim.loglikelihood(p(t), p(fl), p(er), 1000, p(pk), p(md), p(me))
+
+    def fresh():
+        shim.hb_shim_set_memo(0)
+        v = call()
+        shim.hb_shim_set_memo(1)
+        return v
+
+    shim.hb_shim_set_memo(1)
+    v0 = call()
+    h = shim.hb_shim_memo_hits()
+    assert call() == v0 and shim.hb_shim_memo_hits() == h + 1
+    fl[10] += 1e-3  # same pointer, other data
+    v1 = call()
+    assert shim.hb_shim_memo_hits() == h + 1 and v1 != v0 and v1 == fresh()
+    md[1] += 0.1  # other magnitude
+    v2 = call()
+    assert shim.hb_shim_memo_hits() == h + 1 and v2 != v1 and v2 == fresh()
+    pk[4] = np.nextafter(pk[4], 10.0)  # one parameter bit
+    v3 = call()
+    assert shim.hb_shim_memo_hits() == h + 1 and v3 == fresh()
+    er[5] = 1e-9  # clamped in place by the call (Q2), then compared as clamped
+    v4 = call()
+    assert er[5] == 1e-5 and call() == v4 and shim.hb_shim_memo_hits() == h + 2 and v4 == fresh()
 
 
 @pytest.mark.gpu
