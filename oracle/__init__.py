@@ -42,7 +42,7 @@ def build(ref: bool = True) -> None:
         if os.path.exists("/root/reference/src/mcmc_wrapper2.c"):
             # the unmodified driver, stand-alone (statistical goldens, the PT baseline of bench.py) and linked
             # against the product's link-level drop-in libhb_likelihood3.so when that has been built
-            targets = ["ref_driver"]
+            targets = ["ref_driver", "ref_fma"]  # ref_fma: tests/tools/ref_self_consistency.py only
             if os.path.exists(os.path.join(os.path.dirname(HERE), "hb_mcmc_b200", "csrc", "libhb_likelihood3.so")):
                 targets.append("ref_driver_shim")
                 if os.path.exists("/root/reference/src/pyHB.pyx"):
@@ -210,8 +210,10 @@ class Reference:
 
     kind = "reference"
 
-    def __init__(self, color: bool = False):
-        name = "libref_lik3_color.so" if color else "libref_lik3.so"
+    def __init__(self, color: bool = False, variant: str = ""):
+        # variant "fma": the same unmodified file compiled with FMA contraction (`make -C oracle ref_fma`), only
+        # used to show how far the reference moves under a legal change of its own compilation
+        name = "libref_lik3_color.so" if color else ("libref_lik3_%s.so" % variant if variant else "libref_lik3.so")
         path = os.path.join(HERE, "_ref", name)
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")

@@ -15,7 +15,7 @@ over = 0
 total = 0
 for rep in range(REPS):
   for truth, N, emax, n, seed0 in ((wl.TRUTH_A, 20000, 0.95, 512, 1), (wl.TRUTH_B, 20000, 0.99, 512, 2), (wl.TRUTH_A, 1001, 0.99, 1024, 3), (wl.TRUTH_B, 50000, 0.97, 128, 4), (wl.TRUTH_A, 375, 0.9, 2048, 5)):
-    seed = seed0 + 100 * rep
+    seed = seed0 + 100 * rep + int(os.environ.get("SEED_OFFSET", "0"))
     t, fl, er = wl.make_dataset(N, truth, R.calc_light_curve)
     ctx.set_data(t, fl, er)
     P = wl.draw_chains(n, truth, ctx.roche_overflow, seed=seed, e_max=emax)
