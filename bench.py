@@ -511,22 +511,19 @@ def pt_reference_size_leg(ctx):
         # (25 OpenMP threads as in the reference; their concurrent calls are combined into device batches)
         shim_exe = os.path.join(ROOT, "oracle", "_ref", "hb_mcmc_ref_shim")
         if os.path.exists(shim_exe):
-            # two run lengths: the difference removes the process start-up (CUDA context creation, ~1 s, is as long
-            # as 1500 steps) from the rate; the whole-process figure of the short run is reported next to it
-            times = []
-            subprocess.run([shim_exe, "20", "102289966", repr(logp), "9"], capture_output=True, text=True, cwd=scr)  # page-in
-            for n_it in (ref_iters, 3 * ref_iters):
-                t0 = time.perf_counter()
-                r = subprocess.run([shim_exe, str(n_it), "102289966", repr(logp), "9"], capture_output=True, text=True, cwd=scr)
-                times.append(time.perf_counter() - t0)
-                if r.returncode != 0 or not re.search(r"Begining main mcmc loop", r.stdout):
-                    times = None
-                    break
-            if times is not None and times[1] > times[0]:
-                out.update({"shim_steps_per_sec": 2 * ref_iters / (times[1] - times[0]),
-                            "shim_steps_per_sec_whole_process": ref_iters / times[0],
+            # HB_SHIM_STATS=1 makes the shim print, at exit, the wall-clock span from the end of its first device
+            # batch to the end of its last: the run without the process start-up (CUDA context creation takes 1-4 s
+            # on a fresh box, as long as the 1500 steps themselves); the whole-process figure is reported next to it
+            t0 = time.perf_counter()
+            r = subprocess.run([shim_exe, str(ref_iters), "102289966", repr(logp), "9"], capture_output=True, text=True,
+                               cwd=scr, env=dict(os.environ, HB_SHIM_STATS="1"))
+            dt = time.perf_counter() - t0
+            m = re.search(r"span ([0-9.]+) s", r.stderr + r.stdout)
+            if r.returncode == 0 and re.search(r"Begining main mcmc loop", r.stdout) and m and float(m.group(1)) > 0:
+                out.update({"shim_steps_per_sec": ref_iters / float(m.group(1)),
+                            "shim_steps_per_sec_whole_process": ref_iters / dt,
                             "shim_note": "unmodified mcmc_wrapper2.c linked against libhb_likelihood3.so (link-level drop-in); "
-                                         f"rate from the difference of a {ref_iters}- and a {3 * ref_iters}-iteration run"})
+                                         "rate over the span from the shim's first to its last device batch (start-up excluded)"})
     return out
 
 

@@ -212,6 +212,7 @@ int RocheOverflow(double *pars)
  * next call, and one device call costs ~50 us whatever its size -- waiting for the team pays */
 #define SHIM_IDLE_US 50.0
 #define SHIM_MAX_US 300.0
+#define SHIM_DECAY_BATCHES 16
 typedef struct {
     const double *time, *flux, *noise, *params, *mag_data, *magerr;
     long N;
@@ -223,16 +224,20 @@ typedef struct {
 static pthread_mutex_t q_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t q_cv = PTHREAD_COND_INITIALIZER;
 static shim_req *q_items[SHIM_QMAX];
-static int q_len = 0, q_leader = 0, q_expect = 1;
+static int q_len = 0, q_leader = 0, q_expect = 1, q_decay = 0;
+static double idle_us = SHIM_IDLE_US;
 /* HB_SHIM_STATS=1: batches, requests and the time spent collecting / evaluating are printed at exit */
 static long st_batches = 0, st_reqs = 0, st_memo_hits = 0;
-static double st_collect_us = 0., st_eval_us = 0.;
+static double st_collect_us = 0., st_eval_us = 0., st_first_us = 0., st_last_us = 0.; /* end of the first / last batch */
 static int st_on = -1;
 static void st_print(void)
 {
     if (st_batches > 0)
         fprintf(stderr, "libhb_likelihood3: %ld loglikelihood calls in %ld batches (%.1f per batch), %.1f us collecting and %.1f us evaluating per batch; %ld more calls answered from the memo\n",
                 st_reqs, st_batches, (double)st_reqs / st_batches, st_collect_us / st_batches, st_eval_us / st_batches, st_memo_hits);
+    if (st_batches > 1)
+        fprintf(stderr, "libhb_likelihood3: span %.6f s from the end of the first batch to the end of the last (start-up excluded)\n",
+                (st_last_us - st_first_us) * 1e-6);
 }
 
 static double now_us(void)
@@ -291,13 +296,15 @@ static void eval_group(hb_ctx *c, shim_req **items, int n)
  * for bit (the 21 parameters, the 9 magnitude numbers, and the caller's three data arrays against the copy the
  * device data set was made from), never on pointers alone.  HB_SHIM_MEMO=0 switches it off.
  */
-#define MEMO_SLOTS 1024
+#define MEMO_SETS 2048 /* x 4 ways: a rung's current state must survive the ~100 stores of one driver step */
+#define MEMO_WAYS 4
 typedef struct {
     double params[NPARS], mags[9], out;
     long gen, N;
     int valid;
 } memo_ent;
-static memo_ent memo[MEMO_SLOTS];
+static memo_ent memo[MEMO_SETS][MEMO_WAYS];
+static unsigned char memo_victim[MEMO_SETS]; /* round-robin replacement */
 static pthread_mutex_t memo_mu = PTHREAD_MUTEX_INITIALIZER;
 static int memo_on = -1;
 
@@ -305,7 +312,7 @@ static int memo_on = -1;
 void hb_shim_set_memo(int on) { memo_on = on != 0; }
 long hb_shim_memo_hits(void) { return st_memo_hits; }
 
-static unsigned memo_slot(const double *params)
+static unsigned memo_set(const double *params)
 {
     unsigned long long h = 1469598103934665603ULL, w;
     for (int i = 0; i < NPARS; i++) {
@@ -313,18 +320,28 @@ static unsigned memo_slot(const double *params)
         h = (h ^ w) * 1099511628211ULL;
         h ^= h >> 29;
     }
-    return (unsigned)(h % MEMO_SLOTS);
+    return (unsigned)(h % MEMO_SETS);
+}
+
+static int memo_same_key(const memo_ent *e, const shim_req *r)
+{
+    return e->valid && e->N == r->N && !memcmp(e->params, r->params, sizeof e->params) &&
+           !memcmp(e->mags, r->mag_data, 5 * sizeof(double)) && !memcmp(e->mags + 5, r->magerr, 4 * sizeof(double));
 }
 
 static int memo_lookup(const shim_req *r, double *out)
 {
     memo_ent e;
+    int found = 0;
+    const unsigned set = memo_set(r->params);
     pthread_mutex_lock(&memo_mu);
-    e = memo[memo_slot(r->params)];
+    for (int w = 0; w < MEMO_WAYS && !found; w++)
+        if (memo_same_key(&memo[set][w], r)) {
+            e = memo[set][w];
+            found = 1;
+        }
     pthread_mutex_unlock(&memo_mu);
-    if (!e.valid || e.N != r->N || memcmp(e.params, r->params, sizeof e.params) ||
-        memcmp(e.mags, r->mag_data, 5 * sizeof(double)) || memcmp(e.mags + 5, r->magerr, 4 * sizeof(double)))
-        return 0;
+    if (!found) return 0;
     int hit = 0;
     const size_t bytes = (size_t)(r->N > 0 ? r->N : 0) * sizeof(double);
     pthread_rwlock_rdlock(&g_data_rw);
@@ -346,8 +363,13 @@ static void memo_store(const shim_req *r)
     e.gen = r->gen;
     e.N = r->N;
     e.valid = 1;
+    const unsigned set = memo_set(r->params);
     pthread_mutex_lock(&memo_mu);
-    memo[memo_slot(r->params)] = e;
+    int w = -1;
+    for (int k = 0; k < MEMO_WAYS && w < 0; k++)
+        if (memo_same_key(&memo[set][k], r) || !memo[set][k].valid) w = k; /* same key (older data set) or free */
+    if (w < 0) w = memo_victim[set]++ % MEMO_WAYS;
+    memo[set][w] = e;
     pthread_mutex_unlock(&memo_mu);
 }
 
@@ -378,6 +400,8 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
         }
         q_leader = 1; /* lead ONE batch; my own request is still queued, so it is part of it */
         if (st_on < 0) {
+            const char *env = getenv("HB_SHIM_IDLE_US"); /* patience of the collecting leader (default SHIM_IDLE_US) */
+            if (env && atof(env) > 0.) idle_us = atof(env);
             st_on = getenv("HB_SHIM_STATS") != NULL;
             if (st_on) atexit(st_print);
         }
@@ -393,14 +417,19 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
                 pthread_mutex_lock(&q_mu);
                 const double t = now_us();
                 if (q_len != last) { last = q_len; t_last = t; }
-                if (t - t_last > SHIM_IDLE_US || t - t0 > SHIM_MAX_US) break;
+                if (t - t_last > idle_us || t - t0 > SHIM_MAX_US) break;
             }
         }
         shim_req *batch[SHIM_QMAX];
         const int n = q_len;
         memcpy(batch, q_items, (size_t)n * sizeof(batch[0]));
         q_len = 0;
-        q_expect = n >= q_expect ? n : q_expect - 1; /* follows the team size up at once, down slowly */
+        /* follows the team size up at once, down slowly: one step per SHIM_DECAY_BATCHES smaller batches.  (A
+         * decrement at every smaller batch settles on splitting a 25-thread team into 15 + 10 once the memo
+         * answers half of the calls and the arrivals spread out: the late third comes a few us after the
+         * leader has left.) */
+        if (n >= q_expect) { q_expect = n; q_decay = 0; }
+        else if (++q_decay >= SHIM_DECAY_BATCHES) { q_expect--; q_decay = 0; }
         pthread_cond_broadcast(&q_cv);                          /* room in the queue again */
         pthread_mutex_unlock(&q_mu);
         const double st_t1 = st_on ? now_us() : 0.;
@@ -419,7 +448,9 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
             st_batches++;
             st_reqs += n;
             st_collect_us += st_t1 - st_t0;
-            st_eval_us += now_us() - st_t1;
+            st_last_us = now_us();
+            st_eval_us += st_last_us - st_t1;
+            if (st_batches == 1) st_first_us = st_last_us;
         }
         for (int i = 0; i < n; i++) batch[i]->done = 1;
         q_leader = 0;
