@@ -78,8 +78,11 @@ static hb_ctx *ctx(void)
 void hb_shim_set_flags(int use_gmag, int use_color)
 {
     ctx();
+    pthread_rwlock_wrlock(&g_data_rw);
     g_use_gmag = use_gmag;
     g_use_color = use_color;
+    g_gen++; /* values remembered under the old flags are not answers any more */
+    pthread_rwlock_unlock(&g_data_rw);
 }
 
 void hb_shim_shutdown(void)
@@ -278,12 +281,13 @@ static void eval_group(hb_ctx *c, shim_req **items, int n)
         pthread_rwlock_unlock(&g_data_rw);
         CK(hb_set_data(c, r0->time, r0->flux, r0->noise, N));
     }
+    const long gen = g_gen; /* taken BEFORE the flags are read: a concurrent hb_shim_set_flags voids this batch's memo entries */
     CK(hb_set_mags(c, r0->mag_data, r0->magerr, g_use_gmag, g_use_color));
     for (int i = 0; i < n; i++) memcpy(pbuf + (size_t)i * NPARS, items[i]->params, NPARS * sizeof(double));
     CK(hb_loglikelihood_batch(c, pbuf, n, obuf));
     for (int i = 0; i < n; i++) {
         items[i]->out = obuf[i];
-        items[i]->gen = g_gen;
+        items[i]->gen = gen;
     }
     pthread_mutex_unlock(&g_mu);
 }

@@ -38,6 +38,7 @@ def shim():
     L.initialize_proposals.argtypes = [dp, C.c_void_p]
     L.quickSort.argtypes = [dp, C.c_int, C.c_int]
     L.hb_shim_set_memo.argtypes = [C.c_int]
+    L.hb_shim_set_flags.argtypes = [C.c_int, C.c_int]
     L.hb_shim_memo_hits.restype = C.c_long
     return L
 
@@ -222,6 +223,11 @@ def test_memo_checks_every_input(shim, golden):
     pk[4] = np.nextafter(pk[4], 10.0)  # one parameter bit
     v3 = call()
     assert shim.hb_shim_memo_hits() == h + 1 and v3 == fresh()
+    shim.hb_shim_set_flags(0, 0)  # Gaia term off (likelihood3.h:11): remembered values are void
+    v3b = call()
+    assert shim.hb_shim_memo_hits() == h + 1 and v3b != v3
+    shim.hb_shim_set_flags(1, 0)
+    assert call() == v3 and shim.hb_shim_memo_hits() == h + 1
     er[5] = 1e-9  # clamped in place by the call (Q2), then compared as clamped
     v4 = call()
     assert er[5] == 1e-5 and call() == v4 and shim.hb_shim_memo_hits() == h + 2 and v4 == fresh()
