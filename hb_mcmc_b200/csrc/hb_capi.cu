@@ -722,8 +722,12 @@ struct hb_pt {
     // one iteration captured as a CUDA graph (the step is latency-bound at the reference's sizes)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    // kPtGraphIters iterations in one graph: one graph launch (and one inter-launch gap) per 8 steps
+    cudaGraph_t graph_k = nullptr;
+    cudaGraphExec_t graph_exec_k = nullptr;
     unsigned long graph_generation = 0;
 };
+constexpr long kPtGraphIters = 8;
 
 namespace {
 
@@ -836,6 +840,8 @@ void hb_pt_destroy(hb_pt* pt)
         cudaFree(pt->index); cudaFree(pt->jump); cudaFree(pt->counters); cudaFree(pt->d_iter);
         if (pt->graph_exec) cudaGraphExecDestroy(pt->graph_exec);
         if (pt->graph) cudaGraphDestroy(pt->graph);
+        if (pt->graph_exec_k) cudaGraphExecDestroy(pt->graph_exec_k);
+        if (pt->graph_k) cudaGraphDestroy(pt->graph_k);
     }
     delete pt;
 }
@@ -902,9 +908,26 @@ int hb_pt_step(hb_pt* pt, long n_iters)
         if (rc != HB_OK) return rc;
         if (ce != cudaSuccess) return fail_cuda(ctx, ce, "cudaStreamEndCapture");
         CK(cudaGraphInstantiate(&pt->graph_exec, pt->graph, 0));
+        // the same iteration kPtGraphIters times over (the iteration counter lives on the device)
+        if (pt->graph_exec_k) { cudaGraphExecDestroy(pt->graph_exec_k); pt->graph_exec_k = nullptr; }
+        if (pt->graph_k) { cudaGraphDestroy(pt->graph_k); pt->graph_k = nullptr; }
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        for (long k = 0; k < kPtGraphIters && rc == HB_OK; k++) rc = pt_enqueue_step(pt);
+        ce = cudaStreamEndCapture(ctx->stream, &pt->graph_k);
+        ctx->launches = launches_before;
+        if (rc != HB_OK) return rc;
+        if (ce != cudaSuccess) return fail_cuda(ctx, ce, "cudaStreamEndCapture");
+        CK(cudaGraphInstantiate(&pt->graph_exec_k, pt->graph_k, 0));
         pt->graph_generation = ctx->generation;
     }
-    for (long k = 0; k < n_iters; k++) {
+    long k = 0;
+    if (use_graph)
+        for (; k + kPtGraphIters <= n_iters; k += kPtGraphIters) {
+            CK(cudaGraphLaunch(pt->graph_exec_k, ctx->stream));
+            ctx->launches += 5 * kPtGraphIters;
+            pt->iter += kPtGraphIters;
+        }
+    for (; k < n_iters; k++) {
         if (use_graph) {
             CK(cudaGraphLaunch(pt->graph_exec, ctx->stream));
             ctx->launches += 5;
