@@ -1,0 +1,36 @@
+"""bench.py on the B200: one JSON line carrying the contract's keys (small sizes; the numbers are not judged here)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_line_has_the_contract_keys():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--chains", "256",
+                        "--points", "4000", "--pt-steps", "4", "--no-pt-reference"], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["metric"] == "model_point_logL_evals_per_sec" and line["unit"] == "points/s" and line["n_gpus"] == 1
+    assert line["value"] > 0 and line["steps"] == 3 and line["warmup"] >= 3 and line["scaling"] == "weak"
+    assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["gpu_launches"] >= 2 * 3
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 256 * 21 * 8
+    assert e2e["d2h_bytes_per_step"] == 256 * 8
+    roof = line["roofline"]
+    assert roof["kernel"] == "k_chain_eval" and roof["peak"] > 0 and roof["achieved"] > 0
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12 and 0 < roof["kernel_share_of_step"] <= 1.0
+    assert roof["traffic"] is None and roof["executed"] is None  # both belong to the C2 capture only
+    clocks = line["clocks"]
+    assert clocks["sm_mhz"] > 0 and clocks["sm_max_mhz"] >= clocks["sm_mhz"] and isinstance(clocks["reasons"], list)
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1
+    assert cb["max_rel_err_gpu_vs_cpu_on_sample"] <= 1e-10
+    assert line["pt"]["steps_per_sec"] > 0 and line["pt"]["gathered_finite"] is True
