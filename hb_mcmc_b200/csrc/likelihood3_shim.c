@@ -306,9 +306,10 @@ typedef struct {
     double params[NPARS], mags[9], out;
     long gen, N;
     int valid;
+    unsigned long stamp; /* last store or hit: the least recently used way of a set is replaced */
 } memo_ent;
 static memo_ent memo[MEMO_SETS][MEMO_WAYS];
-static unsigned char memo_victim[MEMO_SETS]; /* round-robin replacement */
+static unsigned long memo_clock = 0;
 static pthread_mutex_t memo_mu = PTHREAD_MUTEX_INITIALIZER;
 static int memo_on = -1;
 
@@ -341,6 +342,7 @@ static int memo_lookup(const shim_req *r, double *out)
     pthread_mutex_lock(&memo_mu);
     for (int w = 0; w < MEMO_WAYS && !found; w++)
         if (memo_same_key(&memo[set][w], r)) {
+            memo[set][w].stamp = ++memo_clock; /* a state that keeps being asked for stays */
             e = memo[set][w];
             found = 1;
         }
@@ -372,7 +374,12 @@ static void memo_store(const shim_req *r)
     int w = -1;
     for (int k = 0; k < MEMO_WAYS && w < 0; k++)
         if (memo_same_key(&memo[set][k], r) || !memo[set][k].valid) w = k; /* same key (older data set) or free */
-    if (w < 0) w = memo_victim[set]++ % MEMO_WAYS;
+    if (w < 0) {
+        w = 0;
+        for (int k = 1; k < MEMO_WAYS; k++)
+            if (memo[set][k].stamp < memo[set][w].stamp) w = k;
+    }
+    e.stamp = ++memo_clock;
     memo[set][w] = e;
     pthread_mutex_unlock(&memo_mu);
 }
