@@ -515,8 +515,11 @@ def pt_reference_size_leg(ctx):
             # batch to the end of its last: the run without the process start-up (CUDA context creation takes 1-4 s
             # on a fresh box, as long as the 1500 steps themselves); the whole-process figure is reported next to it
             t0 = time.perf_counter()
-            r = subprocess.run([shim_exe, str(ref_iters), "102289966", repr(logp), "9"], capture_output=True, text=True,
-                               cwd=scr, env=dict(os.environ, HB_SHIM_STATS="1"))
+            try:
+                r = subprocess.run([shim_exe, str(ref_iters), "102289966", repr(logp), "9"], capture_output=True, text=True,
+                                   cwd=scr, env=dict(os.environ, HB_SHIM_STATS="1"), timeout=180)
+            except subprocess.TimeoutExpired:
+                return out
             dt = time.perf_counter() - t0
             m = re.search(r"span ([0-9.]+) s", r.stderr + r.stdout)
             if r.returncode == 0 and re.search(r"Begining main mcmc loop", r.stdout) and m and float(m.group(1)) > 0:

@@ -19,7 +19,7 @@
  * loglikelihood below); a call that repeats a recent one bit for bit is answered from a memo; everything else
  * funnels into one context whose C ABI serialises it.
  */
-#define _POSIX_C_SOURCE 200809L /* clock_gettime, sched_yield under -std=c99 */
+#define _GNU_SOURCE /* clock_gettime, sched_yield, syscall under -std=c99 */
 #include <math.h>
 #include <pthread.h>
 #include <sched.h>
@@ -27,6 +27,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <unistd.h>
+#include <sys/syscall.h>
+#include <linux/futex.h>
 
 #include "hb_b200.h"
 
@@ -216,6 +220,10 @@ int RocheOverflow(double *pars)
 #define SHIM_IDLE_US 50.0
 #define SHIM_MAX_US 300.0
 #define SHIM_DECAY_BATCHES 16
+/* states of shim_req.done, the word a waiting caller sleeps on */
+enum { REQ_WAITING = 0, REQ_DONE = 1, REQ_LEAD = 2 };
+static void futex_wait(int *addr, int val) { syscall(SYS_futex, addr, FUTEX_WAIT_PRIVATE, val, NULL, NULL, 0); }
+static void futex_wake(int *addr) { syscall(SYS_futex, addr, FUTEX_WAKE_PRIVATE, 1, NULL, NULL, 0); }
 typedef struct {
     const double *time, *flux, *noise, *params, *mag_data, *magerr;
     long N;
@@ -404,12 +412,20 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
     pthread_mutex_lock(&q_mu);
     while (q_len >= SHIM_QMAX) pthread_cond_wait(&q_cv, &q_mu);
     q_items[q_len++] = &me;
-    while (!me.done) {
-        if (q_leader) { /* someone is collecting or evaluating: wait for my value, or for the leadership */
-            pthread_cond_wait(&q_cv, &q_mu);
-            continue;
-        }
-        q_leader = 1; /* lead ONE batch; my own request is still queued, so it is part of it */
+    int lead = !q_leader; /* nobody collecting or evaluating: lead ONE batch (my own request is queued, so it is in it) */
+    if (lead) q_leader = 1;
+    pthread_mutex_unlock(&q_mu);
+    if (!lead) {
+        /* wait on my OWN word (futex), not on a shared condition variable: 25 sleepers woken by one broadcast come
+         * back one after the other through q_mu, and that queue was most of the next batch's collecting time */
+        int st;
+        while ((st = __atomic_load_n(&me.done, __ATOMIC_ACQUIRE)) == REQ_WAITING) futex_wait(&me.done, REQ_WAITING);
+        if (st == REQ_DONE) goto finished; /* the leader does not touch `me` after publishing REQ_DONE */
+        /* REQ_LEAD: the previous leader handed the leadership to me (q_leader is still 1) */
+        __atomic_store_n(&me.done, REQ_WAITING, __ATOMIC_RELAXED);
+    }
+    {
+        pthread_mutex_lock(&q_mu);
         if (st_on < 0) {
             const char *env = getenv("HB_SHIM_IDLE_US"); /* patience of the collecting leader (default SHIM_IDLE_US) */
             if (env && atof(env) > 0.) idle_us = atof(env);
@@ -441,7 +457,7 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
          * leader has left.) */
         if (n >= q_expect) { q_expect = n; q_decay = 0; }
         else if (++q_decay >= SHIM_DECAY_BATCHES) { q_expect--; q_decay = 0; }
-        pthread_cond_broadcast(&q_cv);                          /* room in the queue again */
+        pthread_cond_broadcast(&q_cv);                          /* room in the queue again (callers blocked on a full queue) */
         pthread_mutex_unlock(&q_mu);
         const double st_t1 = st_on ? now_us() : 0.;
         /* evaluate group by group (normally one group) */
@@ -463,11 +479,22 @@ double loglikelihood(double time[], double lightcurve[], double noise[], long N,
             st_eval_us += st_last_us - st_t1;
             if (st_batches == 1) st_first_us = st_last_us;
         }
-        for (int i = 0; i < n; i++) batch[i]->done = 1;
-        q_leader = 0;
-        pthread_cond_broadcast(&q_cv); /* results are in; whoever is still queued may lead the next batch */
+        /* whoever queued up meanwhile leads the next batch: the leadership passes to the first of them directly */
+        shim_req *next = q_len > 0 ? q_items[0] : NULL;
+        if (!next) q_leader = 0;
+        pthread_mutex_unlock(&q_mu);
+        for (int i = 0; i < n; i++)
+            if (batch[i] != &me) { /* results are in: publish, wake, and never touch batch[i] again */
+                int *w = &batch[i]->done;
+                __atomic_store_n(w, REQ_DONE, __ATOMIC_RELEASE);
+                futex_wake(w);
+            }
+        if (next) {
+            __atomic_store_n(&next->done, REQ_LEAD, __ATOMIC_RELEASE);
+            futex_wake(&next->done);
+        }
     }
-    pthread_mutex_unlock(&q_mu);
+finished:
     if (memo_on) memo_store(&me);
     return me.out;
 }
