@@ -236,8 +236,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             }
             if (tid == 0) {
                 sm.ctl.cnt = 0;
-                if (r_lo < 0) sm.ctl.lo = 0ull;
-                if (r_hi > kThreads - 1) sm.ctl.hi = ~0ull;
+                // a bracket rank outside the sample leaves that side open (the keys of -inf / +inf decode to
+                // themselves; the integer sentinels 0 / ~0 would decode to NaN and reject every sample)
+                if (r_lo < 0) sm.ctl.lo = dkey(-INFINITY);
+                if (r_hi > kThreads - 1) sm.ctl.hi = dkey(INFINITY);
             }
             if (tid == r_lo) sm.ctl.lo = sorted;
             if (tid == r_hi) sm.ctl.hi = sorted;
@@ -334,7 +336,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 const bool valid = i < N;
                 const double uj = u[j];
                 // with data, a NaN sample poisons S0 and is detected once after the loop
-                if (!kData) nanflag |= (uj != uj);
+                if (!kData) nanflag |= valid & (uj != uj);  // the padding of a staged time grid may hold anything
                 if (kStore && valid) tmpl[i] = dkey(uj);
                 if (valid & (uj < lo)) c_lt++;
                 const bool inr = valid & (uj >= lo) & (uj <= hi);

@@ -59,15 +59,24 @@ static void die(const char *what, const char *why)
     abort();
 }
 
+/* HB_USE_GMAG / HB_USE_COLOR_INFO stand in for the compile-time macros of likelihood3.h:11-12.  They are read
+ * once, without creating a device context: the reference driver calls set_limits / initialize_proposals
+ * (mcmc_wrapper2.c:195-198) before its first loglikelihood (:342), and the sigma table depends on them. */
+static pthread_once_t g_env_once = PTHREAD_ONCE_INIT;
+static void read_env_flags(void)
+{
+    const char *env;
+    if ((env = getenv("HB_USE_GMAG"))) g_use_gmag = atoi(env);
+    if ((env = getenv("HB_USE_COLOR_INFO"))) g_use_color = atoi(env);
+}
+
 static hb_ctx *ctx(void)
 {
+    pthread_once(&g_env_once, read_env_flags);
     pthread_mutex_lock(&g_mu);
     if (!g_ctx) {
         const char *dev = getenv("HB_DEVICE");
-        const char *env;
         if (hb_create(&g_ctx, dev ? atoi(dev) : 0) != HB_OK) die("hb_create", hb_global_error());
-        if ((env = getenv("HB_USE_GMAG"))) g_use_gmag = atoi(env);
-        if ((env = getenv("HB_USE_COLOR_INFO"))) g_use_color = atoi(env);
     }
     pthread_mutex_unlock(&g_mu);
     return g_ctx;
@@ -81,7 +90,7 @@ static hb_ctx *ctx(void)
 /* runtime switch for the compile-time macros USE_GMAG / USE_COLOR_INFO (likelihood3.h:11-12) */
 void hb_shim_set_flags(int use_gmag, int use_color)
 {
-    ctx();
+    pthread_once(&g_env_once, read_env_flags); /* an explicit call wins over the environment */
     pthread_rwlock_wrlock(&g_data_rw);
     g_use_gmag = use_gmag;
     g_use_color = use_color;
@@ -524,6 +533,7 @@ void initialize_proposals(double *sigma, double ***history)
     static const double base[NPARS] = {1e-2, 1e-2, 1e-8, 1e-2, 1e-3, 1e-3, 1e-3, 1e-1, 1e-1, 1e-2, 1e-2,
                                        1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-2, 1e-1, 1e-1, 1e-3, 1e-5};
     (void)history;
+    pthread_once(&g_env_once, read_env_flags);
     memcpy(sigma, base, sizeof(base));
     if ((!g_use_color) || (!g_use_gmag)) { /* the enlarged set, likelihood3.c:1158-1179 */
         sigma[0] = sigma[1] = 1e-1;

@@ -99,18 +99,28 @@ def likelihood(times, fluxes, errs, pars, lctype=3):
     return ll if ll > minlike else minlike
 
 
-def likelihood_batch(times, fluxes, errs, pars):
-    """Same quantity for pars[n, 22] with one device call: chi^2 through the fused kernel, the
-    noise rescale applied analytically (chi^2 scales with exp(-2 ln_resc))."""
-    P = np.asarray(pars, dtype=np.float64)
-    ctx = context()
-    errs = np.asarray(errs, dtype=np.float64)
-    ctx.set_data(times, fluxes, errs)
-    ctx.set_mags([1000, 1, 1, 1, 1], [1e15] * 4, 0, 0)
-    logL = ctx.loglikelihood(P[:, :NPARS])  # -chi^2/2 (Roche override: -5e14)
+_batch_ctx: Context | None = None
+
+
+def likelihood_batch(times, fluxes, errs, pars, device: int = 0):
+    """`likelihood` (pyHB.pyx:230-252) for pars[n, 22] with one device call: the n model light curves come
+    from the batched kernel, the Gaussian sum is taken on the host exactly as the scalar function takes it --
+    no Roche override, no 1e-5 noise clamp (loglikelihood of likelihood3.c applies both, the binding's
+    likelihood neither).  A private context is used, so the data set and magnitudes of `context()` stay as
+    the caller left them."""
+    global _batch_ctx
+    P = np.asarray(pars, dtype=np.float64).reshape(-1, NPARS + 1)
+    times = np.asarray(times, dtype=np.float64)
+    fluxes, errs = np.asarray(fluxes, dtype=np.float64), np.asarray(errs, dtype=np.float64)
+    if _batch_ctx is None:
+        _batch_ctx = Context(device)
+    _batch_ctx.set_data(times, fluxes, errs)
+    models = _batch_ctx.light_curves(P[:, :NPARS])
     ln = P[:, NPARS]
-    out = logL * np.exp(-2 * ln) - len(errs) * ln
-    return np.where(out > -1e18, out, -1e18)
+    sig = errs[None, :] * np.exp(ln)[:, None]
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        ll = -np.sum(((fluxes[None, :] - models) / sig) ** 2, axis=1) / 2 - errs.size * ln
+    return np.where(ll > -1e18, ll, -1e18)  # NaN and anything below the floor map to the floor (pyHB.pyx:250)
 
 
 class parspace:

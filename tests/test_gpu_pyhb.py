@@ -27,6 +27,20 @@ def test_pyhb_functions(golden, orc):
         m = orc.calc_light_curve(t, p[:21])
         want.append(-np.sum(((flux - m) / (err * np.exp(p[21]))) ** 2) / 2 - 1000 * p[21])
     assert np.allclose(one, want, rtol=1e-10) and np.allclose(batch, want, rtol=1e-10)
+    # the batch is `likelihood` for every row: a Roche-overflowing row and tiny error bars get neither the
+    # -5e14 override nor the 1e-5 noise clamp of loglikelihood() (pyHB.pyx:230-252 applies neither)
+    Pr = np.column_stack([golden["roche_params"][:4], np.zeros(4)])
+    tiny = np.full(1000, 1e-7)
+    one_r = [pyHB.likelihood(t, flux, tiny, p) for p in Pr]
+    assert np.allclose(pyHB.likelihood_batch(t, flux, tiny, Pr), one_r, rtol=1e-10)
+    # and it leaves the module-level context (data set, magnitudes) as the caller set it
+    c = pyHB.context()
+    c.set_data(t, flux, err)
+    c.set_mags(golden["kat_mag_data"], golden["kat_mag_err"], 1, 0)
+    before = c.loglikelihood(golden["n1000_params"][:4])
+    pyHB.likelihood_batch(t[:500], flux[:500], tiny[:500], Pr)
+    assert np.array_equal(c.loglikelihood(golden["n1000_params"][:4]), before)
+    c.set_mags([1000, 1, 1, 1, 1], [1e15] * 4, 1, 0)
     assert pyHB.likelihood(t, flux, err, P[0], lctype=2) == -1e18
     # Q9: the stale 22-slot marshalling is available for comparisons and differs from the physical layout
     stale = pyHB.lightcurve3(golden["kat_times"], list(kat), reference_q9_layout=True)

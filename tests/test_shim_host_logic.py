@@ -50,3 +50,31 @@ def test_repeated_calls_come_from_the_memo(stress):
     assert evaluated + remembered == 50 + 400 * 100
     # the current state of every rung, every step (same bits: checked by the harness); an eviction only costs a re-evaluation
     assert remembered >= 0.98 * 400 * 50
+
+
+def test_proposal_table_reads_the_env_flags_before_any_likelihood(tmp_path):
+    """The reference driver calls initialize_proposals (mcmc_wrapper2.c:198) before its first loglikelihood (:342):
+    the sigma table must already follow HB_USE_GMAG / HB_USE_COLOR_INFO (likelihood3.c:1158-1179) then, without a
+    device context having been created (the stand-in library would abort the process if it were asked for one)."""
+    d, inc = str(tmp_path), os.path.join(ROOT, "include")
+    run = lambda *cmd: subprocess.run(cmd, check=True, cwd=d, capture_output=True, text=True)
+    # a libhb_b200 whose hb_create fails: any attempt to open the device ends the process
+    with open(os.path.join(d, "nodev.c"), "w") as f:
+        f.write('#include "hb_b200.h"\nint hb_create(hb_ctx** o, int dev) { (void)o; (void)dev; return HB_ERR_CUDA; }\n'
+                'const char* hb_global_error(void) { return "no device in this test"; }\n')
+    run("gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-I", inc, "-o", "libnodev.so", "nodev.c")
+    run("gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-I", inc, "-o", "libhb_b200.so", os.path.join(STUB, "stub_hb_b200.c"))
+    run("gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-I", inc, "-o", "libhb_likelihood3.so", SHIM_SRC, "-L", d, "-lhb_b200",
+        "-lpthread", "-lm")
+    with open(os.path.join(d, "sig.c"), "w") as f:
+        f.write('#include <stdio.h>\nvoid initialize_proposals(double*, double***);\n'
+                'int main(void) { double s[21]; initialize_proposals(s, 0); printf("%g %g %g\\n", s[0], s[4], s[12]); return 0; }\n')
+    run("gcc", "-O2", "-o", "sig", "sig.c", "-L", d, "-lhb_likelihood3", "-lhb_b200", "-lm")
+    go = lambda **env: subprocess.run([os.path.join(d, "sig")], capture_output=True, text=True, timeout=60,
+                                      env=dict(os.environ, LD_LIBRARY_PATH=d, LD_PRELOAD=os.path.join(d, "libnodev.so"), **env))
+    r = go()
+    assert r.returncode == 0 and r.stdout.split() == ["0.1", "0.01", "0.1"], r.stdout + r.stderr  # defaults: colours off
+    r = go(HB_USE_GMAG="1", HB_USE_COLOR_INFO="1")
+    assert r.returncode == 0 and r.stdout.split() == ["0.01", "0.001", "0.01"], r.stdout + r.stderr
+    r = go(HB_USE_GMAG="0", HB_USE_COLOR_INFO="1")
+    assert r.returncode == 0 and r.stdout.split() == ["0.1", "0.01", "0.1"], r.stdout + r.stderr
