@@ -43,10 +43,15 @@ struct hb_ctx {
     ChainConst* d_cc = nullptr;
     double* d_logL = nullptr;
     long cap_chains = 0;
-    uint64_t* d_scratch = nullptr;
-    size_t scratch_stride = 0;
+    uint64_t* d_scratch = nullptr;   // per region: 3 key buffers of key_stride + the per-segment partial sums
+    size_t key_stride = 0, region_stride = 0;
+    int scratch_segments = 0;        // segments the partial-sum area of a region holds
     int grid = 0;
-    int* d_counter = nullptr;
+    int* d_counter = nullptr;        // [0] work-item scheduler of k_chain_eval
+    unsigned long long* d_evaluated = nullptr;  // chains whose model was really evaluated (hb_evaluated_chains)
+    ChainSync* d_sync = nullptr;     // [grid] hand-over words of chains shared by several CTAs
+    double sum_w2 = 0.;              // sum of the squared weights of the uploaded data set
+    int max_parts = kMaxSegments;    // most CTAs one light curve may be spread over (hb_set_max_parts)
     double* d_lc = nullptr;
     size_t cap_lc = 0;
     double* d_times2 = nullptr;  // hb_calc_light_curve / hb_traj time grid
@@ -150,18 +155,39 @@ int ensure_chains(hb_ctx* ctx, long n)
     return HB_OK;
 }
 
-// scratch: per resident CTA three key arrays of `stride` entries (template + two select buffers)
+// scratch: per region (one per resident CTA, or per chain when chains are shared by CTAs) three key arrays of
+// `key_stride` entries (template + two select buffers) and 2 x threads partial sums for every segment
 int ensure_scratch(hb_ctx* ctx, long n_points)
 {
-    size_t stride = ((size_t)std::max(n_points, 1L) + 31) / 32 * 32;
-    if (ctx->d_scratch && stride <= ctx->scratch_stride) return HB_OK;
+    const size_t tile = (size_t)eval_tile();
+    const size_t stride = ((size_t)std::max(n_points, 1L) + tile - 1) / tile * tile;
+    const int nseg = eval_segments(n_points);
+    if (ctx->d_scratch && stride <= ctx->key_stride && nseg <= ctx->scratch_segments) return HB_OK;
+    const size_t ks = std::max(stride, ctx->key_stride);
+    const int sg = std::max(nseg, ctx->scratch_segments);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     ctx->d_scratch = nullptr;
-    ctx->scratch_stride = 0;
-    CK(cudaMalloc((void**)&ctx->d_scratch, (size_t)ctx->grid * 3 * stride * sizeof(uint64_t)));
-    ctx->scratch_stride = stride;
+    ctx->key_stride = ctx->region_stride = 0;
+    ctx->scratch_segments = 0;
+    const size_t region = 3 * ks + (size_t)sg * 2 * tile;
+    CK(cudaMalloc((void**)&ctx->d_scratch, (size_t)ctx->grid * region * sizeof(uint64_t)));
+    ctx->key_stride = ks;
+    ctx->region_stride = region;
+    ctx->scratch_segments = sg;
     ctx->generation++;
     return HB_OK;
+}
+
+// CTAs per chain: 1 when the batch fills the grid (or the pass has to store the template), else the largest
+// power of two that keeps chains x parts within the grid, does not exceed the light curve's segment count and
+// respects hb_set_max_parts.  The result never depends on it (see k_chain_eval).
+int choose_parts(const hb_ctx* ctx, long n_chains, long N, bool hot)
+{
+    if (!hot || N <= kCandA / 2) return 1;
+    const int nseg = eval_segments(N);
+    int p = 1;
+    while (2 * p <= nseg && 2 * p <= ctx->max_parts && n_chains * 2 * p <= ctx->grid) p *= 2;  // (p need not divide nseg)
+    return p;
 }
 
 // true when p points into page-locked host memory the device can DMA from / to directly
@@ -198,10 +224,32 @@ int download(hb_ctx* ctx, double* dst, const double* src, size_t n)
 int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, const double2* d_fw,
              long N, double* d_logL, double* d_lc)
 {
-    CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->d_counter, ctx->grid, ctx->stream));
+    EvalArgs a;
+    a.cc = ctx->d_cc;
+    a.n_chains = (int)n;
+    a.N = (int)N;
+    a.tsec = d_t;
+    a.fw = d_fw;
+    a.sum_w2 = d_fw ? ctx->sum_w2 : 0.0;
+    a.scratch = ctx->d_scratch;
+    a.region_stride = ctx->region_stride;
+    a.key_stride = ctx->key_stride;
+    a.logL = d_logL;
+    a.lc_out = d_lc;
+    a.counter = ctx->d_counter;
+    a.evaluated = ctx->d_evaluated;
+    a.sync = ctx->d_sync;
+    a.sctab = ctx->d_sctab;
+    a.bracket_sigma = ctx->bracket_sigma;
+    a.hot_hi_limit = ctx->hot_hi_limit;
+    a.nseg = eval_segments(N);
+    a.seg_shift = eval_seg_shift(N);
+    a.nparts = choose_parts(ctx, n, N, d_fw != nullptr && d_lc == nullptr);
+    const long n_work = n * a.nparts;
+    const int grid = (int)std::min<long>(ctx->grid, n_work);
+    CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->d_counter, grid, ctx->stream));
     if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
-    CK(launch_chain_eval(ctx->d_cc, (int)n, d_t, d_fw, (int)N, ctx->d_scratch, ctx->scratch_stride, ctx->grid,
-                         d_logL, d_lc, ctx->d_counter, ctx->bracket_sigma, ctx->d_sctab, ctx->hot_hi_limit, ctx->stream));
+    CK(launch_chain_eval(a, grid, ctx->stream));
     if (ctx->time_kernels) {
         CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
         ctx->ev_valid = true;
@@ -268,6 +316,10 @@ int hb_create(hb_ctx** out, int device)
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_counter, 2 * sizeof(int)) == cudaSuccess &&
               cudaMemset(ctx->d_counter, 0, 2 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_evaluated, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(ctx->d_evaluated, 0, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_sync, (size_t)ctx->grid * sizeof(ChainSync)) == cudaSuccess &&
+              cudaMemset(ctx->d_sync, 0, (size_t)ctx->grid * sizeof(ChainSync)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_small, 64 * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_sctab, kSinTabN * sizeof(double2)) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess &&
@@ -295,7 +347,7 @@ void hb_destroy(hb_ctx* ctx)
         cudaDeviceSynchronize();
         cudaFree(ctx->d_t); cudaFree(ctx->d_fw);
         cudaFree(ctx->d_params); cudaFree(ctx->d_cc); cudaFree(ctx->d_logL);
-        cudaFree(ctx->d_scratch); cudaFree(ctx->d_counter); cudaFree(ctx->d_lc);
+        cudaFree(ctx->d_scratch); cudaFree(ctx->d_counter); cudaFree(ctx->d_lc); cudaFree(ctx->d_evaluated); cudaFree(ctx->d_sync);
         cudaFree(ctx->d_times2); cudaFree(ctx->d_small); cudaFree(ctx->d_aux); cudaFree(ctx->d_sctab);
         if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
         if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
@@ -350,9 +402,10 @@ int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* 
     ctx->d_t = nullptr;
     ctx->d_fw = nullptr;
     ctx->has_data = false;
-    // padded to whole TMA tiles (k_chain_eval copies full tiles); the padding is finite and never used
+    // padded to whole tiles plus one (k_chain_eval reads full tiles and requests the next tile's time samples one
+    // iteration ahead without a bounds test); the padding is finite and adds nothing to any result
     const size_t tile = (size_t)eval_tile();
-    const size_t padded = ((size_t)std::max(n, 1L) + tile - 1) / tile * tile;
+    const size_t padded = (((size_t)std::max(n, 1L) + tile - 1) / tile + 1) * tile;
     size_t alloc = padded * sizeof(double);
     CK(cudaMalloc((void**)&ctx->d_t, alloc));
     CK(cudaMalloc((void**)&ctx->d_fw, 2 * alloc));
@@ -360,10 +413,14 @@ int hb_set_data(hb_ctx* ctx, const double* t, const double* flux, const double* 
     CK(cudaMemsetAsync(ctx->d_fw, 0, 2 * alloc, ctx->stream));  // padding: flux 0, weight 0 (adds nothing to chi^2)
     // weights 1/max(sigma, 1e-5): the clamp of likelihood3.c:824-827 applied once at upload
     std::vector<double> fw(2 * (size_t)n);
+    long double sw2 = 0.0L;  // S2 = sum w^2 of the chi^2 expansion does not depend on the chain: formed once, here
     for (long i = 0; i < n; i++) {
         fw[2 * i] = flux[i];
-        fw[2 * i + 1] = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
+        const double w = 1.0 / (err[i] < 1.e-5 ? 1.e-5 : err[i]);
+        fw[2 * i + 1] = w;
+        sw2 += (long double)w * (long double)w;
     }
+    ctx->sum_w2 = (double)sw2;
     int rc;
     if ((rc = upload(ctx, ctx->d_t, t, (size_t)n)) != HB_OK) return rc;
     CK(launch_to_seconds(ctx->d_t, (int)n, ctx->d_t, ctx->stream));  // d_t holds t * 86400 from here on
@@ -475,7 +532,7 @@ static int stage_times(hb_ctx* ctx, const double* times, long nt)
         ctx->d_times2 = nullptr;
         ctx->cap_times2 = 0;
         const size_t tile = (size_t)eval_tile();
-        const size_t padded = ((size_t)nt + tile - 1) / tile * tile;  // whole TMA tiles
+        const size_t padded = (((size_t)nt + tile - 1) / tile + 1) * tile;  // whole tiles plus one (see hb_set_data)
         CK(cudaMalloc((void**)&ctx->d_times2, padded * sizeof(double)));
         CK(cudaMemsetAsync(ctx->d_times2, 0, padded * sizeof(double), ctx->stream));
         ctx->cap_times2 = (long)padded;
@@ -557,7 +614,7 @@ int hb_order_statistic(hb_ctx* ctx, const double* x, long n, long k, double* out
     int rc;
     if ((rc = ensure_scratch(ctx, n)) != HB_OK) return rc;
     if ((rc = stage_times(ctx, x, n)) != HB_OK) return rc;
-    CK(launch_order_stat(ctx->d_times2, (int)n, (int)k, ctx->d_scratch, ctx->scratch_stride, ctx->d_small + 48, ctx->stream));
+    CK(launch_order_stat(ctx->d_times2, (int)n, (int)k, ctx->d_scratch, ctx->key_stride, ctx->d_small + 48, ctx->stream));
     ctx->launches += 1;
     double r[2];
     if ((rc = download(ctx, r, ctx->d_small + 48, 2)) != HB_OK) return rc;
@@ -578,7 +635,7 @@ int hb_remove_median(hb_ctx* ctx, double* arr, long n)
     // index rule of likelihood3.c:97-101 (quirk Q3); n == 1 uses the only element
     long k = (n % 2 == 0) ? n / 2 : n / 2 + 1;
     if (k > n - 1) k = n - 1;
-    CK(launch_order_stat(ctx->d_times2, (int)n, (int)k, ctx->d_scratch, ctx->scratch_stride, ctx->d_small + 48, ctx->stream));
+    CK(launch_order_stat(ctx->d_times2, (int)n, (int)k, ctx->d_scratch, ctx->key_stride, ctx->d_small + 48, ctx->stream));
     CK(launch_subtract(ctx->d_times2, (int)n, ctx->d_small + 48, ctx->stream));
     ctx->launches += 2;
     return download(ctx, arr, ctx->d_times2, (size_t)n);
@@ -631,6 +688,28 @@ int hb_set_bracket_sigma(hb_ctx* ctx, double sigma)
     if (!(sigma >= 0.0) || sigma > 100.0) return fail_arg(ctx, "hb_set_bracket_sigma: need 0 <= sigma <= 100");
     ctx->bracket_sigma = (float)sigma;
     ctx->generation++;  // a by-value argument of the captured step changed
+    return HB_OK;
+}
+
+int hb_set_max_parts(hb_ctx* ctx, int max_parts)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (max_parts < 1 || max_parts > kMaxSegments || (max_parts & (max_parts - 1)))
+        return fail_arg(ctx, "hb_set_max_parts: need a power of two between 1 and 64");
+    ctx->max_parts = max_parts;
+    ctx->generation++;
+    return HB_OK;
+}
+
+int hb_evaluated_chains(hb_ctx* ctx, unsigned long long* count, int reset)
+{
+    if (!ctx || !count) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(count, ctx->d_evaluated, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) CK(cudaMemsetAsync(ctx->d_evaluated, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return HB_OK;
 }
 

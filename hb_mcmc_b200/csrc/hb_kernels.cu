@@ -9,6 +9,7 @@
 //   k_fp64_peak   DFMA throughput probe (the roofline denominator, measured on the box)
 //
 // Replaces likelihood3.c:809-873 (loglikelihood) and :530-686 (calc_light_curve).
+#include <algorithm>
 #include <type_traits>
 
 #include "hb_kernels.h"
@@ -105,13 +106,17 @@ struct EvalShared {
 #endif
     ChainConst cc;
     SelectCtl<kEvalThreads> ctl;
-    double red[3 * 32];
+    double red[2 * 32];
     double pivot;  // chi^2 expansion point u0 (a template value near the median)
+    int bcast[4];  // block-wide broadcasts of the CTA that finishes a shared chain
     double ktab[kTableSize];  // the chain's E(M) starter table (hb_device.cuh)
     double2 sctab[kSinTabN];  // {sin, cos}(2 pi k / 1024) for sincos_tab, copied once per CTA
     uint64_t candA[kCandA];
-    uint64_t candB[kCandB];
+    uint64_t candB[kCandB];   // work area of the select; during the model pass: the running chi^2 sums [2][threads]
 };
+static_assert(kCandB * sizeof(uint64_t) >= 2 * kEvalThreads * sizeof(double), "candB holds the running sums of the pass");
+// four CTAs per SM: 228 KB of shared memory less 1 KB reserved per CTA
+static_assert(HB_TMA_STAGING || kEvalCtasPerSm != 4 || sizeof(EvalShared) <= 56 * 1024, "EvalShared no longer fits four CTAs per SM");
 
 size_t eval_smem_bytes() { return sizeof(EvalShared); }
 int eval_tile() { return kTile; }
@@ -124,23 +129,35 @@ __device__ __forceinline__ int median_rank(int N)
     return r < N ? r : N - 1;
 }
 
-// One chain at a time per CTA (persistent CTAs; first chain = block index, further ones from an atomic
-// counter).  Per chain:
-//   table       E(M) starter table of the chain in shared memory (e <= 0.8, build_kepler_table)
-//   pre-sample  every thread evaluates the model at one jittered-stride sample; the block sorts
-//               the kThreads values; sample order statistics give a bracket [lo, hi] around the
-//               reference's median rank and the expansion point u0 of the chi^2.
-//   model pass  u_i at every sample (the FP64-bound part): #(u < lo) counted, u in [lo, hi] appended to a
-//               candidate list (shared memory, or the CTA's global scratch for long light curves), and the
-//               three sums of   chi^2(m) = S0 + 2 d S1 + d^2 S2,   d = -A (m - u0),
+// One chain at a time per CTA (persistent CTAs; first work item = block index, further ones from an atomic
+// counter).  A work item is (chain, part): the time axis of a light curve is cut into SEGMENTS of 2^seg_shift
+// tiles -- a function of N alone (eval_seg_shift) -- and a launch hands every chain to `nparts` CTAs (1 for
+// batches that fill the grid), each taking a contiguous run of segments.  The chi^2 sums are formed per thread
+// and per segment and added up in segment order, then across the block: the same operations in the same order
+// whatever `nparts` is, so a chain's logL does not depend on the batch it arrives in, while a batch smaller than
+// the grid (one chain, a 50-rung ladder of long light curves) spreads every light curve over many SMs.  The
+// reference loops serially over the samples (likelihood3.c:147,649,822).
+// Per work item:
+//   table       E(M) starter table of the chain in shared memory (e <= 0.99, build_kepler_table)
+//   pre-sample  every thread evaluates the model at one jittered-stride sample of the WHOLE light curve; the
+//               block sorts the kThreads values; sample order statistics give a bracket [lo, hi] around the
+//               reference's median rank and the expansion point u0 of the chi^2 (every part of a chain repeats
+//               this bit for bit, so all agree on the bracket without talking to each other).
+//   model pass  u_i at every sample of the part (the FP64-bound part): #(u < lo) counted, u in [lo, hi] appended
+//               to the chain's candidate list (warp-aggregated atomic; shared memory, or global scratch for long
+//               or shared light curves, which stays in L2), and per segment the two sums of
+//                   chi^2(m) = S0 + 2 d S1 + d^2 S2,   d = -A (m - u0),
 //               S0 = sum ((A (u_i - u0) + ft - f_i) w_i)^2,  S1 = sum (A (u_i - u0) + ft - f_i) w_i^2,
-//               S2 = sum w_i^2   (model_i = A (u_i - m) + ft, A = ft (1 - blending), likelihood3.c:681-685).
-//               Two compile-time variants: the logL-only pass keeps everything on chip; the general one
-//               also stores the template keys (light-curve output, small N, re-runs) and checks per sample
-//               what the hot one checks per chain (sincos range, NaN).
+//               S2 = sum w_i^2 (per data set, from the host)  (model_i = A (u_i - m) + ft, A = ft (1 - blending),
+//               likelihood3.c:681-685).  Compile-time variants: the logL-only pass keeps everything on chip (one
+//               instance for a CTA that owns its chain, one for a part of a shared chain); the general one also
+//               stores the template keys (light-curve output, small N, re-runs) and checks per sample what the
+//               hot one checks per chain (sincos range, NaN).
+//   hand-over   (nparts > 1) counts and flags go to the chain's ChainSync words; the CTA that arrives last
+//               finishes the chain, the others move on.
 //   select      exact order statistic among the candidates: one histogram pass (block_select_hist), else
 //               sampling rounds (block_select_key); a chain whose bracket missed or whose Newton iterates
-//               left the table sincos' range is evaluated once more with the general pass.
+//               left the table sincos' range is evaluated once more, whole, with the general pass.
 // Between chains a CTA sits at barriers while its latency-bound neighbours on the SM cannot speed up, so
 // the per-chain phases count in full: clock64 gives table 3 k, pre-sample 6-8 k, pass 120-220 k, select
 // 8-13 k, final 2 k cycles at N = 20 000.
@@ -148,21 +165,21 @@ template <int kThreads>
 __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
 k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
              const double2* __restrict__ fw, int N, uint64_t* __restrict__ scratch,
-             size_t scratch_stride, double* __restrict__ logL, double* __restrict__ lc_out, int* __restrict__ counter,
-             float bracket_sigma, const double2* __restrict__ sctab_g, int hot_hi_limit)
+             size_t region_stride, size_t key_stride, double* __restrict__ logL, double* __restrict__ lc_out,
+             int* __restrict__ counter, float bracket_sigma, const double2* __restrict__ sctab_g, int hot_hi_limit,
+             double sum_w2, unsigned long long* __restrict__ evaluated, ChainSync* __restrict__ sync_all, int nparts,
+             int nseg, int seg_shift)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    uint64_t* tmpl = scratch + (size_t)blockIdx.x * 3 * scratch_stride;
-    uint64_t* gbufB = tmpl + scratch_stride;
-    uint64_t* gbufC = tmpl + 2 * scratch_stride;
-    const SelectBuf bufs[4] = {{sm.candB, kCandB}, {sm.candA, kCandA}, {gbufB, N}, {gbufC, N}};
-    static_assert(kCandB >= 2 * kThreads, "candB doubles as the work area of block_select_hist");
-    __shared__ int s_chain;
+    __shared__ int s_work;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int krank = median_rank(N);
     const int n_tiles = (N + kTile - 1) / kTile;
+    const int n_work = n_chains * nparts;
+    static_assert((kTile & (kTile - 1)) == 0, "segment ends are read off the bits of the sample index");
+    const int seg_bits = ((1 << seg_shift) - 1) * kTile;  // the tile-in-segment bits of a sample index
     for (int i = tid; i < kSinTabN; i += kThreads) sm.sctab[i] = sctab_g[i];  // published by the first barrier below
     const double2* sctab = sm.sctab;
 #if HB_TMA_STAGING
@@ -179,16 +196,25 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
 #endif
 
     for (int round = 0;; round++) {
-        // dynamic chain scheduler: chains differ in cost (eclipse fraction, Roche early-out).  The first chain of
+        // dynamic scheduler: chains differ in cost (eclipse fraction, Roche early-out).  The first work item of
         // a CTA is its own index (the counter starts at gridDim.x), so a batch that fits one wave -- a PT step
-        // at the reference's size -- runs without a single atomic round trip.
+        // at the reference's size, every shared batch -- runs without a single atomic round trip.
         if (round > 0) {
-            if (n_chains <= (int)gridDim.x) break;
-            if (tid == 0) s_chain = atomicAdd(counter, 1);
+            if (n_work <= (int)gridDim.x) break;
+            if (tid == 0) s_work = atomicAdd(counter, 1);
             __syncthreads();
         }
-        const int chain = round == 0 ? (int)blockIdx.x : s_chain;
-        if (chain >= n_chains) break;
+        const int work = round == 0 ? (int)blockIdx.x : s_work;
+        if (work >= n_work) break;
+        // (a shared chain's work item is always the block index: chains x parts never exceeds the grid)
+        const int chain = nparts == 1 ? work : (int)blockIdx.x / nparts;
+        const int part = nparts == 1 ? 0 : (int)blockIdx.x % nparts;
+        // scratch region: the CTA's own, or -- when several CTAs share a chain -- the chain's
+        uint64_t* tmpl = scratch + (size_t)(nparts == 1 ? (int)blockIdx.x : chain) * region_stride;
+        uint64_t* gbufB = tmpl + key_stride;
+        uint64_t* gbufC = tmpl + 2 * key_stride;
+        double* partials = reinterpret_cast<double*>(tmpl + 3 * key_stride);  // [nseg][2][kThreads]
+        const SelectBuf bufs[4] = {{sm.candB, kCandB}, {sm.candA, kCandA}, {gbufB, (int)key_stride}, {gbufC, (int)key_stride}};
         {
             const double* src = reinterpret_cast<const double*>(cc_all + chain);
             double* dst = reinterpret_cast<double*>(&sm.cc);
@@ -201,15 +227,18 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
 
         if (nan_model || (roche && lc_out == nullptr) || N <= 0) {
             // quirk Q13: the reference evaluates the model and then discards it on Roche overflow
-            if (lc_out != nullptr)
-                for (int i = tid; i < N; i += kThreads) lc_out[(size_t)chain * N + i] = qnan;
-            if (tid == 0 && logL != nullptr)
-                logL[chain] = roche ? -0.5 * kBig : (nan_model ? qnan : -0.5 * cc.chi2_extra);
+            if (part == 0) {
+                if (lc_out != nullptr)
+                    for (int i = tid; i < N; i += kThreads) lc_out[(size_t)chain * N + i] = qnan;
+                if (tid == 0 && logL != nullptr)
+                    logL[chain] = roche ? -0.5 * kBig : (nan_model ? qnan : -0.5 * cc.chi2_extra);
+            }
             __syncthreads();
             continue;
         }
+        if (tid == 0 && part == 0 && evaluated != nullptr) atomicAdd(evaluated, 1ull);
 
-        // ---- E(M) starter table for chains whose solve is path-independent (0 <= e <= 0.8) ----
+        // ---- E(M) starter table for chains whose solve is path-independent where the table is used ----
         const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= 4 * kTableSize);
         const double* ktab = use_table ? sm.ktab : nullptr;
         if (use_table) {
@@ -221,6 +250,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const bool bracketed = N > kCandA / 2;
         uint64_t* cand = sm.candA;  // first-round survivors
         int cand_cap = kCandA;
+        bool cand_small = true;  // the candidate list is the shared-memory one
         double lo = -INFINITY, hi = INFINITY;
         if (bracketed) {
             const uint32_t seed = (uint32_t)cc.seed;
@@ -230,9 +260,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             int r_lo, r_hi, r_mid;
             bracket_ranks(kThreads, N, krank, bracket_sigma, r_lo, r_hi, r_mid);
             const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)kThreads);
-            if ((int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // large N: survivors go to global scratch
+            if (nparts > 1 || (int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // survivors go to global scratch
                 cand = gbufB;
-                cand_cap = N;
+                cand_cap = (int)key_stride;
+                cand_small = false;
             }
             if (tid == 0) {
                 sm.ctl.cnt = 0;
@@ -257,21 +288,37 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const double u0 = sm.pivot;
         const double A = cc.ft * (1.0 - cc.blend), ft = cc.ft;
 
-        // ---- model pass: kPointsPerThread samples per thread and iteration ----
+        // ---- model pass: one sample per thread and iteration ----
         // The template keys go to global scratch only when something will read them back: light-curve
         // output, the small-N direct chi^2, or the re-run after a missed bracket (below).  The common
         // logL-only pass keeps everything on chip: no store, no address arithmetic for it.
         int nanflag = 0, c_lt = 0;
-        double S0 = 0., S1 = 0., S2 = 0.;
+        double S0 = 0., S1 = 0.;
         constexpr int V = kPointsPerThread;
+        static_assert(V == 1, "the segment bookkeeping of the pass is written for one sample per thread and iteration");
         int hi_acc = 0;  // largest sincos argument exponent of the hot pass (checked once, below)
-        auto model_pass = [&](auto store_tag, auto data_tag) {
+        ChainSync* const sync = sync_all + (nparts == 1 ? 0 : chain);
+        auto model_pass = [&](auto store_tag, auto data_tag, auto part_tag) {
         constexpr bool kStore = decltype(store_tag)::value;
         constexpr bool kHot = !kStore;  // the logL-only pass defers the sincos range check to the end of the chain
         constexpr bool kData = decltype(data_tag)::value;  // fw != nullptr, known at compile time in the hot variant
+        constexpr bool kPart = decltype(part_tag)::value;  // this CTA evaluates one part of a chain shared by nparts CTAs
+        static_assert(!(kStore && kPart), "parts are logL-only");
+        // the tiles of this pass: the whole light curve, or the part's run of segments
+        int tile_first = 0, tile_last = n_tiles;
+        if (kPart) {
+            const int spp = (nseg + nparts - 1) / nparts;  // segments per part (the last parts may get fewer, or none)
+            tile_first = min((part * spp) << seg_shift, n_tiles);
+            tile_last = min(((part + 1) * spp) << seg_shift, n_tiles);
+        }
+        // running sums of a CTA that owns its chain: in shared memory (the select's work area is idle now),
+        // so that the per-segment sums can restart without costing registers
+        double* const tsum = reinterpret_cast<double*>(sm.candB);  // [2][kThreads]
+        if (kData && !kPart) tsum[tid] = tsum[kThreads + tid] = 0.0;
         nanflag = 0;
         c_lt = 0;
-        S0 = S1 = S2 = 0.;
+        S0 = S1 = 0.;
+        if (tile_first >= tile_last) return;
 #if HB_TMA_STAGING
         // the data arrays are padded to whole tiles by the host side, so every copy is a full tile
         auto issue_tile = [&](int tile, uint32_t g) {
@@ -281,13 +328,13 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             bulk_g2s(sm.stage[st].ts, tsec + off, tile_bytes, &sm.full_bar[st]);
             if (fw != nullptr) bulk_g2s(sm.stage[st].fw, fw + off, 2 * tile_bytes, &sm.full_bar[st]);
         };
-        if (tid == 0) issue_tile(0, git);  // every stage is free here: the chain-level barriers drained the pipe
-        for (int tile = 0; tile < n_tiles; tile++, git++) {
+        if (tid == 0) issue_tile(tile_first, git);  // every stage is free here: the chain-level barriers drained the pipe
+        for (int tile = tile_first; tile < tile_last; tile++, git++) {
             const int base = tile * kTile;
             const int st = git % kStages;
-            if (tid == 0 && tile + 1 < n_tiles) {
+            if (tid == 0 && tile + 1 < tile_last) {
                 // next tile into the other stage, once every warp has taken the previous tile out of it
-                if (tile >= 1) mbar_wait(&sm.empty_bar[(git + 1) % kStages], ((git - 1) / kStages) & 1);
+                if (tile > tile_first) mbar_wait(&sm.empty_bar[(git + 1) % kStages], ((git - 1) / kStages) & 1);
                 issue_tile(tile + 1, git + 1);
             }
             mbar_wait(&sm.full_bar[st], (git / kStages) & 1);
@@ -308,11 +355,11 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         // (the arrays are padded to whole tiles, so no index clamp is needed)
         double ts_next[V];
 #pragma unroll
-        for (int j = 0; j < V; j++) ts_next[j] = tsec[j * kThreads + tid];
+        for (int j = 0; j < V; j++) ts_next[j] = tsec[tile_first * kTile + j * kThreads + tid];
         // this thread's first sample of the tile, carried in a register the compiler cannot re-derive
         // (it would otherwise rebuild it from the tile counter and SR_TID twice per iteration)
-        int i0 = tid;
-        for (int tile = 0; tile < n_tiles; tile++, i0 += kTile) {
+        int i0 = tile_first * kTile + tid;
+        for (int tile = tile_first; tile < tile_last; tile++, i0 += kTile) {
             asm volatile("" : "+r"(i0));
             int idx[V];
             double ts[V], u[V], fl[V], wv[V];
@@ -320,7 +367,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             for (int j = 0; j < V; j++) {
                 idx[j] = i0 + j * kThreads;
                 ts[j] = ts_next[j];
-                if (tile + 1 < n_tiles) ts_next[j] = tsec[idx[j] + kTile];
+                if (tile + 1 < tile_last) ts_next[j] = tsec[idx[j] + kTile];
                 fl[j] = wv[j] = 0.0;
                 if (kData) {  // one 16-byte load: {flux, 1/sigma} are interleaved
                     const double2 v = fw[idx[j]];
@@ -344,11 +391,12 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 if (mask) {
                     const int leader = __ffs(mask) - 1;
                     int basepos = 0;
-                    if (lane == leader) basepos = atomicAdd(&sm.ctl.cnt, __popc(mask));
+                    if (lane == leader) basepos = kPart ? atomicAdd(&sync->cnt, __popc(mask)) : atomicAdd(&sm.ctl.cnt, __popc(mask));
                     basepos = __shfl_sync(0xffffffffu, basepos, leader);
                     if (inr) {
                         const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
-                        if (pos < cand_cap) cand[pos] = dkey(uj);
+                        // (the list in global scratch holds a whole light curve: only the shared-memory one can overflow)
+                        if (!cand_small || pos < kCandA) cand[pos] = dkey(uj);
                     }
                 }
                 if (kData) {  // padded samples carry weight 0 and a finite model: they add exactly 0
@@ -357,34 +405,119 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                     const double r = a * wi;
                     S0 = fma(r, r, S0);
                     S1 = fma(r, wi, S1);
-                    S2 = fma(wi, wi, S2);
                 }
             }
-        }
-        if (kData) nanflag = (S0 != S0);
-        };
-        // two instantiations: the hot logL-only pass, and a general one (template stored) for
-        // light-curve output, small N and the re-run after a missed bracket
-        const bool store_template = (lc_out != nullptr) || !bracketed || (fw == nullptr);
-        auto general_pass = [&]() {
-            if (fw != nullptr) model_pass(std::true_type{}, std::true_type{});
-            else model_pass(std::true_type{}, std::false_type{});
-        };
-        bool have_template = store_template;
-        if (store_template) {
-            general_pass();
-        } else {
-            model_pass(std::false_type{}, std::true_type{});
-            // a Newton iterate left the table sincos' range somewhere in this chain (e -> 1 only): the sums are
-            // not trustworthy; evaluate the chain again with the per-sample check and the library fallback
-            if (__syncthreads_or(hi_acc > hot_hi_limit)) {
-                if (tid == 0) sm.ctl.cnt = 0;
-                __syncthreads();
-                general_pass();
-                have_template = true;
+            // a segment (or the pass) ends with this tile: this thread's sums of the segment join the running
+            // sums in segment order -- here, or (a part) through the chain's scratch at the hands of the finisher
+            // (the segment's end is read off the bits of the sample index, the pass's end off the tile counter: the
+            // latter then serves loop control alone and stays in a uniform register)
+#if HB_TMA_STAGING
+            const int i_here = tile * kTile + tid;
+#else
+            const int i_here = i0;
+#endif
+            if (kData && ((((i_here + kTile) & seg_bits) == 0) || tile + 1 == tile_last)) {
+                if (kPart) {
+                    const int seg = tile >> seg_shift;
+                    partials[(size_t)(2 * seg) * kThreads + tid] = S0;
+                    partials[(size_t)(2 * seg + 1) * kThreads + tid] = S1;
+                } else {
+                    tsum[tid] += S0;
+                    tsum[kThreads + tid] += S1;
+                }
+                S0 = S1 = 0.;
             }
         }
-        const int any_nan = __syncthreads_or(nanflag);
+        };
+        // instantiations: the hot logL-only pass (whole chain / one part), and a general one (template stored) for
+        // light-curve output, small N and the re-run after a missed bracket
+        const bool store_template = (lc_out != nullptr) || !bracketed || (fw == nullptr);
+        auto general_pass = [&]() {  // the whole chain, by this CTA alone
+            if (tid == 0) sm.ctl.cnt = 0;
+            __syncthreads();
+            if (fw != nullptr) model_pass(std::true_type{}, std::true_type{}, std::false_type{});
+            else model_pass(std::true_type{}, std::false_type{}, std::false_type{});
+        };
+        auto load_sums = [&](bool from_parts) {  // this thread's chi^2 sums: its segment sums added in segment order
+            if (fw == nullptr) return;
+            if (!from_parts) {
+                const double* tsum = reinterpret_cast<const double*>(sm.candB);
+                S0 = tsum[tid];
+                S1 = tsum[kThreads + tid];
+            } else {  // written by the other CTAs of the chain: read from L2, eight loads in flight
+                S0 = S1 = 0.;
+                for (int seg = 0; seg < nseg; seg += 4) {
+                    double p0[4], p1[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int sg = seg + k < nseg ? seg + k : nseg - 1;
+                        p0[k] = __ldcg(&partials[(size_t)(2 * sg) * kThreads + tid]);
+                        p1[k] = __ldcg(&partials[(size_t)(2 * sg + 1) * kThreads + tid]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (seg + k < nseg) {
+                            S0 += p0[k];
+                            S1 += p1[k];
+                        }
+                }
+            }
+            nanflag = (S0 != S0);
+        };
+        bool have_template = store_template;
+        int c_in;
+        if (store_template) {
+            general_pass();
+            c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
+            c_in = sm.ctl.cnt;
+            load_sums(false);
+        } else {
+            if (nparts == 1) model_pass(std::false_type{}, std::true_type{}, std::false_type{});
+            else model_pass(std::false_type{}, std::true_type{}, std::true_type{});
+            // a Newton iterate left the table sincos' range somewhere in this chain (e -> 1 only): the sums are
+            // not trustworthy; the chain is evaluated again with the per-sample check and the library fallback
+            int redo = __syncthreads_or(hi_acc > hot_hi_limit);
+            c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
+            if (nparts > 1) {
+                // hand-over: this part's counts and flags to the chain's sync words; the last part to arrive
+                // finishes the chain.  Every thread's stores (segment sums, candidate keys) are fenced before the
+                // barrier in front of thread 0's ticket.
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    atomicAdd(&sync->c_lt, c_lt);
+                    if (redo) atomicOr(&sync->flags, 1);
+                    __threadfence();
+                    const int ticket = atomicAdd(&sync->done, 1);
+                    sm.bcast[0] = (ticket == nparts - 1);
+                    if (ticket == nparts - 1) {
+                        __threadfence();
+                        sm.bcast[1] = atomicAdd(&sync->c_lt, 0);
+                        sm.bcast[2] = atomicAdd(&sync->cnt, 0);
+                        sm.bcast[3] = atomicAdd(&sync->flags, 0);
+                        sync->cnt = 0; sync->c_lt = 0; sync->done = 0; sync->flags = 0;  // ready for the next launch
+                    }
+                }
+                __syncthreads();
+                if (!sm.bcast[0]) continue;  // not the last: on to the next work item
+                __threadfence();
+                c_lt = sm.bcast[1];
+                c_in = sm.bcast[2];
+                redo = sm.bcast[3];
+            } else {
+                c_in = sm.ctl.cnt;
+            }
+            if (redo) {
+                general_pass();
+                have_template = true;
+                c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
+                c_in = sm.ctl.cnt;
+                load_sums(false);
+            } else {
+                load_sums(nparts > 1);
+            }
+        }
+        const int any_nan = __syncthreads_or(nanflag);  // (also the barrier between reading cnt and the select's reset of it)
         if (any_nan) {
             if (lc_out != nullptr)
                 for (int i = tid; i < N; i += kThreads) lc_out[(size_t)chain * N + i] = qnan;
@@ -394,26 +527,23 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         }
 
         // ---- exact order statistic ----
-        c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
-        const int c_in = sm.ctl.cnt;
-        __syncthreads();
         const uint32_t seed2 = (uint32_t)cc.seed ^ 0x9e3779b9u;
         uint64_t mkey;
         if (krank >= c_lt && krank < c_lt + c_in && c_in <= cand_cap) {
             // the candidates lie between two order statistics of the pre-sample: one histogram pass finds the
             // bin of the median (hb_select.cuh); sampling rounds only when that fails (ties) or there is no bracket
             if (!(bracketed && c_in > kThreads &&
-                  block_select_hist<kThreads>(cand, c_in, krank - c_lt, lo, hi, sm.ctl, sm.candB, &mkey)))
-                mkey = block_select_key<kThreads>(cand, c_in, krank - c_lt, sm.ctl, bufs, 4, seed2);
+                  block_select_hist<kThreads>(cand, c_in, krank - c_lt, lo, hi, sm.ctl, sm.candB, &mkey))) {
+                mkey = block_select_key<kThreads>(cand, c_in, krank - c_lt, sm.ctl, bufs, 4, seed2);  // (skips the buffer it reads)
+            }
         }
         else {
             // the bracket missed (or overflowed; ~1 % of chains by construction of the 2.5 sigma bracket):
             // evaluate the chain once more, this time storing the template, and select on that
             if (!have_template) {
-                if (tid == 0) sm.ctl.cnt = 0;
-                __syncthreads();
                 general_pass();
                 __syncthreads();
+                load_sums(false);
             }
             mkey = block_select_key<kThreads>(tmpl, N, krank, sm.ctl, bufs, 4, seed2);
         }
@@ -438,31 +568,27 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                         S0 = fma(r, r, S0);
                     }
                 S1 = 0.;
-                S2 = 0.;
             }
-            // three block sums in one go
+            // two block sums in one go
             const int wid = tid >> 5;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 S0 += __shfl_xor_sync(0xffffffffu, S0, o);
                 S1 += __shfl_xor_sync(0xffffffffu, S1, o);
-                S2 += __shfl_xor_sync(0xffffffffu, S2, o);
             }
             if (lane == 0) {
                 sm.red[wid] = S0;
                 sm.red[32 + wid] = S1;
-                sm.red[64 + wid] = S2;
             }
             __syncthreads();
             if (tid == 0) {
-                double t0 = 0., t1 = 0., t2 = 0.;
+                double t0 = 0., t1 = 0.;
                 for (int i = 0; i < kThreads / 32; i++) {
                     t0 += sm.red[i];
                     t1 += sm.red[32 + i];
-                    t2 += sm.red[64 + i];
                 }
                 const double d = -A * (med - u0);
-                const double chi2 = bracketed ? t0 + d * (2.0 * t1 + d * t2) : t0;
+                const double chi2 = bracketed ? t0 + d * (2.0 * t1 + d * sum_w2) : t0;
                 logL[chain] = roche ? -0.5 * kBig : -0.5 * (chi2 + cc.chi2_extra);
             }
         }
@@ -650,7 +776,7 @@ cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, Cha
                             int eval_grid, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter, eval_grid < n ? eval_grid : n);
+    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter, eval_grid);
     return cudaGetLastError();
 }
 
@@ -660,14 +786,29 @@ cudaError_t configure_eval()
                                 (int)sizeof(EvalShared));
 }
 
-cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
-                              int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
-                              int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s)
+// Segments of the time axis: runs of 2^shift tiles (at least 4 tiles; doubled until at most kMaxSegments segments
+// cover the light curve) -- a function of the light curve's length alone; the summation order of the chi^2 follows it.
+int eval_seg_shift(long n_points)
 {
-    if (n_chains <= 0) return cudaSuccess;
-    if (grid > n_chains) grid = n_chains;  // *counter was set to this grid by the k_prologue launch in front of this one
-    k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(cc, n_chains, t, fw, N, scratch,
-                                                                               scratch_stride, logL, lc_out, counter, bracket_sigma, sctab, hot_hi_limit);
+    const long n_tiles = (n_points + kTile - 1) / kTile;
+    int shift = 2;
+    while (((n_tiles + (1L << shift) - 1) >> shift) > kMaxSegments) shift++;
+    return shift;
+}
+int eval_segments(long n_points)
+{
+    const long n_tiles = std::max(1L, (n_points + kTile - 1) / kTile);
+    const int shift = eval_seg_shift(n_points);
+    return (int)((n_tiles + (1L << shift) - 1) >> shift);
+}
+
+cudaError_t launch_chain_eval(const EvalArgs& a, int grid, cudaStream_t s)
+{
+    if (a.n_chains <= 0) return cudaSuccess;
+    // *counter was set to this grid by the k_prologue launch in front of this one
+    k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(
+        a.cc, a.n_chains, a.tsec, a.fw, a.N, a.scratch, a.region_stride, a.key_stride, a.logL, a.lc_out, a.counter, a.bracket_sigma,
+        a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, a.nparts, a.nseg, a.seg_shift);
     return cudaGetLastError();
 }
 

@@ -28,17 +28,51 @@ struct MagSetup;
 constexpr int kPointsPerThread = HB_POINTS_PER_THREAD;  // independent samples in flight per thread
 constexpr int kEvalThreads = HB_EVAL_THREADS;  // threads per CTA of k_chain_eval
 constexpr int kEvalCtasPerSm = HB_EVAL_CTAS;   // resident CTAs per SM (sets the register budget)
-constexpr int kCandA = HB_CAND_A;              // shared-memory survivor buffers of the select (keys)
-constexpr int kCandB = HB_CAND_B;
+constexpr int kCandA = HB_CAND_A;              // shared-memory candidate list of short light curves / survivor buffer of the select (keys)
+constexpr int kCandB = HB_CAND_B;              // work area of the select (keys); running chi^2 sums during the model pass
+
+constexpr int kMaxSegments = 64;                // most segments (hence CTAs) one light curve is cut into
+
+// hand-over words of a chain whose light curve is shared by several CTAs (zero between launches)
+struct ChainSync {
+    int cnt;    // candidate keys appended to the chain's flat list
+    int c_lt;   // samples below the bracket
+    int done;   // parts that have finished
+    int flags;  // bit 0: a part saw a Newton iterate outside the table sincos' range
+};
+
+// arguments of k_chain_eval
+struct EvalArgs {
+    const ChainConst* cc;  // [n_chains], from k_prologue
+    int n_chains;
+    int N;                 // samples per light curve
+    const double* tsec;    // t * 86400, padded with one whole tile beyond the last (partial) one
+    const double2* fw;     // {flux, 1 / max(sigma, 1e-5)}, padded likewise with weight 0; nullptr: model only
+    double sum_w2;         // sum of the squared weights (S2 of the chi^2 expansion), formed once per data set
+    uint64_t* scratch;     // per region: template keys, two key buffers (key_stride each), nseg x 2 x threads partial sums
+    size_t region_stride, key_stride;
+    double* logL;          // [n_chains] or nullptr
+    double* lc_out;        // [n_chains][N] or nullptr
+    int* counter;          // work-item scheduler (armed by k_prologue)
+    unsigned long long* evaluated;  // += 1 per chain whose model is really evaluated (not Roche / NaN early-outs)
+    ChainSync* sync;       // [n_chains] when nparts > 1
+    const double2* sctab;
+    float bracket_sigma;
+    int hot_hi_limit;
+    int nparts;            // CTAs per chain (each takes a contiguous run of segments)
+    int nseg;              // eval_segments(N)
+    int seg_shift;         // eval_seg_shift(N): a segment is 2^seg_shift tiles
+};
 
 size_t eval_smem_bytes();
-int eval_tile();  // samples per TMA tile: device time / flux / weight arrays are padded to a multiple of it
+int eval_tile();  // samples per tile: device time / flux / weight arrays are padded to whole tiles plus one
+int eval_segments(long n_points);
+int eval_seg_shift(long n_points);
 cudaError_t configure_eval();
+// eval_grid: the grid of the k_chain_eval launch that follows (its work-item counter starts there)
 cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, ChainConst* out, int* eval_counter,
                             int eval_grid, cudaStream_t s);
-cudaError_t launch_chain_eval(const ChainConst* cc, int n_chains, const double* t, const double2* fw,
-                              int N, uint64_t* scratch, size_t scratch_stride, int grid, double* logL, double* lc_out,
-                              int* counter, float bracket_sigma, const double2* sctab, int hot_hi_limit, cudaStream_t s);
+cudaError_t launch_chain_eval(const EvalArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_order_stat(const double* x, int n, int k, uint64_t* scratch, size_t stride, double* out,
                               cudaStream_t s);
 cudaError_t launch_subtract(double* arr, int n, const double* value, cudaStream_t s);

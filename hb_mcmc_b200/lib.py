@@ -29,6 +29,7 @@ ABI_SYMBOLS = (
     "hb_set_data", "hb_set_mags", "hb_loglikelihood_batch", "hb_loglikelihood_batch_dev", "hb_light_curve_batch",
     "hb_calc_light_curve", "hb_chain_info_batch", "hb_traj", "hb_order_statistic", "hb_remove_median", "hb_scalar", "hb_gaia_batch", "hb_fp64_peak",
     "hb_time_kernels", "hb_last_eval_kernel_ms", "hb_launch_count", "hb_set_bracket_sigma", "hb_set_sincos_range",
+    "hb_set_max_parts", "hb_evaluated_chains",
     "hb_pt_create", "hb_pt_destroy", "hb_pt_init_random", "hb_pt_set_state", "hb_pt_step", "hb_pt_iteration",
     "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
     "hb_pt_get_counters", "hb_pt_device_logL", "hb_pt_cold_logL_dev",
@@ -80,6 +81,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_fp64_peak.argtypes = [vp, d, _dp]
     L.hb_set_bracket_sigma.argtypes = [vp, d]
     L.hb_set_sincos_range.argtypes = [vp, d]
+    L.hb_set_max_parts.argtypes = [vp, i]
+    L.hb_evaluated_chains.argtypes = [vp, C.POINTER(C.c_ulonglong), i]
     L.hb_time_kernels.argtypes = [vp, i]
     L.hb_last_eval_kernel_ms.argtypes = [vp, _dp]
     L.hb_launch_count.argtypes = [vp]
@@ -284,6 +287,16 @@ class Context:
     def set_sincos_range(self, max_abs: float) -> None:
         """|E| above which the logL-only pass re-evaluates a chain with the libm fallback (test knob)."""
         self._ck(self._L.hb_set_sincos_range(self._h, float(max_abs)))
+
+    def set_max_parts(self, max_parts: int) -> None:
+        """Most CTAs one light curve may be spread over in small batches (latency knob; results do not depend on it)."""
+        self._ck(self._L.hb_set_max_parts(self._h, int(max_parts)))
+
+    def evaluated_chains(self, reset: bool = False) -> int:
+        """Chains whose model was really evaluated since the last reset (Roche / e >= 1 early-outs are not counted)."""
+        out = C.c_ulonglong()
+        self._ck(self._L.hb_evaluated_chains(self._h, C.byref(out), int(reset)))
+        return int(out.value)
 
     def time_kernels(self, enable: bool = True) -> None:
         self._ck(self._L.hb_time_kernels(self._h, int(enable)))

@@ -168,6 +168,14 @@ int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops);
  * and selected exactly, so the result never depends on this value -- only the cost does (0 forces every
  * chain down the miss path; the tests use that). */
 int hb_set_bracket_sigma(hb_ctx* ctx, double sigma);
+/* Batches smaller than the grid: k_chain_eval spreads every light curve over up to max_parts CTAs (a power of two
+ * between 1 and 64; default 64; 1 = one CTA per chain always).  The chi^2 is summed per time segment and in segment
+ * order whatever the spread is, so a chain's logL does not depend on this value or on the size of the batch it
+ * arrives in -- only the latency of small batches does (likelihood3.c:147,649,822 loop serially over the samples). */
+int hb_set_max_parts(hb_ctx* ctx, int max_parts);
+/* Chains whose model was really evaluated by the likelihood kernel since the last reset (Roche-overflow and e >= 1
+ * chains return early without touching the light curve, quirk Q13, and are NOT counted). */
+int hb_evaluated_chains(hb_ctx* ctx, unsigned long long* count, int reset);
 /* Second test knob.  The logL-only pass of k_chain_eval does not range-check its table sincos per sample: it
  * records the largest |E| any Newton iterate of the chain reached and, when that exceeds max_abs (default and
  * maximum 1024, the validity range of the table sincos), evaluates the chain again with the per-sample check
