@@ -50,11 +50,11 @@ def _glob(d: str, exts: tuple[str, ...]) -> list[str]:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("hb_kernels.cu", "hb_capi.cu", "hb_pt.cu", "hb_gaia_pt.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("hb_kernels.cu", "hb_capi.cu", "hb_pt.cu", "hb_gaia_pt.cu", "hb_comm.cu")]
     srcs = [s for s in srcs if os.path.exists(s)]
     deps = _glob(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "hb_b200.h")]
     if force or _stale(LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-ldl"]
         subprocess.run(cmd, check=True, cwd=CSRC)
     return LIB
 
@@ -78,7 +78,7 @@ def build_driver(force: bool = False) -> str | None:
             continue
         if force or _stale(target, [src, LIB, os.path.join(ROOT, "include", "hb_b200.h")]):
             cmd = ["gcc", "-O2", "-std=gnu99", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", target, src, "-L", CSRC,
-                   "-lhb_b200", "-Wl,-rpath," + CSRC, "-lm"]
+                   "-lhb_b200", "-Wl,-rpath," + CSRC, "-lm", "-lpthread"]
             subprocess.run(cmd, check=True, cwd=HOST_DIR)
         built = built or target
     return built

@@ -12,6 +12,7 @@
 #include "../../include/hb_b200.h"
 #include "hb_device.cuh"
 #include "hb_kernels.h"
+#include "hb_comm.h"
 #include "hb_gaia_pt.cuh"
 #include "hb_pt.cuh"
 #include "hb_sincos_tab.h"
@@ -798,6 +799,12 @@ struct hb_pt {
     int *index = nullptr, *jump = nullptr;
     unsigned long long* counters = nullptr;
     unsigned* d_iter = nullptr;  // [0] iteration, [1] arrival ticket of k_pt_swap
+    // evaluation shard (hb_pt_set_eval_shard): every rank holds the whole sampler state and proposes, accepts and
+    // swaps redundantly; the likelihood -- all of the cost -- is evaluated for the walkers [eval_first,
+    // eval_first + eval_count) only and the logL vector is all-gathered (chunk doubles per rank, in place)
+    int shard_rank = 0, shard_world = 1;
+    long eval_first = 0, eval_count = 0, chunk = 0;
+    hb_comm* comm = nullptr;  // NCCL communicator of the all-gather (not owned); nullptr: host-driven exchange
     // one iteration captured as a CUDA graph (the step is latency-bound at the reference's sizes)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -807,6 +814,7 @@ struct hb_pt {
     unsigned long graph_generation = 0;
 };
 constexpr long kPtGraphIters = 8;
+constexpr int kPtMaxShards = 64;  // most ranks the evaluation of one sampler is sharded over
 
 namespace {
 
@@ -853,11 +861,18 @@ extern "C" {
 int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc_period, unsigned long long seed,
                  double dtemp, int npast, int quirks)
 {
+    return hb_pt_create_sharded(ctx, out, n_temps, n_ens, 0, log_lc_period, seed, dtemp, npast, quirks);
+}
+
+int hb_pt_create_sharded(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, int ens_offset, double log_lc_period,
+                         unsigned long long seed, double dtemp, int npast, int quirks)
+{
     if (!ctx || !out) return HB_ERR_ARG;
     *out = nullptr;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (n_temps < 1 || n_temps > kPtMaxTemps || n_ens < 1 || npast < 2 || !(dtemp > 1.0))
-        return fail_arg(ctx, "hb_pt_create: need 1 <= n_temps <= 128, n_ens >= 1, npast >= 2, dtemp > 1");
+    if (n_temps < 1 || n_temps > kPtMaxTemps || n_ens < 1 || npast < 2 || !(dtemp > 1.0) || ens_offset < 0 ||
+        ((long)ens_offset + n_ens) * n_temps > 0x7fffffffL)
+        return fail_arg(ctx, "hb_pt_create: need 1 <= n_temps <= 128, n_ens >= 1, ens_offset >= 0, npast >= 2, dtemp > 1");
     if (!ctx->has_data) {
         ctx->err = "hb_pt_create: hb_set_data has not been called";
         return HB_ERR_STATE;
@@ -868,6 +883,7 @@ int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc
     PtConfig& c = pt->cfg;
     std::memset(&c, 0, sizeof(c));
     c.n_temps = n_temps; c.n_ens = n_ens; c.npast = npast; c.quirks = quirks ? 1 : 0;
+    c.ens_offset = ens_offset;
     c.seed = seed; c.dtemp = dtemp;
     c.temp[0] = 1.0;
     for (int i = 1; i < n_temps; i++) c.temp[i] = c.temp[i - 1] * dtemp;
@@ -876,10 +892,12 @@ int hb_pt_create(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, double log_lc
     c.gamma = 2.388 / sqrt(2. * kPtNpars);
     fill_limits(c, ctx->ms.use_gmag, ctx->ms.use_color);
     const int W = pt->W = n_temps * n_ens;
+    pt->eval_count = pt->chunk = W;
     const size_t wd = (size_t)W * sizeof(double);
     bool ok = cudaMalloc((void**)&pt->d_cfg, sizeof(PtConfig)) == cudaSuccess &&
               cudaMalloc((void**)&pt->x, wd * kPtNpars) == cudaSuccess && cudaMalloc((void**)&pt->y, wd * kPtNpars) == cudaSuccess &&
-              cudaMalloc((void**)&pt->logLx, wd) == cudaSuccess && cudaMalloc((void**)&pt->logLy, wd) == cudaSuccess &&
+              cudaMalloc((void**)&pt->logLx, wd) == cudaSuccess &&
+              cudaMalloc((void**)&pt->logLy, wd + kPtMaxShards * sizeof(double)) == cudaSuccess &&  // padded to whole chunks
               cudaMalloc((void**)&pt->logPy, wd) == cudaSuccess && cudaMalloc((void**)&pt->tmp, wd * (kPtNpars + 1)) == cudaSuccess &&
               cudaMalloc((void**)&pt->history, wd * kPtNpars * (size_t)npast) == cudaSuccess &&
               cudaMalloc((void**)&pt->xmap, (size_t)n_ens * kPtNpars * sizeof(double)) == cudaSuccess &&
@@ -949,18 +967,33 @@ int hb_pt_set_state(hb_pt* pt, const double* x)
     return pt_eval_current(pt);
 }
 
-// enqueue the kernels of ONE iteration on the context's stream
-static int pt_enqueue_step(hb_pt* pt)
+// enqueue the kernels of ONE iteration on the context's stream.  phases: 1 = propose + likelihood of this rank's
+// shard (+ the NCCL all-gather when a communicator is bound), 2 = accept + swaps, 3 = both
+static int pt_enqueue_step(hb_pt* pt, int phases = 3)
 {
     hb_ctx* ctx = pt->ctx;
     int rc;
-    CK(launch_pt_propose(pt->d_cfg, pt->d_iter, pt->x, pt->index, pt->history, pt->y, pt->logPy, pt->jump, pt->W, ctx->stream));
-    if ((rc = run_eval(ctx, pt->y, pt->W, ctx->d_t, ctx->d_fw, ctx->N, pt->logLy, nullptr)) != HB_OK) return rc;
-    CK(launch_pt_accept(pt->d_cfg, pt->d_iter, pt->x, pt->y, pt->logLx, pt->logLy, pt->logPy, pt->jump, pt->index, pt->history,
-                        pt->counters, pt->W, ctx->stream));
-    CK(launch_pt_swap(pt->d_cfg, pt->d_iter, pt->index, pt->logLx, pt->x, pt->counters, pt->xmap, pt->logLmap, pt->cfg.n_ens,
-                      ctx->stream));
-    ctx->launches += 3;
+    if (phases & 1) {
+        CK(launch_pt_propose(pt->d_cfg, pt->d_iter, pt->x, pt->index, pt->history, pt->y, pt->logPy, pt->jump, pt->W, ctx->stream));
+        ctx->launches += 1;
+        if (pt->eval_count > 0 &&
+            (rc = run_eval(ctx, pt->y + (size_t)pt->eval_first * kPtNpars, pt->eval_count, ctx->d_t, ctx->d_fw, ctx->N,
+                           pt->logLy + pt->eval_first, nullptr)) != HB_OK)
+            return rc;
+        if (pt->shard_world > 1 && pt->comm != nullptr) {
+            if (hb::comm_allgather_inplace(pt->comm, pt->logLy, (size_t)pt->chunk, ctx->stream) != HB_OK) {
+                ctx->err = std::string("hb_pt_step: ") + hb_comm_last_error();
+                return HB_ERR_CUDA;
+            }
+        }
+    }
+    if (phases & 2) {
+        CK(launch_pt_accept(pt->d_cfg, pt->d_iter, pt->x, pt->y, pt->logLx, pt->logLy, pt->logPy, pt->jump, pt->index, pt->history,
+                            pt->counters, pt->W, ctx->stream));
+        CK(launch_pt_swap(pt->d_cfg, pt->d_iter, pt->index, pt->logLx, pt->x, pt->counters, pt->xmap, pt->logLmap, pt->cfg.n_ens,
+                          ctx->stream));
+        ctx->launches += 2;
+    }
     return HB_OK;
 }
 
@@ -971,6 +1004,11 @@ int hb_pt_step(hb_pt* pt, long n_iters)
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     int rc;
+    if (pt->shard_world > 1 && pt->comm == nullptr) {
+        ctx->err = "hb_pt_step: the evaluation is sharded but no communicator is bound (hb_pt_set_comm), use hb_pt_step_begin / "
+                   "hb_pt_exchange_local / hb_pt_step_end";
+        return HB_ERR_STATE;
+    }
     if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
     // Several iterations in one call: replay a captured graph of one iteration (6 nodes) instead of
     // issuing 6 launches per iteration.  The graph is re-captured when the context's buffers or
@@ -1014,6 +1052,97 @@ int hb_pt_step(hb_pt* pt, long n_iters)
             return rc;
         }
         pt->iter++;
+    }
+    return HB_OK;
+}
+
+int hb_pt_set_eval_shard(hb_pt* pt, int rank, int world)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (world < 1 || world > kPtMaxShards || rank < 0 || rank >= world)
+        return fail_arg(ctx, "hb_pt_set_eval_shard: need 0 <= rank < world <= 64");
+    pt->shard_rank = rank;
+    pt->shard_world = world;
+    pt->chunk = (pt->W + world - 1) / world;  // walkers per rank; the logL buffer is padded to world whole chunks
+    pt->eval_first = std::min<long>((long)rank * pt->chunk, pt->W);
+    pt->eval_count = std::min<long>(pt->chunk, pt->W - pt->eval_first);
+    ctx->generation++;  // captured steps are stale
+    return HB_OK;
+}
+
+int hb_pt_set_comm(hb_pt* pt, hb_comm* comm)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (comm && (hb::comm_rank(comm) != pt->shard_rank || hb::comm_world(comm) != pt->shard_world))
+        return fail_arg(ctx, "hb_pt_set_comm: the communicator's rank / size differ from the evaluation shard's");
+    pt->comm = comm;
+    ctx->generation++;
+    return HB_OK;
+}
+
+int hb_pt_get_eval_shard(const hb_pt* pt, long* first, long* count, long* chunk)
+{
+    if (!pt) return HB_ERR_ARG;
+    if (first) *first = pt->eval_first;
+    if (count) *count = pt->eval_count;
+    if (chunk) *chunk = pt->chunk;
+    return HB_OK;
+}
+
+int hb_pt_step_begin(hb_pt* pt)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
+    return pt_enqueue_step(pt, 1);
+}
+
+int hb_pt_step_end(hb_pt* pt)
+{
+    if (!pt) return HB_ERR_ARG;
+    hb_ctx* ctx = pt->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc = pt_enqueue_step(pt, 2);
+    if (rc == HB_OK) pt->iter++;
+    return rc;
+}
+
+int hb_pt_exchange_local(hb_pt** pts, int n)
+{
+    if (!pts || n < 1) return HB_ERR_ARG;
+    // every sampler's shard of the proposal logL into every other sampler's vector (same process: device-to-device
+    // or peer copies), then all streams are drained: the host-driven stand-in for the all-gather
+    for (int i = 0; i < n; i++) {
+        if (!pts[i] || pts[i]->shard_world != n || pts[i]->shard_rank != i || pts[i]->W != pts[0]->W) return HB_ERR_ARG;
+    }
+    for (int i = 0; i < n; i++) {
+        hb_ctx* ctx = pts[i]->ctx;
+        DeviceGuard g(ctx->device);
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < n; i++) {
+        hb_pt* src = pts[i];
+        if (src->eval_count == 0) continue;
+        for (int j = 0; j < n; j++) {
+            if (j == i) continue;
+            hb_ctx* ctx = pts[j]->ctx;
+            DeviceGuard g(ctx->device);
+            CK(cudaMemcpyPeerAsync(pts[j]->logLy + src->eval_first, ctx->device, src->logLy + src->eval_first, src->ctx->device,
+                                   (size_t)src->eval_count * sizeof(double), ctx->stream));
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        hb_ctx* ctx = pts[i]->ctx;
+        DeviceGuard g(ctx->device);
+        CK(cudaStreamSynchronize(ctx->stream));
     }
     return HB_OK;
 }

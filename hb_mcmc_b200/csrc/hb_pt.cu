@@ -17,7 +17,7 @@ __global__ void k_pt_init_random(const PtConfig* __restrict__ cfgp, double* __re
     if (w >= W) return;
     const PtConfig& cfg = *cfgp;
     PtRng g;
-    g.init(cfg.seed, (uint32_t)w, 0xFFFFFFFFu, 3u);
+    g.init(cfg.seed, (uint32_t)(w + cfg.ens_offset * cfg.n_temps), 0xFFFFFFFFu, 3u);
     double* xw = x + (size_t)w * kPtNpars;
     // uniform in the prior box, period pinned, T0 folded (mcmc_wrapper2.c:236-251)
     for (int i = 0; i < kPtNpars; i++) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
     const int c = ens * T + index[r];
     const int n = lane < kPtNpars ? lane : kPtNpars - 1;  // idle lanes shadow the last parameter
     const unsigned long long seed = cfg.seed;
-    const uint32_t id = (uint32_t)r;
+    const uint32_t id = (uint32_t)(r + cfg.ens_offset * T);  // global rung id
     const double temp = cfg.temp[j];
     const double xn = x[(size_t)c * kPtNpars + n];
     const double* hist = history + (size_t)r * cfg.npast * kPtNpars;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ 
     pt_prior_of(n, mean, sig);
     const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(xn, mean, sig)) : 0.0;
     const double logPx = warp_ordered_sum(term, kPtNpars);
-    const bool acc = pt_accept(cfg, (uint32_t)r, iter, cfg.temp[j], logLx[c], logLy[c], logPx, logPy[c]);
+    const bool acc = pt_accept(cfg, (uint32_t)(r + cfg.ens_offset * T), iter, cfg.temp[j], logLx[c], logLy[c], logPx, logPy[c]);
     const int jt = jump[c];
     if (acc) {
         xn = y[(size_t)c * kPtNpars + n];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
         s_dbeta[s] = (heat2 - heat1) / (heat2 * heat1);
     }
     for (int s = lane; s < T; s += 32) {
-        U4 c; c.x = 0x80000000u | (uint32_t)ens; c.y = iter; c.z = 2u; c.w = (uint32_t)s;
+        U4 c; c.x = 0x80000000u | (uint32_t)(ens + cfg.ens_offset); c.y = iter; c.z = 2u; c.w = (uint32_t)s;
         const U4 r = philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
         const double u0 = ((double)(((uint64_t)r.x << 21) | (r.y >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
         const double u1 = ((double)(((uint64_t)r.z << 21) | (r.w >> 11)) + 0.5) * (1.0 / 9007199254740992.0);

@@ -38,6 +38,8 @@ constexpr int kPtMaxTemps = 128;
 
 struct PtConfig {
     int n_temps, n_ens, npast, quirks;
+    int ens_offset;        // global id of this sampler's first ensemble (ensembles sharded over GPUs): the Philox
+    int pad_;              // streams are keyed on GLOBAL rung / ensemble ids, so a chain does not depend on the split
     unsigned long long seed;
     double dtemp;          // temperature ladder ratio, 1.4 (mcmc_wrapper2.c:331)
     double temp[kPtMaxTemps];  // temp[0] = 1, temp[i] = temp[i-1] * dtemp (mcmc_wrapper2.c:332-338)

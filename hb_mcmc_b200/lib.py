@@ -33,6 +33,10 @@ ABI_SYMBOLS = (
     "hb_pt_create", "hb_pt_destroy", "hb_pt_init_random", "hb_pt_set_state", "hb_pt_step", "hb_pt_iteration",
     "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
     "hb_pt_get_counters", "hb_pt_device_logL", "hb_pt_cold_logL_dev",
+    "hb_pt_create_sharded", "hb_pt_set_eval_shard", "hb_pt_get_eval_shard", "hb_pt_set_comm", "hb_pt_step_begin",
+    "hb_pt_exchange_local", "hb_pt_step_end",
+    "hb_comm_unique_id", "hb_comm_create", "hb_comm_create_all", "hb_comm_destroy", "hb_comm_rank", "hb_comm_world",
+    "hb_comm_nccl_version", "hb_comm_last_error", "hb_comm_allgather_f64",
     "hb_gaia_pt_create", "hb_gaia_pt_destroy", "hb_gaia_pt_set_data", "hb_gaia_pt_set_sigma", "hb_gaia_pt_init_random",
     "hb_gaia_pt_set_state", "hb_gaia_pt_records", "hb_gaia_pt_run", "hb_gaia_pt_iteration", "hb_gaia_pt_get_state",
     "hb_gaia_pt_get_proposal", "hb_gaia_pt_get_history", "hb_gaia_pt_get_map", "hb_gaia_pt_get_counters",
@@ -105,6 +109,23 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_pt_device_logL.argtypes = [vp]
     L.hb_pt_device_logL.restype = vp
     L.hb_pt_cold_logL_dev.argtypes = [vp, vp]
+    L.hb_pt_create_sharded.argtypes = [vp, C.POINTER(vp), i, i, i, d, ull, d, i, i]
+    L.hb_pt_set_eval_shard.argtypes = [vp, i, i]
+    L.hb_pt_get_eval_shard.argtypes = [vp, C.POINTER(l), C.POINTER(l), C.POINTER(l)]
+    L.hb_pt_set_comm.argtypes = [vp, vp]
+    L.hb_pt_step_begin.argtypes = [vp]
+    L.hb_pt_exchange_local.argtypes = [C.POINTER(vp), i]
+    L.hb_pt_step_end.argtypes = [vp]
+    L.hb_comm_unique_id.argtypes = [C.c_char_p]
+    L.hb_comm_create.argtypes = [C.POINTER(vp), i, C.c_char_p, i, i]
+    L.hb_comm_create_all.argtypes = [C.POINTER(vp), C.POINTER(i), i]
+    L.hb_comm_destroy.argtypes = [vp]
+    L.hb_comm_destroy.restype = None
+    L.hb_comm_rank.argtypes = [vp]
+    L.hb_comm_world.argtypes = [vp]
+    L.hb_comm_nccl_version.argtypes = [C.POINTER(i)]
+    L.hb_comm_last_error.restype = C.c_char_p
+    L.hb_comm_allgather_f64.argtypes = [vp, vp, l, vp]
     ip = C.POINTER(i)
     L.hb_gaia_pt_create.argtypes = [vp, C.POINTER(vp), i, i, ull, d, i]
     L.hb_gaia_pt_destroy.argtypes = [vp]

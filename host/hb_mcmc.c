@@ -21,8 +21,16 @@
  * Environment: HB_DATA_PREFIX (default /scratch/ssolanski/HB_MCMC/data, the reference's hard-coded
  * prefix, mcmc_wrapper2.c:110), HB_DEVICE, HB_NTEMPS (50 = NCHAINS), HB_NENS (1), HB_SEED,
  * HB_USE_GMAG (1), HB_USE_COLOR_INFO (0), HB_USE_RAND_PARS (1), HB_QUIRKS (1).
+ *
+ * Several GPUs from this one process: HB_DEVICES=0,1,...,7 -- one context and one host thread per device.
+ *   HB_NENS >= devices: whole ladders per device (hb_pt_create_sharded), nothing is exchanged;
+ *   HB_NENS <  devices (the reference's ONE ladder): every device holds the ladder and evaluates its shard of the
+ *   rungs' likelihoods; the per-step logL vector is all-gathered over NCCL from inside the captured step
+ *   (hb_comm_create_all; HB_EXCHANGE=peer uses host-driven peer copies instead).
+ * The chains and files are those of the one-device run, bit for bit (random streams are keyed on global ids).
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -48,6 +56,54 @@ static void die(hb_ctx *ctx, const char *what)
 
 #define CK(call) do { if ((call) != HB_OK) die(ctx, #call); } while (0)
 
+#define MAX_DEV 64
+/* the schedule of hb_pt_step calls every device follows (so that the collectives inside the steps pair up):
+ * run up to and including the next iteration whose index is a multiple of 100 (a log point) */
+static long next_chunk(long done, long NITER)
+{
+    const long next_log = ((done + 99) / 100) * 100;
+    long n = next_log + 1 - done;
+    if (done + n > NITER) n = NITER - done;
+    return n;
+}
+
+struct worker {
+    hb_ctx *ctx;
+    hb_pt *pt;
+    long NITER;
+    int peer_mode, rank, ndev;
+    hb_pt **all;                 /* peer mode: every device's sampler */
+    pthread_barrier_t *bar;
+};
+
+/* one iteration with the host-driven exchange: all devices propose + evaluate, device 0 copies, all accept */
+static void peer_steps(struct worker *w, long n)
+{
+    hb_ctx *ctx = w->ctx;
+    for (long k = 0; k < n; k++) {
+        CK(hb_pt_step_begin(w->pt));
+        pthread_barrier_wait(w->bar);
+        if (w->rank == 0 && hb_pt_exchange_local(w->all, w->ndev) != HB_OK) die(ctx, "hb_pt_exchange_local");
+        pthread_barrier_wait(w->bar);
+        CK(hb_pt_step_end(w->pt));
+    }
+}
+
+static void *worker_main(void *arg)
+{
+    struct worker *w = arg;
+    hb_ctx *ctx = w->ctx;
+    long done = 0;
+    while (done < w->NITER) {
+        const long n = next_chunk(done, w->NITER);
+        if (w->peer_mode) peer_steps(w, n);
+        else CK(hb_pt_step(w->pt, n));
+        done += n;
+    }
+    CK(hb_sync(ctx));
+    return NULL;
+}
+
 int main(int argc, char *argv[])
 {
     if (argc < 5) {
@@ -62,7 +118,9 @@ int main(int argc, char *argv[])
 
     const char *prefix = getenv("HB_DATA_PREFIX") ? getenv("HB_DATA_PREFIX") : "/scratch/ssolanski/HB_MCMC/data";
     const int use_gmag = env_int("HB_USE_GMAG", 1), use_color = env_int("HB_USE_COLOR_INFO", 0);
-    const int n_temps = env_int("HB_NTEMPS", 50), n_ens = env_int("HB_NENS", 1);
+    const int n_temps = env_int("HB_NTEMPS", 50);
+    int n_ens = env_int("HB_NENS", 1);
+    const int n_ens_total = n_ens;
     const int use_rand_pars = env_int("HB_USE_RAND_PARS", 1), quirks = env_int("HB_QUIRKS", 1);
     const unsigned long long seed = (unsigned long long)env_int("HB_SEED", 0) + (unsigned long long)run;
 
@@ -117,14 +175,59 @@ int main(int argc, char *argv[])
         printf("Magnitude file not found/used; assigning infinite error to mag data \n");
     }
 
-    /* device */
-    hb_ctx *ctx = NULL;
-    if (hb_create(&ctx, env_int("HB_DEVICE", 0)) != HB_OK) die(NULL, "hb_create");
-    CK(hb_set_mags(ctx, mag_data, mag_err, use_gmag, use_color));
-    CK(hb_set_data(ctx, t_data, a_data, e_data, Nt));
-    hb_pt *pt = NULL;
-    CK(hb_pt_create(ctx, &pt, n_temps, n_ens, log_LC_PERIOD, seed, 1.4, 500, quirks));
+    /* devices */
+    int devs[MAX_DEV], ndev = 0;
+    {
+        const char *dl = getenv("HB_DEVICES");
+        if (dl && *dl) {
+            char *copy = strdup(dl), *save = NULL;
+            for (char *tok = strtok_r(copy, ",", &save); tok && ndev < MAX_DEV; tok = strtok_r(NULL, ",", &save)) devs[ndev++] = atoi(tok);
+            free(copy);
+        }
+        if (ndev == 0) devs[ndev++] = env_int("HB_DEVICE", 0);
+    }
+    const int rung_split = n_ens < ndev; /* fewer ladders than devices: split the likelihood evaluation of every ladder */
+    const char *xch = getenv("HB_EXCHANGE");
+    const int peer_mode = rung_split && xch && strcmp(xch, "peer") == 0;
+    hb_ctx *ctxs[MAX_DEV];
+    hb_pt *pts[MAX_DEV];
+    hb_comm *comms[MAX_DEV];
+    int ens_first[MAX_DEV], ens_count[MAX_DEV];
+    for (int d = 0; d < ndev; d++) {
+        hb_ctx *ctx = NULL;
+        if (hb_create(&ctx, devs[d]) != HB_OK) die(NULL, "hb_create");
+        ctxs[d] = ctx;
+        comms[d] = NULL;
+        CK(hb_set_mags(ctx, mag_data, mag_err, use_gmag, use_color));
+        CK(hb_set_data(ctx, t_data, a_data, e_data, Nt));
+        if (rung_split) {
+            ens_first[d] = 0;
+            ens_count[d] = n_ens;
+        } else { /* contiguous blocks of whole ladders */
+            const int base = n_ens / ndev, rem = n_ens % ndev;
+            ens_count[d] = base + (d < rem ? 1 : 0);
+            ens_first[d] = d * base + (d < rem ? d : rem);
+        }
+        CK(hb_pt_create_sharded(ctx, &pts[d], n_temps, ens_count[d], ens_first[d], log_LC_PERIOD, seed, 1.4, 500, quirks));
+        if (rung_split) CK(hb_pt_set_eval_shard(pts[d], d, ndev));
+    }
+    if (rung_split && !peer_mode) {
+        if (hb_comm_create_all(comms, devs, ndev) != HB_OK) {
+            fprintf(stderr, "hb_mcmc: NCCL communicator: %s\n", hb_comm_last_error());
+            return 2;
+        }
+        for (int d = 0; d < ndev; d++) {
+            hb_ctx *ctx = ctxs[d];
+            CK(hb_pt_set_comm(pts[d], comms[d]));
+        }
+    }
+    hb_ctx *ctx = ctxs[0]; /* device 0 holds ladder 0 -- the ladder the files follow -- in either split */
+    hb_pt *pt = pts[0];
+    n_ens = ens_count[0];
     const int W = n_temps * n_ens;
+    if (ndev > 1)
+        printf("%d devices: %s\n", ndev, rung_split ? (peer_mode ? "rungs split, peer-copy exchange" : "rungs split, NCCL all-gather of logL per step")
+                                                      : "whole ladders per device, no exchange");
 
     /* initial state (mcmc_wrapper2.c:203-252) */
     if (!use_rand_pars && access(parname, R_OK) == 0) {
@@ -138,11 +241,17 @@ int main(int argc, char *argv[])
         }
         fclose(f);
         for (int w = 0; w < W; w++) memcpy(x + (size_t)w * NPARS, p, sizeof p);
-        CK(hb_pt_set_state(pt, x));
+        for (int d = 0; d < ndev; d++) { /* (device 0 holds at least as many ladders as any other) */
+            hb_ctx *ctx = ctxs[d];
+            CK(hb_pt_set_state(pts[d], x));
+        }
         free(x);
     } else {
         printf("Parameter file not found, assigning random pars \n");
-        CK(hb_pt_init_random(pt));
+        for (int d = 0; d < ndev; d++) {
+            hb_ctx *ctx = ctxs[d];
+            CK(hb_pt_init_random(pts[d]));
+        }
     }
     double *cold_x = malloc(sizeof(double) * n_ens * NPARS), *cold_L = malloc(sizeof(double) * n_ens);
     double *rung_L = malloc(sizeof(double) * W), *xmap = malloc(sizeof(double) * n_ens * NPARS),
@@ -165,13 +274,24 @@ int main(int argc, char *argv[])
     const clock_t c0 = clock();
     struct timespec ts0, ts1;
     clock_gettime(CLOCK_MONOTONIC, &ts0);
+    pthread_t threads[MAX_DEV];
+    pthread_barrier_t bar;
+    struct worker wk[MAX_DEV];
+    pthread_barrier_init(&bar, NULL, (unsigned)ndev);
+    for (int d = 0; d < ndev; d++) {
+        wk[d].ctx = ctxs[d]; wk[d].pt = pts[d]; wk[d].NITER = NITER; wk[d].peer_mode = peer_mode; wk[d].rank = d;
+        wk[d].ndev = ndev; wk[d].all = pts; wk[d].bar = &bar;
+        if (d > 0 && pthread_create(&threads[d], NULL, worker_main, &wk[d]) != 0) {
+            fprintf(stderr, "hb_mcmc: cannot start the host thread of device %d\n", devs[d]);
+            return 2;
+        }
+    }
     long done = 0; /* iterations completed */
     while (done < NITER) {
         /* run up to and including the next iteration whose index is a multiple of 100 */
-        const long next_log = ((done + 99) / 100) * 100; /* iteration index to log after */
-        long n = next_log + 1 - done;
-        if (done + n > NITER) n = NITER - done;
-        CK(hb_pt_step(pt, n));
+        const long n = next_chunk(done, NITER);
+        if (peer_mode) peer_steps(&wk[0], n);
+        else CK(hb_pt_step(pt, n));
         done += n;
         const long iter = done - 1;
         if (iter % 100 != 0) break; /* ran out of iterations before the next log point */
@@ -209,6 +329,8 @@ int main(int argc, char *argv[])
             fclose(f);
         }
     }
+    CK(hb_sync(ctx));
+    for (int d = 1; d < ndev; d++) pthread_join(threads[d], NULL);
     clock_gettime(CLOCK_MONOTONIC, &ts1);
     const double wall = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
 
@@ -233,9 +355,24 @@ int main(int argc, char *argv[])
             done, wall, wall > 0 ? done / wall : 0., (double)(clock() - c0) / CLOCKS_PER_SEC, cnt[3], cnt[4], cnt[5], cnt[6], Lmap[0]);
     printf("done: %ld iterations in %.3f s (%.1f PT steps/s, %d rungs x %d ensembles, %ld points), MAP logL %.10g\n", done, wall,
            wall > 0 ? done / wall : 0., n_temps, n_ens, Nt, Lmap[0]);
+    if (ndev > 1 && !rung_split) { /* every ladder's MAP logL, by global ensemble id */
+        fprintf(logfile, "MAP logL by ensemble:");
+        double *L = malloc(sizeof(double) * n_ens_total);
+        for (int d = 0; d < ndev; d++) {
+            hb_ctx *ctx = ctxs[d];
+            CK(hb_pt_get_map(pts[d], NULL, L + ens_first[d]));
+        }
+        for (int e = 0; e < n_ens_total; e++) fprintf(logfile, " %.12g", L[e]);
+        fprintf(logfile, "\n");
+        free(L);
+    }
+    fprintf(logfile, "devices %d split %s ensembles %d\n", ndev, ndev == 1 ? "none" : (rung_split ? "rungs" : "ensembles"), n_ens_total);
     fclose(logfile); fclose(chain_file); fclose(logL_file);
-    hb_pt_destroy(pt);
-    hb_destroy(ctx);
+    for (int d = 0; d < ndev; d++) {
+        hb_pt_destroy(pts[d]);
+        if (comms[d]) hb_comm_destroy(comms[d]);
+        hb_destroy(ctxs[d]);
+    }
     free(t_data); free(a_data); free(e_data); free(a_model); free(cold_x); free(cold_L); free(rung_L); free(xmap);
     free(Lmap); free(cnt);
     return 0;

@@ -127,6 +127,42 @@ void* hb_pt_device_logL(hb_pt* pt);
  * stream: the send buffer of the per-step NCCL all-gather */
 int hb_pt_cold_logL_dev(hb_pt* pt, double* d_out);
 
+/* ---- the sampler on several GPUs ---------------------------------------------------------- */
+/* Two ways to use more than one GPU; in both, every random number is keyed on GLOBAL rung / ensemble ids, so the
+ * chains are those of the one-GPU run bit for bit, whatever the split.
+ *  (1) whole ensembles per GPU (n_ens >= GPUs): hb_pt_create_sharded(ens_offset = global id of the first local
+ *      ensemble).  Ladders never talk to each other: no exchange at all (mcmc_wrapper2.c:383 treats rungs alike).
+ *  (2) fewer ensembles than GPUs -- the reference's own case is ONE ladder (mcmc_wrapper2.h:11): every rank holds
+ *      the whole sampler state and proposes, accepts and swaps redundantly (counter-based RNG), but evaluates the
+ *      likelihood -- all of the cost -- only for its contiguous shard of the walkers; the per-step log-likelihood
+ *      vector is then all-gathered (8 bytes per walker: the only exchange) and the swaps (mcmc_wrapper2.c:554-563,
+ *      ptmcmc :768-817) are decided identically everywhere.  hb_pt_set_eval_shard + either a communicator
+ *      (hb_pt_set_comm: ncclAllGather on the context's stream, inside the captured step) or, within one process,
+ *      hb_pt_step_begin / hb_pt_exchange_local / hb_pt_step_end (peer copies driven by the host). */
+int hb_pt_create_sharded(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, int ens_offset, double log_lc_period,
+                         unsigned long long seed, double dtemp, int npast, int quirks);
+int hb_pt_set_eval_shard(hb_pt* pt, int rank, int world);                        /* world <= 64 */
+int hb_pt_get_eval_shard(const hb_pt* pt, long* first, long* count, long* chunk); /* walkers evaluated here */
+typedef struct hb_comm hb_comm;
+#define HB_COMM_ID_BYTES 128
+/* NCCL is bound at run time (dlopen of libnccl.so.2, or $HB_NCCL_LIB).  One process per GPU: rank 0 makes an id,
+ * hands the 128 bytes to the others by any means (torch.distributed, a file, MPI ...), every rank creates its
+ * communicator on its device.  One process, several GPUs: hb_comm_create_all (ncclCommInitAll). */
+int hb_comm_unique_id(unsigned char id[HB_COMM_ID_BYTES]);
+int hb_comm_create(hb_comm** out, int device, const unsigned char id[HB_COMM_ID_BYTES], int rank, int world);
+int hb_comm_create_all(hb_comm** out, const int* devices, int n);
+void hb_comm_destroy(hb_comm* comm);
+int hb_comm_rank(const hb_comm* comm);
+int hb_comm_world(const hb_comm* comm);
+int hb_comm_nccl_version(int* version);
+const char* hb_comm_last_error(void);
+/* in-place all-gather of doubles on a CUDA stream: rank r's count_per_rank values sit at d_buf + r * count_per_rank */
+int hb_comm_allgather_f64(hb_comm* comm, double* d_buf, long count_per_rank, void* cuda_stream);
+int hb_pt_set_comm(hb_pt* pt, hb_comm* comm);   /* not owned; NULL unbinds */
+int hb_pt_step_begin(hb_pt* pt);                 /* propose + likelihood of this rank's shard (asynchronous) */
+int hb_pt_exchange_local(hb_pt** pts, int n);    /* the n samplers of one process swap their shards' logL */
+int hb_pt_step_end(hb_pt* pt);                   /* accept + swaps + MAP */
+
 /* ---- Gaia-colour sampler ---------------------------------------------------------------- */
 /* The stand-alone sampler of GAIA_mcmc.c:663-780 (run_mcmc) on the device: n_ens independent
  * ladders (one warp each, one lane per rung; n_temps <= 32; the reference: NCHAINS = 20 rungs with

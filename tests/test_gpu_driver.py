@@ -88,3 +88,47 @@ def test_gaia_driver_cli_and_file_formats(tmp_path, ctx):
     # missing magnitude file: the reference prints and carries on with garbage; the driver stops
     r = subprocess.run([exe, "10", "NOPE", "1"], env=env, capture_output=True, text=True, timeout=120)
     assert "Could not open magnitude file" in r.stdout
+
+
+def _driver_files(prefix, sfx):
+    names = (f"chains/chain.{sfx}.dat", f"logL/logL.{sfx}.dat", f"lightcurves/mcmc_lightcurves/{sfx}.out", f"pars/par.{sfx}.dat",
+             f"subpars/subpar.{sfx}.dat")
+    return [open(prefix / n, "rb").read() for n in names]
+
+
+def test_driver_on_several_devices_writes_the_same_files(tmp_path, ctx):
+    """HB_DEVICES: one process, one context and host thread per device (mcmc_wrapper2.c main, :8-699, has one
+    ladder and one OpenMP team).  ONE ladder over three contexts -- the rungs' likelihood evaluations split, the
+    logL vector exchanged every step -- and four ladders over three contexts (whole ladders each) write the files
+    of the one-device run byte for byte.  The contexts share GPU 0 here (peer-copy exchange; NCCL needs distinct
+    GPUs: tests/test_gpu_multi.py and `HB_DEVICES=0,...,7 ./hb_mcmc` on a multi-GPU box)."""
+    build.build_lib()
+    exe = build.build_driver()
+    prefix = tmp_path / "data"
+    for d in ("chains", "logL", "log", "pars", "subpars", "magnitudes", "lightcurves/folded_lightcurves",
+              "lightcurves/mcmc_lightcurves"):
+        (prefix / d).mkdir(parents=True)
+    N = 1500
+    t = np.sort(np.random.default_rng(0).uniform(0, 10 ** wl.TRUTH_A[2], N))
+    flux = ctx.calc_light_curve(t, wl.TRUTH_A) + 3e-4 * np.random.default_rng(1).standard_normal(N)
+    with open(prefix / "lightcurves/folded_lightcurves/TIC7_new.txt", "w") as f:
+        f.write(f"{N}\n")
+        for a, b in zip(t, flux):
+            f.write(f"{a:.10f}\t{b:.10f}\t{3e-4:.10f}\n")
+    sfx = "TIC7_gmag_B200_2"
+    logp = repr(float(wl.TRUTH_A[2]))
+
+    def run(**env):
+        e = dict(os.environ, HB_DATA_PREFIX=str(prefix), HB_SEED="5", **env)
+        r = subprocess.run([exe, "230", "TIC7", logp, "2"], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout, _driver_files(prefix, sfx), open(prefix / f"log/log.{sfx}.dat").read()
+
+    _, one, _ = run(HB_NTEMPS="10")
+    out, three, log = run(HB_NTEMPS="10", HB_DEVICES="0,0,0", HB_EXCHANGE="peer")
+    assert "3 devices: rungs split" in out and "split rungs" in log
+    assert three == one
+    _, one4, _ = run(HB_NTEMPS="6", HB_NENS="4")
+    out, three4, log = run(HB_NTEMPS="6", HB_NENS="4", HB_DEVICES="0,0,0")
+    assert "whole ladders per device" in out and "MAP logL by ensemble:" in log
+    assert three4 == one4

@@ -1,5 +1,6 @@
-"""Two ranks on two GPUs (NCCL): sharded likelihood == single-GPU likelihood bit for bit, and the
-sharded PT driver all-gathers the cold-rung logL.  Skipped on boxes with fewer than 2 GPUs."""
+"""Two ranks on two GPUs (NCCL): sharded likelihood == single-GPU likelihood bit for bit; the sampler split by
+ensembles and split by rungs (logL all-gathered by NCCL from inside libhb_b200's captured step) walks the one-GPU
+chains bit for bit.  Skipped on boxes with fewer than 2 GPUs."""
 import os
 import socket
 import subprocess
@@ -34,17 +35,40 @@ parts = [torch.empty_like(mine) for _ in range(world)]
 dist.all_gather(parts, mine)
 gathered = torch.cat(parts).cpu().numpy()
 ok_shard = bool(np.array_equal(gathered, full, equal_nan=True))
-sp = ShardedPT(ctx, 8, 6, float(wl.TRUTH_A[2]), seed=5, npast=20)
+from hb_mcmc_b200.pt import PTSampler
+logp = float(wl.TRUTH_A[2])
+# (1) whole ensembles per rank: this rank's ladders are the one-GPU run's ladders, bit for bit; host gather of the cold rung
+sp = ShardedPT(ctx, 8, 6, logp, seed=5, npast=10)
 sp.sampler.init_random()
 sp.step(25)
-g = sp.gather_cold_logL_device().cpu().numpy()
-_, local = sp.sampler.cold()
+one = PTSampler(ctx, 8, 6, logp, seed=5, npast=10)
+one.init_random()
+one.step(25)
 first, count = shard_ensembles(6, world, rank)
-ok_pt = bool(np.array_equal(g[rank, :count], local)) and bool(np.isfinite(g[:, :count]).all())
+x1, l1, i1 = one.state()
+xs, ls, is_ = sp.sampler.state()
+ok_pt = sp.mode == "ensembles" and bool(np.array_equal(xs, x1.reshape(6, 8, 21)[first:first + count].reshape(-1, 21))) \
+    and bool(np.array_equal(ls, l1.reshape(6, 8)[first:first + count].ravel(), equal_nan=True)) and bool(np.array_equal(is_, i1[first:first + count]))
 host = sp.gather_cold_logL()
-ok_host = bool(np.array_equal(host[first:first + count], local)) and host.shape == (6,)
+ok_host = bool(np.array_equal(host, one.cold()[1])) and host.shape == (6,)
+sp.close(); one.close()
+# (2) ONE ladder over the ranks: likelihood evaluation sharded, logL all-gathered by NCCL inside the library's captured
+# step, swaps decided redundantly -- every rank ends with the one-GPU chain, bit for bit
+sr = ShardedPT(ctx, 16, 1, logp, seed=9, npast=10)
+sr.sampler.init_random()
+sr.step(3)      # single steps
+sr.step(37)     # CUDA-graph replays with the all-gather captured
+one = PTSampler(ctx, 16, 1, logp, seed=9, npast=10)
+one.init_random()
+one.step(40)
+ok_rungs = sr.mode == "rungs" and all(bool(np.array_equal(a, b, equal_nan=True)) for a, b in zip(sr.sampler.state(), one.state()))
+ok_rungs = ok_rungs and sr.sampler.eval_shard()[1] == 8
+flag = torch.tensor([int(ok_pt), int(ok_host), int(ok_rungs)], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+ok_pt, ok_host, ok_rungs = (bool(v) for v in flag.tolist())
+sr.close(); one.close()
 if rank == 0:
-    print(json.dumps({"ok_shard": ok_shard, "ok_pt": ok_pt, "ok_host": ok_host}))
+    print(json.dumps({"ok_shard": ok_shard, "ok_pt": ok_pt, "ok_host": ok_host, "ok_rungs": ok_rungs}))
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -63,4 +87,4 @@ def test_two_gpu_sharding_and_allgather(tmp_path):
     import json
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
-    assert res == {"ok_shard": True, "ok_pt": True, "ok_host": True}, res
+    assert res == {"ok_shard": True, "ok_pt": True, "ok_host": True, "ok_rungs": True}, res

@@ -55,6 +55,7 @@ def _worker(rank, world, port, n_ens, out):
     try:
         sp = ptmod.ShardedPT.__new__(ptmod.ShardedPT)
         sp.dist, sp.rank, sp.world, sp.n_ens_total = dist, rank, world, n_ens
+        sp.mode, sp.comm = "ensembles", None
         sp.first, sp.count = ptmod.shard_ensembles(n_ens, world, rank)
         sp.sampler = StubSampler(sp.first, sp.count)
         sp.step(3)
@@ -83,3 +84,17 @@ def test_all_gather_cold_logL_world2(n_ens):
         assert allL == want and best == 4 and val == 0.0 and steps == 3
     owners = [xb for _, _, _, _, xb, _ in res]
     assert owners.count(None) == 1 and 4.0 in owners  # exactly one rank owns the MAP ensemble
+
+
+@pytest.mark.parametrize("W,world", [(64, 8), (50, 8), (7, 8), (2048, 3), (1, 2), (64, 64)])
+def test_walker_shards_tile_the_sampler(W, world):
+    """hb_pt_set_eval_shard's partition (mirrored by shard_walkers): contiguous chunks of ceil(W / world) that tile
+    [0, W) in rank order, so that the in-place all-gather of `chunk` doubles per rank lands every walker at its index."""
+    covered = []
+    for r in range(world):
+        first, count, chunk = ptmod.shard_walkers(W, world, r)
+        assert chunk == -(-W // world) and 0 <= count <= chunk
+        assert first == min(r * chunk, W)
+        covered += list(range(first, first + count))
+    assert covered == list(range(W))
+    assert world * chunk >= W and world * chunk < W + world
