@@ -15,12 +15,15 @@ One JSON line on stdout (rank 0):
              CUDA-event time per step, L2 flushed between steps, max over ranks
   e2e        same metric through hb_loglikelihood_batch with HOST buffers (H2D of the parameter
              batch from pinned memory + D2H of logL inside every step)
-  roofline   FP64 CUDA-core roofline of k_chain_eval: 520 algorithmic flop / model point
-             (the work of the reference's formulation) / kernel duration (events on
-             the launching stream) against the DFMA peak measured on this box by hb_fp64_peak in
-             the same run.  The kernel EXECUTES far fewer flops than that count (table starter,
-             table sincos, folded harmonics), so `frac` can exceed 1; `executed` gives the
-             hardware view (FP64 instructions and pipe utilisation from the committed ncu capture)
+  roofline   FP64 CUDA-core roofline of k_chain_eval on EXECUTED work: FP64 flop per model point as counted by
+             the committed `ncu --set full` capture of this kernel (2 x DFMA + DMUL + DADD, profiles/) x points /
+             kernel duration (CUDA events on the launching stream) against the DFMA peak measured on this box by
+             hb_fp64_peak in the same run: `frac` <= 1.  `frac_vs_reference_formulation` is the same time set
+             against the 520 flop / point of the REFERENCE's formulation -- it exceeds 1 because
+             the kernel reaches the reference's numbers with a quarter of its operations
+  extra      the other BASELINE configs in the same line: C1 latency, C3's per-GPU share, C4 (+Gaia), C5's share;
+             at N > 1 C3 as named (64 x 256 walkers, strong scaling), one ladder of 64 rungs x 200 000 points with
+             the rungs split over the GPUs, and `shard_bit_identical` (sharded logL == full logL on a 512-chain probe)
   cpu_baseline  the reference's own loglikelihood() (oracle/_ref, or the oracle port when the
              compiled reference is absent) on all host cores over a bounded sample
 `--impl reference` times that CPU path alone on the same config and prints the same line.
@@ -47,16 +50,16 @@ UNIT = "points/s"
 FLOP_PER_POINT = 520.0  # 156 plain + 6 sincos x 40 + 8 div x 14 + 1 sqrt x 14
 NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
 CHAIN_CONST_BYTES = 47 * 8  # sizeof(ChainConst): what k_chain_eval reads per chain
-# From the committed `ncu --set full` capture of one k_chain_eval launch on C2
-# (profiles/r1_chain_eval_ncu_summary.txt); only meaningful for the default workload:
-NCU_TRAFFIC_C2_BYTES = 2.778112e6 + 5.378816e6  # dram__bytes_read.sum + dram__bytes_write.sum
+# From the committed `ncu --set full` capture of one k_chain_eval launch on C2 (profiles/r2_chain_eval_ncu_summary.txt,
+# tools/ncu_mix.py); only meaningful for the default workload:
+NCU_TRAFFIC_C2_BYTES = 2.850048e6 + 7.115776e6  # dram__bytes_read.sum + dram__bytes_write.sum
 NCU_EXECUTED = {
-    "fp64_instr_per_point": 92.6,   # DFMA 53.7 + DMUL 18.6 + DADD 13.7 + DSETP 6.6 (warp instructions / 32 samples)
-    "flop_per_point": 139.7,        # 2 x DFMA + DMUL + DADD
-    "all_instr_per_point": 219.9,
-    "fp64_pipe_active": 0.586,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
-    "issue_active": 0.696,          # smsp__issue_active.avg.pct_of_peak_sustained_active
-    "source": "profiles/r1_chain_eval_ncu_summary.txt",
+    "fp64_instr_per_point": 93.3,   # DFMA 52.2 + DMUL 20.4 + DADD 14.1 + DSETP 6.5 (warp instructions / 32 samples)
+    "flop_per_point": 138.9,        # 2 x DFMA + DMUL + DADD
+    "all_instr_per_point": 219.0,
+    "fp64_pipe_active": 0.58,       # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "issue_active": 0.69,           # smsp__issue_active.avg.pct_of_peak_sustained_active
+    "source": "profiles/r2_chain_eval_ncu_summary.txt",
 }
 
 
@@ -80,7 +83,8 @@ def parse_args():
     ap.add_argument("--points", type=int, default=0, help="override points per light curve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic)")
-    ap.add_argument("--pt-steps", type=int, default=40, help="PT-MCMC iterations timed for the steps/s figure (0 = skip)")
+    ap.add_argument("--pt-steps", type=int, default=240, help="PT-MCMC iterations timed for the steps/s figure (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (other BASELINE configs, multi-GPU probes)")
     ap.add_argument("--no-pt-reference", action="store_true",
                     help="skip the reference-size PT comparison (50 rungs x 375 real points, GPU vs the reference driver binary)")
     return ap.parse_args()
@@ -354,6 +358,17 @@ def gpu_arm(args, cfg, rank, local_rank, world):
     assert np.array_equal(out, logL_dev, equal_nan=True), "host-buffer and device-buffer paths disagree"
 
     pt_info = pt_leg(args, ctx, cfg, rank, world, dist, stream) if args.pt_steps > 0 else None
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        if world > 1:
+            extra["shard_bit_identical"] = shard_probe(ctx, rank, world, dist)
+        if args.pt_steps > 0:
+            extra["pt_one_ladder_64_rungs_x_200k"] = rung_split_leg(ctx, rank, world, dist, stream, max(args.pt_steps, 8))
+        if world == 1:
+            extra.update(extra_legs(ctx, stream))
+        # back to the headline data set (the reference-size leg below sets its own)
+        ctx.set_data(t, flux, err)
 
     if pt_info is not None and rank == 0 and world == 1 and not args.no_pt_reference and not args.no_cpu_baseline:
         pt_info["reference_size"] = pt_reference_size_leg(ctx)
@@ -364,7 +379,6 @@ def gpu_arm(args, cfg, rank, local_rank, world):
         value = pts_per_step / (ms_per_step * 1e-3)
         e2e_value = pts_per_step / (e2e_s / args.steps)
         k_ms = float(np.mean(kernel_ms))
-        achieved_tf = float(n) * N * FLOP_PER_POINT / (k_ms * 1e-3) * 1e-12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -373,24 +387,15 @@ def gpu_arm(args, cfg, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes), "d2h_bytes_per_step": int(out.nbytes)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(t_begin, t_end),
-            "roofline": {
-                "bound": "fp64", "kernel": "k_chain_eval", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
-                "traffic": NCU_TRAFFIC_C2_BYTES if (args.workload == "C2" and not args.chains and not args.points) else None,
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r1_chain_eval_ncu_summary.txt)",
-                "hbm": hbm_block(n, N, k_ms),
-                "flop_per_point": FLOP_PER_POINT, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-                # the instruction counts come from the C2 capture: not carried over to other workloads
-                "executed": executed_block(n, N, k_ms, peak_tf)
-                            if (args.workload == "C2" and not args.chains and not args.points) else None,
-                "peak_source": "hb_fp64_peak DFMA probe on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                               f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
-                "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
-            },
+            "roofline": roofline_block(args, n, N, k_ms, ms_per_step, peak_tf),
             "nan_fraction": float(np.isnan(logL_dev).mean()),
         }
         if pt_info is not None:
             line["pt"] = pt_info
+        if extra is not None:
+            line["extra"] = extra
+            if "shard_bit_identical" in extra:
+                line["shard_bit_identical"] = extra["shard_bit_identical"]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg(cfg, t, flux, err, P, logL_dev)
         sys.stdout.flush()
@@ -414,57 +419,206 @@ def hbm_block(n, N, k_ms):
             "bytes_per_point": nbytes / (float(n) * N), "peak_source": src}
 
 
-def executed_block(n, N, k_ms, peak_tf):
-    """What the hardware executes (instruction counts from the committed ncu capture, time from this run)."""
+def roofline_block(args, n, N, k_ms, ms_per_step, peak_tf):
+    """FP64 roofline of k_chain_eval on executed work (see the module docstring)."""
+    default = args.workload == "C2" and not args.chains and not args.points
     ex = dict(NCU_EXECUTED)
-    tf = float(n) * N * ex["flop_per_point"] / (k_ms * 1e-3) * 1e-12
-    ex.update({"achieved": tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf > 0 else None})
-    return ex
+    pts_per_s = float(n) * N / (k_ms * 1e-3)
+    achieved = pts_per_s * ex["flop_per_point"] * 1e-12
+    formulation = pts_per_s * FLOP_PER_POINT * 1e-12
+    return {
+        "bound": "fp64", "kernel": "k_chain_eval", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved / peak_tf if peak_tf > 0 else None,
+        "flop_per_point": ex["flop_per_point"],
+        "flop_per_point_source": ex["source"] + " (2 x DFMA + DMUL + DADD per model point, counted by ncu on C2"
+                                 + ("" if default else "; this workload was not captured separately") + ")",
+        "frac_vs_reference_formulation": formulation / peak_tf if peak_tf > 0 else None,
+        "reference_formulation_flop_per_point": FLOP_PER_POINT,
+        "traffic": NCU_TRAFFIC_C2_BYTES if default else None,
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, " + ex["source"] + ")",
+        "hbm": hbm_block(n, N, k_ms),
+        "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+        "executed": ex if default else None,
+        "peak_source": "hb_fp64_peak DFMA probe on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                       f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
+        "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+    }
 
 
-def pt_leg(args, ctx, cfg, rank, world, dist, stream):
-    """Second half of BASELINE.json's metric: full PT-MCMC iterations per second on config C3's
-    per-GPU share (64 temperatures x 32 ensembles = 2048 walkers per GPU on the resident light curve;
-    256 ensembles over 8 GPUs).  Every iteration = propose + ONE likelihood per walker + accept +
-    64 swap proposals per ensemble + the all-gather of the cold-rung logL vector across ranks."""
+def time_batch(ctx, stream, n, N, truth, gaia, reps, seed=1, e_max=0.95):
+    """One BASELINE configuration, device-resident: mean CUDA-event time per call of hb_loglikelihood_batch_dev."""
     import torch
-    from hb_mcmc_b200.pt import ShardedPT
-    n_temps, ens_per_gpu = 64, 32
-    sp = ShardedPT(ctx, n_temps, ens_per_gpu * world, float(cfg["truth_vec"][2]), seed=11)
-    sp.sampler.init_random()
+    t, flux, err = wl.make_dataset(N, truth, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    if gaia:
+        md, me = gaia_setup(truth, ctx.chain_info(truth[None], 100.0)[0, 4])
+        ctx.set_mags(md, me, 1, 0)
+    else:
+        ctx.set_mags([1000, 1, 1, 1, 1], [1e15] * 4, 1, 0)
+    P = wl.draw_chains(n, truth, ctx.roche_overflow, seed=seed, e_max=e_max)
+    dP = torch.from_numpy(P).to("cuda")
+    dL = torch.empty(n, dtype=torch.float64, device="cuda")
     for _ in range(3):
-        sp.step(1)
-        sp.gather_cold_logL_device()
+        ctx.loglikelihood_dev(dP.data_ptr(), n, dL.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        ctx.loglikelihood_dev(dP.data_ptr(), n, dL.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = dL.cpu().numpy()
+    return {"n_chains": n, "n_points": N, "ms": ms, "points_per_sec": n * N / (ms * 1e-3), "nan_fraction": float(np.isnan(out).mean()),
+            "reps": reps}
+
+
+def extra_legs(ctx, stream):
+    """The BASELINE configs the headline does not carry, on this GPU (C3 / C5: the per-GPU share of the 8-GPU job)."""
+    out = {}
+    out["C1_latency"] = dict(time_batch(ctx, stream, 1, 20000, wl.TRUTH_A, False, 200),
+                             note="one chain x 20 000 points (test_likelihoods.c): the light curve is shared by several CTAs")
+    out["C3_share"] = dict(time_batch(ctx, stream, 2048, 20000, wl.TRUTH_A, False, 20),
+                           note="64 temperatures x 32 ensembles: the likelihood batch of one PT step")
+    out["C4"] = dict(time_batch(ctx, stream, 8192, 50000, wl.TRUTH_A, True, 5), note="8192 chains x 50 000 points + Gaia G term")
+    out["C5_share"] = dict(time_batch(ctx, stream, 2048, 200000, wl.TRUTH_B, False, 5),
+                           note="2048 of 16 384 chains x 200 000 points, truth B, e <= 0.95")
+    ctx.set_mags([1000, 1, 1, 1, 1], [1e15] * 4, 1, 0)
+    return out
+
+
+def shard_probe(ctx, rank, world, dist):
+    """Sharded logL == full logL, bit for bit, on a 512-chain probe (every rank evaluates the whole probe and its
+    own shard; the shards are all-gathered over NCCL)."""
+    import torch
+    N, n = 20000, 512
+    t, flux, err = wl.make_dataset(N, wl.TRUTH_A, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    P = wl.draw_chains(n, wl.TRUTH_A, ctx.roche_overflow, seed=77)
+    full = ctx.loglikelihood(P)
+    per = -(-n // world)
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    mine = np.full(per, np.nan)
+    mine[: hi - lo] = ctx.loglikelihood(P[lo:hi]) if hi > lo else []
+    send = torch.from_numpy(mine).to("cuda")
+    recv = torch.empty(world * per, dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(recv, send)
+    gathered = recv.cpu().numpy()[:n]
+    ok = bool(np.array_equal(gathered, full, equal_nan=True))
+    flag = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def _timed_steps(sp, ctx, stream, dist, n_steps):
+    """n_steps iterations through hb_pt_step (captured graphs), CUDA-event time, max over ranks; the evaluated-walker
+    count of the same steps from the likelihood kernel's own counter."""
+    import torch
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    ctx.evaluated_chains(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launch_count
     e0.record(stream)
-    for _ in range(args.pt_steps):
-        sp.step(1)
-        g = sp.gather_cold_logL_device()
+    sp.step(n_steps)
     e1.record(stream)
     torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
     ms = e0.elapsed_time(e1)
+    evaluated = ctx.evaluated_chains(reset=True)
     if dist is not None:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+        ev = torch.tensor([evaluated], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ev, op=dist.ReduceOp.SUM)
+        evaluated = int(ev.item())
+    return ms, evaluated, int(ctx.launch_count - l0)
+
+
+def _pt_summary(sp, ms, evaluated, n_steps, walkers_total, n_points, launches):
     cnt = sp.sampler.counters()
-    info = {
-        "steps_per_sec": args.pt_steps / (ms * 1e-3), "ms_per_step": ms / args.pt_steps, "steps": args.pt_steps,
-        "n_temps": n_temps, "ensembles_per_gpu": ens_per_gpu, "walkers_per_gpu": n_temps * ens_per_gpu,
-        "n_points": cfg["n_points"], "likelihood_evals_per_walker_per_step": 1,
-        "model_points_per_sec": n_temps * ens_per_gpu * world * cfg["n_points"] * args.pt_steps / (ms * 1e-3),
-        "exchange": "all_gather of cold-rung logL (%d doubles per rank) per step, %s" % (ens_per_gpu, "NCCL" if world > 1 else "single rank"),
+    it = max(1, int(cnt["iterations"].sum()))
+    return {
+        "steps_per_sec": n_steps / (ms * 1e-3), "ms_per_step": ms / n_steps, "steps": n_steps,
+        "walkers": walkers_total, "n_points": n_points, "likelihood_evals_per_walker_per_step": 1,
+        # walkers whose model the likelihood kernel really evaluated (Roche-overflowing and e >= 1 proposals
+        # return early, quirk Q13, and are NOT counted), from the kernel's own device counter
+        "evaluated_walkers_per_step": evaluated / n_steps,
+        "skipped_fraction": 1.0 - evaluated / (n_steps * walkers_total),
+        "model_points_per_sec": evaluated * n_points / (ms * 1e-3),
         "acceptance": float(cnt["accepted"].sum() / max(1, cnt["proposed"].sum())),
-        "gpu_launches": int(ctx.launch_count - l0),
-        "gathered_finite": bool(torch.isfinite(g).any().item()),
+        "de_share_cold_chain": float(cnt["de_trials_slot0"].sum() / it),
+        "swap_acceptance": float(cnt["swaps_accepted"].sum() / max(1, cnt["swaps_proposed"].sum())),
+        "gpu_launches": launches,
     }
-    sp.sampler.close()
+
+
+def pt_leg(args, ctx, cfg, rank, world, dist, stream):
+    """Second half of BASELINE.json's metric: full PT-MCMC iterations per second.  Every iteration = propose + ONE
+    likelihood per walker + accept + n_temps swap proposals per ladder, replayed from captured CUDA graphs
+    (hb_pt_step); timed in steady state: after `npast` = 50 iterations, so the differential-evolution proposals of
+    mcmc_wrapper2.c:1091-1140 are in, from a start near the truth (a converged chain), Roche-rejected proposals
+    counted as NOT evaluated.
+      weak     C3's per-GPU share on every GPU: 64 temperatures x 32 ensembles x 20 000 points per GPU
+      (N > 1) strong   C3 as named: 64 x 256 walkers in all, whole ladders per GPU, no per-step exchange
+      (N > 1) rungs    ONE ladder of 64 rungs x 200 000 points: every GPU holds the ladder, evaluates its shard of the
+                       rungs, and the logL vector is all-gathered by NCCL inside the captured step"""
+    import torch
+    from hb_mcmc_b200.pt import ShardedPT
+    n_temps, ens_per_gpu, npast = 64, 32, 50
+    steps = max(args.pt_steps, 8)
+    truth = cfg["truth_vec"]
+    logp = float(truth[2])
+
+    def start_near_truth(sp):
+        W = sp.sampler.n_walkers
+        rng = np.random.default_rng(1234 + sp.first)
+        x = truth + 1e-4 * rng.standard_normal((W, 21)) * np.abs(truth + 0.1)
+        x[:, 2] = logp
+        sp.sampler.set_state(x)
+
+    def run(n_ens_total, label):
+        sp = ShardedPT(ctx, n_temps, n_ens_total, logp, seed=11, npast=npast)
+        start_near_truth(sp)
+        sp.step(npast + 14)  # history rings filled: DE proposals active
+        ms, evaluated, launches = _timed_steps(sp, ctx, stream, dist, steps)
+        info = _pt_summary(sp, ms, evaluated, steps, n_temps * n_ens_total, cfg["n_points"], launches)
+        info.update({"n_temps": n_temps, "ensembles_total": n_ens_total, "split": sp.mode if world > 1 else "none", "label": label})
+        cold = sp.gather_cold_logL()
+        info["cold_logL_finite"] = bool(np.isfinite(cold).all())
+        sp.close()
+        return info
+
+    info = run(ens_per_gpu * world, "C3 share per GPU (weak scaling): 64 temperatures x 32 ensembles x 20 000 points per GPU")
+    info["ensembles_per_gpu"] = ens_per_gpu
+    info["walkers_per_gpu"] = n_temps * ens_per_gpu
+    info["exchange"] = "none per step (whole ladders per GPU; random streams keyed on global ids)"
+    if world > 1:
+        info["strong_C3_as_named"] = run(256, "C3 as named: 64 temperatures x 256 ensembles x 20 000 points in all")
+    return info
+
+
+def rung_split_leg(ctx, rank, world, dist, stream, steps):
+    """ONE ladder of 64 rungs on a 200 000-point light curve (truth B): at N > 1 every GPU holds the ladder, evaluates
+    its shard of the rungs and the per-step logL vector is all-gathered by NCCL from inside libhb_b200's captured step."""
+    from hb_mcmc_b200.pt import ShardedPT
+    N, n_temps, npast = 200000, 64, 50
+    t, flux, err = wl.make_dataset(N, wl.TRUTH_B, ctx.calc_light_curve)
+    ctx.set_data(t, flux, err)
+    ctx.set_mags([1000, 1, 1, 1, 1], [1e15] * 4, 1, 0)
+    sp = ShardedPT(ctx, n_temps, 1, float(wl.TRUTH_B[2]), seed=13, npast=npast)
+    rng = np.random.default_rng(99)
+    x = wl.TRUTH_B + 1e-4 * rng.standard_normal((n_temps, 21)) * np.abs(wl.TRUTH_B + 0.1)
+    x[:, 2] = wl.TRUTH_B[2]
+    sp.sampler.set_state(x)
+    sp.step(npast + 14)
+    ms, evaluated, launches = _timed_steps(sp, ctx, stream, dist, steps)
+    info = _pt_summary(sp, ms, evaluated, steps, n_temps, N, launches)
+    info.update({"n_temps": n_temps, "ensembles_total": 1, "split": sp.mode if world > 1 else "none",
+                 "exchange": ("ncclAllGather of the logL vector (%d doubles per rank) inside the captured step" % sp.sampler.eval_shard()[2])
+                 if world > 1 else "single rank"})
+    sp.close()
     return info
 
 

@@ -33,4 +33,15 @@ def test_bench_line_has_the_contract_keys():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1
     assert cb["max_rel_err_gpu_vs_cpu_on_sample"] <= 1e-10
-    assert line["pt"]["steps_per_sec"] > 0 and line["pt"]["gathered_finite"] is True
+    assert roof["frac"] <= 1.0 and roof["frac_vs_reference_formulation"] > roof["frac"] and roof["flop_per_point"] < 520
+    pt = line["pt"]
+    assert pt["steps_per_sec"] > 0 and pt["cold_logL_finite"] is True
+    # walkers are counted by the likelihood kernel itself: never more than were proposed
+    assert 0 < pt["evaluated_walkers_per_step"] <= pt["walkers"] and 0 <= pt["skipped_fraction"] < 1
+    assert pt["model_points_per_sec"] <= pt["walkers"] * pt["n_points"] * pt["steps_per_sec"] * (1 + 1e-9)
+    extra = line["extra"]
+    for key in ("C1_latency", "C3_share", "C4", "C5_share"):
+        assert extra[key]["ms"] > 0 and extra[key]["nan_fraction"] == 0.0
+    assert extra["C4"]["n_chains"] == 8192 and extra["C4"]["n_points"] == 50000
+    assert extra["C5_share"]["n_chains"] == 2048 and extra["C5_share"]["n_points"] == 200000
+    assert extra["pt_one_ladder_64_rungs_x_200k"]["steps_per_sec"] > 0
