@@ -20,6 +20,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(CSRC, "libhb_b200.so")
+LIB_DEBUG = os.path.join(CSRC, "libhb_b200_dbg.so")  # -DHB_DEBUG_BOUNDS: every indexed access asserted (tests only)
 SHIM = os.path.join(CSRC, "libhb_likelihood3.so")
 HOST_DIR = os.path.join(ROOT, "host")
 DRIVER = os.path.join(HOST_DIR, "hb_mcmc")
@@ -59,6 +60,16 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_debug_lib(force: bool = False) -> str:
+    """The bounds-asserting build (hb_select.cuh: HB_CHK): same sources, -DHB_DEBUG_BOUNDS."""
+    srcs = [os.path.join(CSRC, f) for f in ("hb_kernels.cu", "hb_capi.cu", "hb_pt.cu", "hb_gaia_pt.cu", "hb_comm.cu")]
+    deps = _glob(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "hb_b200.h")]
+    if force or _stale(LIB_DEBUG, deps):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-DHB_DEBUG_BOUNDS", "-o", LIB_DEBUG] + srcs + ["-ldl"]
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_DEBUG
+
+
 def build_shim(force: bool = False) -> str | None:
     src = os.path.join(CSRC, "likelihood3_shim.c")
     if not os.path.exists(src):
@@ -86,6 +97,7 @@ def build_driver(force: bool = False) -> str | None:
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_lib(force, verbose)
+    build_debug_lib(force)
     build_shim(force)
     build_driver(force)
 

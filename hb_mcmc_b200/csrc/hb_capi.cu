@@ -179,9 +179,11 @@ int ensure_scratch(hb_ctx* ctx, long n_points)
     return HB_OK;
 }
 
-// CTAs per chain: 1 when the batch fills the grid (or the pass has to store the template), else the largest
-// power of two that keeps chains x parts within the grid, does not exceed the light curve's segment count and
-// respects hb_set_max_parts.  The result never depends on it (see k_chain_eval).
+// CTAs per chain: 1 when the batch fills more than half the grid (or the pass has to store the template), else the
+// largest power of two that keeps chains x parts within the grid, does not exceed the light curve's segment count
+// and respects hb_set_max_parts.  The result never depends on it (see k_chain_eval).  (Sharing only the chains of a
+// large batch's last, partial wave was built and measured: the per-item decode costs the main path more than the
+// shorter tail gives back.)
 int choose_parts(const hb_ctx* ctx, long n_chains, long N, bool hot)
 {
     if (!hot || N <= kCandA / 2) return 1;
@@ -750,6 +752,19 @@ int hb_last_eval_kernel_ms(hb_ctx* ctx, double* ms)
     *ms = (double)f;
     return HB_OK;
 }
+
+#ifdef HB_DEBUG_BOUNDS
+/* libhb_b200_dbg.so only: proves that the bounds assertions fire (index against capacity 4; the trap poisons the context) */
+int hb_debug_bounds_selftest(hb_ctx* ctx, int index)
+{
+    if (!ctx) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(launch_bounds_selftest(index, ctx->d_counter + 1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+#endif
 
 int hb_fp64_peak(hb_ctx* ctx, double seconds_target, double* tflops)
 {

@@ -21,6 +21,10 @@
 #define HB_NEWTON_UNROLL 5
 #endif
 
+#ifndef HB_CHK  // (defined by hb_select.cuh in the bounds-asserting debug build; the host emulation never checks)
+#define HB_CHK(i, cap, site) ((void)0)
+#endif
+
 namespace hb {
 
 constexpr int NPARS = 21;  // likelihood3.h:20
@@ -693,6 +697,7 @@ __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* 
         const double kd = t - kMagic;
         double r = fma(-kd, kTabC[1], x[j]);
         r = fma(-kd, kTabC[2], r);
+        HB_CHK(k, kSinTabN, 1);
         const double2 sc = tab[k];  // {sin, cos}(k h)
         const double z = r * r;
         const double sd = fma(r * z, fma(z, kT5, kTabC[4]), r);
@@ -794,6 +799,7 @@ __device__ __forceinline__ double kepler_table_guess(const double* __restrict__ 
     const double t = x - (double)j;  // in [0, 1]
     // cubic Lagrange on the nodes -1, 0, 1, 2 with the weights paired up:
     //   E = a/6 (y3 (t+1) - y0 (t-2)) + b/2 (y1 (t-1) - y2 t),  a = t (t-1),  b = (t+1)(t-2) = a - 2
+    HB_CHK(j, kTableSize - 3, 2);
     const double y0 = tab[j], y1 = tab[j + 1], y2 = tab[j + 2], y3 = tab[j + 3];
     const double a = fma(t, t, -t);
     const double p = fma(t, y3 - y0, fma(2.0, y0, y3));
@@ -835,6 +841,8 @@ static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab
 #pragma unroll
         for (int i = 0; i < 2; i++) E[i] -= div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
     }
+    HB_CHK(j[0], kTableSize, 3);
+    HB_CHK(j[1], kTableSize, 3);
     ktab[j[0]] = E[0];
     ktab[j[1]] = E[1];
     if (tid == 0) ktab[1] = 0.0;

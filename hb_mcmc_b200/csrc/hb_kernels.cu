@@ -13,8 +13,8 @@
 #include <type_traits>
 
 #include "hb_kernels.h"
-#include "hb_device.cuh"
 #include "hb_select.cuh"
+#include "hb_device.cuh"
 
 namespace hb {
 
@@ -367,6 +367,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             for (int j = 0; j < V; j++) {
                 idx[j] = i0 + j * kThreads;
                 ts[j] = ts_next[j];
+                HB_CHK(idx[j] + (tile + 1 < tile_last ? kTile : 0), (size_t)(n_tiles + 1) * kTile, 6);
                 if (tile + 1 < tile_last) ts_next[j] = tsec[idx[j] + kTile];
                 fl[j] = wv[j] = 0.0;
                 if (kData) {  // one 16-byte load: {flux, 1/sigma} are interleaved
@@ -384,7 +385,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 const double uj = u[j];
                 // with data, a NaN sample poisons S0 and is detected once after the loop
                 if (!kData) nanflag |= valid & (uj != uj);  // the padding of a staged time grid may hold anything
-                if (kStore && valid) tmpl[i] = dkey(uj);
+                if (kStore && valid) {
+                    HB_CHK(i, key_stride, 4);
+                    tmpl[i] = dkey(uj);
+                }
                 if (valid & (uj < lo)) c_lt++;
                 const bool inr = valid & (uj >= lo) & (uj <= hi);
                 const unsigned mask = __ballot_sync(0xffffffffu, inr);
@@ -396,7 +400,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                     if (inr) {
                         const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
                         // (the list in global scratch holds a whole light curve: only the shared-memory one can overflow)
-                        if (!cand_small || pos < kCandA) cand[pos] = dkey(uj);
+                        if (!cand_small || pos < kCandA) {
+                            HB_CHK(pos, cand_cap, 5);
+                            cand[pos] = dkey(uj);
+                        }
                     }
                 }
                 if (kData) {  // padded samples carry weight 0 and a finite model: they add exactly 0
@@ -419,6 +426,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             if (kData && ((((i_here + kTile) & seg_bits) == 0) || tile + 1 == tile_last)) {
                 if (kPart) {
                     const int seg = tile >> seg_shift;
+                    HB_CHK(seg, nseg, 8);
                     partials[(size_t)(2 * seg) * kThreads + tid] = S0;
                     partials[(size_t)(2 * seg + 1) * kThreads + tid] = S1;
                 } else {
@@ -863,6 +871,20 @@ cudaError_t launch_to_seconds(const double* t, int n, double* tsec, cudaStream_t
     k_to_seconds<<<(n + 255) / 256, 256, 0, s>>>(t, n, tsec);
     return cudaGetLastError();
 }
+
+#ifdef HB_DEBUG_BOUNDS
+// self-test of the bounds-asserting build: index `i` against capacity 4 (traps when i >= 4)
+__global__ void k_bounds_selftest(int i, int* out)
+{
+    HB_CHK(i, 4, 99);
+    out[0] = i;
+}
+cudaError_t launch_bounds_selftest(int i, int* out, cudaStream_t s)
+{
+    k_bounds_selftest<<<1, 1, 0, s>>>(i, out);
+    return cudaGetLastError();
+}
+#endif
 
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t s)
 {

@@ -84,6 +84,9 @@ cudaError_t launch_gaia(const double* p6, int n, double D, const double* data, c
 cudaError_t launch_chain_info(const ChainConst* cc, int n, double* out, cudaStream_t s);
 cudaError_t launch_to_seconds(const double* t, int n, double* tsec, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t s);
+#ifdef HB_DEBUG_BOUNDS
+cudaError_t launch_bounds_selftest(int i, int* out, cudaStream_t s);
+#endif
 
 // parallel tempering (hb_pt.cu)
 struct PtConfig;

@@ -7,6 +7,7 @@
 // (history[j], mcmc_wrapper2.c:424,543-546).  One iteration = k_pt_propose -> k_prologue ->
 // k_chain_eval (the likelihood of all E*T proposals, one batch) -> k_pt_accept -> k_pt_swap.
 #include "hb_kernels.h"
+#include "hb_select.cuh"
 #include "hb_pt.cuh"
 
 namespace hb {
@@ -75,6 +76,8 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
         do { b = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast); } while (b == a);
         const bool scaled = pt_draw(seed, id, iter, 0u, d++) < 0.9;
         const double eps_fac = cfg.quirks ? (pt_gaussian(0., 0., 1.e-4) - 0.5) : 0.0;
+        HB_CHK(a, cfg.npast, 30);
+        HB_CHK(b, cfg.npast, 30);
         double dx = hist[b * kPtNpars + n] - hist[a * kPtNpars + n];
         const double eps = dx * eps_fac;
         if (scaled) dx *= pt_normal(seed, id, iter, 0u, d, n) * cfg.gamma;

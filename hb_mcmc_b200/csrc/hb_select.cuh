@@ -18,6 +18,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Bounds-asserting debug build (-DHB_DEBUG_BOUNDS, libhb_b200_dbg.so): every indexed access of the likelihood path
+// -- candidate lists, template keys, the E(M) and sin/cos tables, select buffers, histogram bins, partial sums,
+// the padded data arrays, the sampler's history rings -- is checked against its capacity and TRAPS with the site
+// number; tests/test_gpu_debug_bounds.py runs the edge-size and select stress sweeps under it (compute-sanitizer
+// is not available on the pool).  In the normal build the macro is empty.
+#ifdef HB_DEBUG_BOUNDS
+#include <cstdio>
+static __device__ __noinline__ void hb_bounds_trap(long long i, long long cap, int site)
+{
+    printf("hb_b200 bounds violation: site %d index %lld capacity %lld (block %d thread %d)\n", site, i, cap, (int)blockIdx.x,
+           (int)threadIdx.x);
+    __trap();
+}
+#define HB_CHK(i, cap, site)                                                                               \
+    do {                                                                                                     \
+        if ((unsigned long long)(long long)(i) >= (unsigned long long)(long long)(cap)) hb_bounds_trap((long long)(i), (long long)(cap), site); \
+    } while (0)
+#else
+#define HB_CHK(i, cap, site) ((void)0)
+#endif
+
 namespace hb {
 
 constexpr int kMaxFails = 4;  // unsuccessful rounds before the bisection fallback
@@ -96,6 +117,7 @@ __device__ __noinline__ uint64_t block_sort(uint64_t key, uint64_t* xch)
             if (j >= 32) {
                 xch[tid] = key;
                 __syncthreads();
+                HB_CHK(tid ^ j, kThreads, 20);
                 other = xch[tid ^ j];
                 __syncthreads();
             } else {
@@ -174,7 +196,10 @@ __device__ __noinline__ bool block_select_hist(const uint64_t* keys, int n, int 
         }
 #pragma unroll
         for (int u = 0; u < kBatch; u++)
-            if (base + u * kThreads + tid < n) atomicAdd(&hist[bin_of(xs[u])], 1);
+            if (base + u * kThreads + tid < n) {
+                HB_CHK(bin_of(xs[u]), kThreads, 21);
+                atomicAdd(&hist[bin_of(xs[u])], 1);
+            }
     }
     __syncthreads();
     // block-wide inclusive scan of the bins (one per thread)
@@ -210,7 +235,11 @@ __device__ __noinline__ bool block_select_hist(const uint64_t* keys, int n, int 
         }
 #pragma unroll
         for (int u = 0; u < kBatch; u++)
-            if (base + u * kThreads + tid < n && bin_of(xs[u]) == bin) surv[atomicAdd(&ctl.cnt, 1)] = xs[u];
+            if (base + u * kThreads + tid < n && bin_of(xs[u]) == bin) {
+                const int slot = atomicAdd(&ctl.cnt, 1);
+                HB_CHK(slot, kThreads, 22);
+                surv[slot] = xs[u];
+            }
     }
     __syncthreads();
     if (count <= 32) {
@@ -264,6 +293,7 @@ __device__ __noinline__ uint64_t block_select_key(const uint64_t* keys, int n, i
         if (fails >= kMaxFails) return select_bisect<kThreads>(cur, cur_n, cur_k, ctl.ired);
 
         // ---- sample + sort ----
+        HB_CHK(sample_index(tid, kThreads, cur_n, seed + 0x632be5abu * (uint32_t)(round + 1)), cur_n, 23);
         const uint64_t smp = cur[sample_index(tid, kThreads, cur_n, seed + 0x632be5abu * (uint32_t)(round + 1))];
         __syncthreads();
         const uint64_t sorted = block_sort<kThreads>(smp, ctl.xch);
@@ -320,7 +350,10 @@ __device__ __noinline__ uint64_t block_select_key(const uint64_t* keys, int n, i
                     basepos = __shfl_sync(0xffffffffu, basepos, leader);
                     if (inr) {
                         const int pos = basepos + __popc(mask & ((1u << lane) - 1u));
-                        if (pos < cap) out[pos] = x;
+                        if (pos < cap) {
+                            HB_CHK(pos, cap, 24);
+                            out[pos] = x;
+                        }
                     }
                 }
             }
