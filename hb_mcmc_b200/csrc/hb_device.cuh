@@ -828,7 +828,7 @@ __device__ __forceinline__ double kepler_table_node(int j, double e)
 // Out of line: it runs once per chain and must not weigh on the register allocation of the sample loop.
 #ifndef HB_HOST_EMUL  // (the host emulation fills its table node by node with kepler_table_node)
 template <int kThreads>
-static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab, double e)
+static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab, double e, const double2* __restrict__ sctab)
 {
     static_assert(2 + 2 * kThreads >= kTableSolved, "two table entries per thread must cover the solved half");
     const int tid = threadIdx.x;
@@ -837,7 +837,9 @@ static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab
     double E[2] = {kepler_starter(m[0], e), kepler_starter(m[1], e)}, s[2], c[2];
     int hi = 0;
     for (int k = 0; k < 6; k++) {  // quadratic convergence: a starter only needs ~1e-10
-        sincos_lean<2>(E, s, c, hi);
+        // (0 <= M <= pi + h and e <= 0.99: Newton from the reference starter converges from above, every iterate stays
+        // below 2 pi -- far inside the table sincos' range; the largest argument seen is not tracked)
+        sincos_tab<2>(E, sctab, s, c, hi);
 #pragma unroll
         for (int i = 0; i < 2; i++) E[i] -= div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
     }

@@ -242,7 +242,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= 4 * kTableSize);
         const double* ktab = use_table ? sm.ktab : nullptr;
         if (use_table) {
-            build_kepler_table<kThreads>(sm.ktab, cc.e);
+            build_kepler_table<kThreads>(sm.ktab, cc.e, sctab);
         }
 
         // ---- pre-sample: bracket of the median rank + expansion point ----
