@@ -15,6 +15,7 @@
 #include "hb_comm.h"
 #include "hb_gaia_pt.cuh"
 #include "hb_pt.cuh"
+#include "hb_pt_run.h"
 #include "hb_sincos_tab.h"
 
 using namespace hb;
@@ -820,6 +821,10 @@ struct hb_pt {
     int shard_rank = 0, shard_world = 1;
     long eval_first = 0, eval_count = 0, chunk = 0;
     hb_comm* comm = nullptr;  // NCCL communicator of the all-gather (not owned); nullptr: host-driven exchange
+    // one-launch step loop (k_pt_run) for short light curves: on by default where it applies
+    bool allow_run = true;
+    unsigned* d_barrier = nullptr;
+    int run_max_walkers = -1;
     // one iteration captured as a CUDA graph (the step is latency-bound at the reference's sizes)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -920,7 +925,8 @@ int hb_pt_create_sharded(hb_ctx* ctx, hb_pt** out, int n_temps, int n_ens, int e
               cudaMalloc((void**)&pt->index, (size_t)W * sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&pt->jump, (size_t)W * sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&pt->counters, (size_t)n_ens * 8 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc((void**)&pt->d_iter, 2 * sizeof(unsigned)) == cudaSuccess;
+              cudaMalloc((void**)&pt->d_iter, 2 * sizeof(unsigned)) == cudaSuccess &&
+              cudaMalloc((void**)&pt->d_barrier, sizeof(unsigned)) == cudaSuccess;
     if (!ok) {
         fail_cuda(ctx, cudaGetLastError(), "hb_pt_create: cudaMalloc");
         hb_pt_destroy(pt);
@@ -949,7 +955,7 @@ void hb_pt_destroy(hb_pt* pt)
         cudaStreamSynchronize(pt->ctx->stream);
         cudaFree(pt->d_cfg); cudaFree(pt->x); cudaFree(pt->y); cudaFree(pt->logLx); cudaFree(pt->logLy);
         cudaFree(pt->logPy); cudaFree(pt->tmp); cudaFree(pt->history); cudaFree(pt->xmap); cudaFree(pt->logLmap);
-        cudaFree(pt->index); cudaFree(pt->jump); cudaFree(pt->counters); cudaFree(pt->d_iter);
+        cudaFree(pt->index); cudaFree(pt->jump); cudaFree(pt->counters); cudaFree(pt->d_iter); cudaFree(pt->d_barrier);
         if (pt->graph_exec) cudaGraphExecDestroy(pt->graph_exec);
         if (pt->graph) cudaGraphDestroy(pt->graph);
         if (pt->graph_exec_k) cudaGraphExecDestroy(pt->graph_exec_k);
@@ -1025,6 +1031,25 @@ int hb_pt_step(hb_pt* pt, long n_iters)
         return HB_ERR_STATE;
     }
     if ((rc = ensure_chains(ctx, pt->W)) != HB_OK) return rc;
+    // Short light curves, every walker resident at once, nothing sharded: the whole loop in ONE launch (k_pt_run)
+    if (pt->allow_run && pt->shard_world == 1 && n_iters > 0 && ctx->N > 0 && ctx->N <= kPtRunMaxPoints && !ctx->time_kernels) {
+        if (pt->run_max_walkers < 0) {
+            CK(configure_pt_run());
+            CK(pt_run_max_walkers(ctx->sm_count, &pt->run_max_walkers));
+        }
+        if (pt->W <= pt->run_max_walkers) {
+            PtRunArgs a;
+            a.cfg = pt->d_cfg; a.d_iter = pt->d_iter; a.x = pt->x; a.y = pt->y; a.logLx = pt->logLx; a.logLy = pt->logLy;
+            a.logPy = pt->logPy; a.jump = pt->jump; a.index = pt->index; a.history = pt->history; a.counters = pt->counters;
+            a.xmap = pt->xmap; a.logLmap = pt->logLmap; a.tsec = ctx->d_t; a.fw = ctx->d_fw; a.N = (int)ctx->N;
+            a.sctab = ctx->d_sctab; a.barrier = pt->d_barrier; a.evaluated = ctx->d_evaluated; a.n_iters = n_iters; a.ms = ctx->ms;
+            CK(cudaMemsetAsync(pt->d_barrier, 0, sizeof(unsigned), ctx->stream));
+            CK(launch_pt_run(a, pt->W, ctx->stream));
+            ctx->launches += 1;
+            pt->iter += n_iters;
+            return HB_OK;
+        }
+    }
     // Several iterations in one call: replay a captured graph of one iteration (6 nodes) instead of
     // issuing 6 launches per iteration.  The graph is re-captured when the context's buffers or
     // by-value kernel arguments changed (generation), never while kernel timing is on.
@@ -1068,6 +1093,14 @@ int hb_pt_step(hb_pt* pt, long n_iters)
         }
         pt->iter++;
     }
+    return HB_OK;
+}
+
+int hb_pt_set_one_launch(hb_pt* pt, int enable)
+{
+    if (!pt) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(pt->ctx->mu);
+    pt->allow_run = enable != 0;
     return HB_OK;
 }
 

@@ -8,7 +8,9 @@
 // k_chain_eval (the likelihood of all E*T proposals, one batch) -> k_pt_accept -> k_pt_swap.
 #include "hb_kernels.h"
 #include "hb_select.cuh"
+#include "hb_device.cuh"
 #include "hb_pt.cuh"
+#include "hb_pt_run.h"
 
 namespace hb {
 
@@ -42,24 +44,18 @@ __device__ __forceinline__ double warp_ordered_sum(double term, int count)
     return acc;  // identical on every lane
 }
 
-__global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__ cfgp, const unsigned* __restrict__ iter_ptr,
-                                                    const double* __restrict__ x, const int* __restrict__ index,
-                                                    const double* __restrict__ history, double* __restrict__ y,
-                                                    double* __restrict__ logPy, int* __restrict__ jump, int W)
+// One walker's proposal by its warp (lane n owns parameter n): rung r (global rung id = r + ens_offset T for the random
+// streams), temperature rung j, this lane's component xn of the current state, the rung's history ring.  Returns this lane's component of y;
+// lane 0 also gets the prior term and the jump type.  mcmc_wrapper2.c:390-481.
+__device__ __forceinline__ double pt_propose_warp(const PtConfig& cfg, unsigned iter, int r, int j, int lane,
+                                                  const double xn, const double* __restrict__ hist,
+                                                  double& logP_out, int& jump_out)
 {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global rung id = ens * T + j
-    const int lane = threadIdx.x & 31;
-    if (r >= W) return;
-    const unsigned iter = *iter_ptr;
-    const PtConfig& cfg = *cfgp;
-    const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
-    const int c = ens * T + index[r];
+    const int T = cfg.n_temps;
     const int n = lane < kPtNpars ? lane : kPtNpars - 1;  // idle lanes shadow the last parameter
     const unsigned long long seed = cfg.seed;
     const uint32_t id = (uint32_t)(r + cfg.ens_offset * T);  // global rung id
     const double temp = cfg.temp[j];
-    const double xn = x[(size_t)c * kPtNpars + n];
-    const double* hist = history + (size_t)r * cfg.npast * kPtNpars;
 
     const double alpha = pt_draw(seed, id, iter, 0u, 0u);
     const double jscale = pow(10., -6. + 6. * alpha);
@@ -104,7 +100,27 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
     double mean, sig;
     pt_prior_of(n, mean, sig);
     const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(yn, mean, sig)) : 0.0;
-    const double lp = warp_ordered_sum(term, kPtNpars);
+    logP_out = warp_ordered_sum(term, kPtNpars);
+    jump_out = jump_type;
+    return yn;
+}
+
+__global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__ cfgp, const unsigned* __restrict__ iter_ptr,
+                                                    const double* __restrict__ x, const int* __restrict__ index,
+                                                    const double* __restrict__ history, double* __restrict__ y,
+                                                    double* __restrict__ logPy, int* __restrict__ jump, int W)
+{
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // local rung id = ens * T + j
+    const int lane = threadIdx.x & 31;
+    if (r >= W) return;
+    const unsigned iter = *iter_ptr;
+    const PtConfig& cfg = *cfgp;
+    const int T = cfg.n_temps, ens = r / T, j = r - ens * T;
+    const int c = ens * T + index[r];
+    double lp;
+    int jump_type;
+    const double xn = x[(size_t)c * kPtNpars + (lane < kPtNpars ? lane : kPtNpars - 1)];
+    const double yn = pt_propose_warp(cfg, iter, r, j, lane, xn, history + (size_t)r * cfg.npast * kPtNpars, lp, jump_type);
     if (lane < kPtNpars) y[(size_t)c * kPtNpars + lane] = yn;
     if (lane == 0) {
         logPy[c] = lp;
@@ -115,6 +131,32 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
 // counters per ensemble: 0 acc (chain slot 0 accepted, the reference's `acc`), 1 DE trials of slot 0,
 // 2 DE accepted of slot 0, 3 accepted over all rungs, 4 proposals over all rungs, 5 swaps accepted,
 // 6 swaps proposed, 7 iterations
+// Metropolis-Hastings decision for the walker at local rung r (chain slot state xn per lane); mcmc_wrapper2.c:492-505.
+__device__ __forceinline__ bool pt_accept_warp(const PtConfig& cfg, unsigned iter, int r, int j, int lane, double xn,
+                                               double logLx, double logLy, double logPy)
+{
+    const int n = lane < kPtNpars ? lane : kPtNpars - 1;
+    double mean, sig;
+    pt_prior_of(n, mean, sig);
+    const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(xn, mean, sig)) : 0.0;
+    const double logPx = warp_ordered_sum(term, kPtNpars);
+    return pt_accept(cfg, (uint32_t)(r + cfg.ens_offset * cfg.n_temps), iter, cfg.temp[j], logLx, logLy, logPx, logPy);
+}
+
+// counters of one walker's step (lane 0 calls): see the list above
+__device__ __forceinline__ void pt_count_step(unsigned long long* cnt, int slot, int jt, bool acc)
+{
+    if (slot == 0 && jt == 2) atomicAdd(&cnt[1], 1ull);
+    atomicAdd(&cnt[4], 1ull);
+    if (acc) {
+        atomicAdd(&cnt[3], 1ull);
+        if (slot == 0) {
+            atomicAdd(&cnt[0], 1ull);
+            if (jt == 2) atomicAdd(&cnt[2], 1ull);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ cfgp, const unsigned* __restrict__ iter_ptr, double* __restrict__ x,
                                                    const double* __restrict__ y, double* __restrict__ logLx,
                                                    const double* __restrict__ logLy, const double* __restrict__ logPy,
@@ -131,31 +173,62 @@ __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ 
     const int slot = index[r], c = ens * T + slot;
     const int n = lane < kPtNpars ? lane : kPtNpars - 1;
     double xn = x[(size_t)c * kPtNpars + n];
-    double mean, sig;
-    pt_prior_of(n, mean, sig);
-    const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(xn, mean, sig)) : 0.0;
-    const double logPx = warp_ordered_sum(term, kPtNpars);
-    const bool acc = pt_accept(cfg, (uint32_t)(r + cfg.ens_offset * T), iter, cfg.temp[j], logLx[c], logLy[c], logPx, logPy[c]);
+    const bool acc = pt_accept_warp(cfg, iter, r, j, lane, xn, logLx[c], logLy[c], logPy[c]);
     const int jt = jump[c];
     if (acc) {
         xn = y[(size_t)c * kPtNpars + n];
         if (lane < kPtNpars) x[(size_t)c * kPtNpars + lane] = xn;
     }
     if (lane == 0) {
-        unsigned long long* cnt = counters + (size_t)ens * 8;
-        if (slot == 0 && jt == 2) atomicAdd(&cnt[1], 1ull);
-        atomicAdd(&cnt[4], 1ull);
-        if (acc) {
-            logLx[c] = logLy[c];
-            atomicAdd(&cnt[3], 1ull);
-            if (slot == 0) {
-                atomicAdd(&cnt[0], 1ull);
-                if (jt == 2) atomicAdd(&cnt[2], 1ull);
-            }
-        }
+        pt_count_step(counters + (size_t)ens * 8, slot, jt, acc);
+        if (acc) logLx[c] = logLy[c];
     }
     // history[j][iter % NPAST] = x[chain_id]  (mcmc_wrapper2.c:381,543-546)
     if (lane < kPtNpars) history[((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars + lane] = xn;
+}
+
+// One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
+// (swap s consumes exactly block s of the ensemble's Philox stream), lane 0 then applies them in
+// order -- each decision depends on the permutation left by the previous one (mcmc_wrapper2.c:554-563).
+// The n_temps swap proposals of one ensemble by one warp (mcmc_wrapper2.c:554-563, ptmcmc :768-817).  s_idx (rung ->
+// slot) and s_logL (by slot) are staged by the caller; on return s_idx holds the new permutation (every lane may read
+// it after the trailing __syncwarp) and the accepted count is returned to lane 0.
+__device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* s_b, double* s_beta,
+                                            double* s_dbeta, int* s_idx, const double* s_logL)
+{
+    const int T = cfg.n_temps;
+    // (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop below
+    // touches shared memory only (the ladder lives in global memory: a dependent load per swap otherwise)
+    for (int s = lane; s + 1 < T; s += 32) {
+        const double heat1 = cfg.temp[s + 1], heat2 = cfg.temp[s];
+        s_dbeta[s] = (heat2 - heat1) / (heat2 * heat1);
+    }
+    for (int s = lane; s < T; s += 32) {
+        U4 c; c.x = 0x80000000u | (uint32_t)(ens_local + cfg.ens_offset); c.y = iter; c.z = 2u; c.w = (uint32_t)s;
+        const U4 r = philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+        const double u0 = ((double)(((uint64_t)r.x << 21) | (r.y >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u1 = ((double)(((uint64_t)r.z << 21) | (r.w >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        int b = (int)(u0 * (double)(T - 1));
+        if (b > T - 2) b = T - 2;
+        s_b[s] = b;
+        s_beta[s] = log(u1);  // exp(x) >= beta  <=>  x >= log(beta): the log is taken here, in parallel
+    }
+    __syncwarp();
+    int nacc = 0;
+    if (lane == 0) {
+        for (int s = 0; s < T && T > 1; s++) {
+            const int b = s_b[s], a = b + 1;
+            const int olda = s_idx[a], oldb = s_idx[b];
+            const double lalpha = (s_logL[oldb] - s_logL[olda]) * s_dbeta[b];
+            if (lalpha >= s_beta[s]) {
+                s_idx[a] = oldb;
+                s_idx[b] = olda;
+                nacc++;
+            }
+        }
+    }
+    __syncwarp();
+    return nacc;
 }
 
 // One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
@@ -175,44 +248,19 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
     __shared__ double s_beta[kPtMaxTemps];  // log of the acceptance draw
     __shared__ int s_idx[kPtMaxTemps];
     __shared__ double s_logL[kPtMaxTemps];
-    // (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop below
-    // touches shared memory only (the ladder lives in global memory: a dependent load per swap otherwise)
     __shared__ double s_dbeta[kPtMaxTemps];
-    for (int s = lane; s + 1 < T; s += 32) {
-        const double heat1 = cfg.temp[s + 1], heat2 = cfg.temp[s];
-        s_dbeta[s] = (heat2 - heat1) / (heat2 * heat1);
-    }
     for (int s = lane; s < T; s += 32) {
-        U4 c; c.x = 0x80000000u | (uint32_t)(ens + cfg.ens_offset); c.y = iter; c.z = 2u; c.w = (uint32_t)s;
-        const U4 r = philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
-        const double u0 = ((double)(((uint64_t)r.x << 21) | (r.y >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
-        const double u1 = ((double)(((uint64_t)r.z << 21) | (r.w >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
-        int b = (int)(u0 * (double)(T - 1));
-        if (b > T - 2) b = T - 2;
-        s_b[s] = b;
-        s_beta[s] = log(u1);  // exp(x) >= beta  <=>  x >= log(beta): the log is taken here, in parallel
         s_idx[s] = index[(size_t)ens * T + s];
         s_logL[s] = logLx[(size_t)ens * T + s];
     }
     __syncwarp();
+    const int nacc = pt_swap_warp(cfg, iter, ens, lane, s_b, s_beta, s_dbeta, s_idx, s_logL);
     if (lane == 0) {
-        int nacc = 0;
-        for (int s = 0; s < T && T > 1; s++) {
-            const int b = s_b[s], a = b + 1;
-            const int olda = s_idx[a], oldb = s_idx[b];
-            const double lalpha = (s_logL[oldb] - s_logL[olda]) * s_dbeta[b];
-            if (lalpha >= s_beta[s]) {
-                s_idx[a] = oldb;
-                s_idx[b] = olda;
-                nacc++;
-            }
-        }
         unsigned long long* cnt = counters + (size_t)ens * 8;
         cnt[5] += (unsigned long long)nacc;
         cnt[6] += (unsigned long long)T;
         cnt[7] += 1ull;
     }
-    __syncwarp();
     for (int s = lane; s < T; s += 32) index[(size_t)ens * T + s] = s_idx[s];
     // MAP of the cold rung (mcmc_wrapper2.c:565-572)
     const int c0 = ens * T + s_idx[0];
@@ -254,6 +302,189 @@ __global__ void k_pt_logL_by_rung(const PtConfig* __restrict__ cfgp, const int* 
     if (r >= W) return;
     const int T = cfgp->n_temps, ens = r / T;
     out[r] = logLx[ens * T + index[r]];
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole step loop in ONE launch, for ladders whose light curves are short (the reference's real, folded light
+// curves have 163-763 points): at that size an iteration is a few microseconds of arithmetic and the five launches
+// of the stream-ordered path (propose, prologue, likelihood, accept, swap) are all latency.  Here every walker
+// (ensemble, rung) owns a CTA for the whole run: warp 0 proposes (lane = parameter) and folds the proposal's
+// constants (chain prologue, lanes = libm calls), the CTA evaluates the light curve and its exact median from
+// shared memory, warp 0 accepts; ONE grid-wide barrier per iteration publishes the new log-likelihoods, after which
+// every CTA of a ladder replays the ladder's n_temps swap proposals for itself (the permutation lives in each CTA's
+// shared memory; rung 0's CTA keeps the counters and the MAP).  Same device functions, same order of operations as
+// the stream-ordered kernels: the chains are identical bit for bit (tests/test_gpu_pt.py).  mcmc_wrapper2.c:378-572.
+struct PtRunShared {
+    ChainConst cc;
+    SelectCtl<kEvalThreads> ctl;
+    double red[32];
+    double y[kPtNpars + 3];
+    double logPy, logLy;
+    int jump;
+    int s_b[kPtMaxTemps];
+    int s_idx[kPtMaxTemps];
+    double s_beta[kPtMaxTemps], s_dbeta[kPtMaxTemps], s_logL[kPtMaxTemps];
+    double2 sctab[kSinTabN];
+    uint64_t keys[kPtRunMaxPoints];  // template keys of the proposal's light curve
+    uint64_t bufA[kPtRunMaxPoints], bufB[kPtRunMaxPoints];  // survivor buffers of the select
+};
+
+size_t pt_run_smem_bytes() { return sizeof(PtRunShared); }
+
+// likelihood of the chain whose constants sit in sm.cc (the small-light-curve path of k_chain_eval: template stored,
+// exact order statistic, chi^2 summed in the reference's own form, likelihood3.c:681-685,809-873)
+__device__ __forceinline__ double pt_run_loglike(PtRunShared& sm, const PtRunArgs& a, int tid)
+{
+    const ChainConst& cc = sm.cc;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int N = a.N;
+    const int flag = (int)cc.flag;
+    const bool roche = flag & 1, nan_model = flag & 2;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (nan_model || roche || N <= 0) return roche ? -0.5 * kBig : (nan_model ? qnan : -0.5 * cc.chi2_extra);  // (uniform; Q13)
+    if (tid == 0 && a.evaluated != nullptr) atomicAdd(a.evaluated, 1ull);
+    int nanflag = 0;
+    const int n_tiles = (N + kEvalThreads - 1) / kEvalThreads;
+    for (int tile = 0; tile < n_tiles; tile++) {
+        const int i = tile * kEvalThreads + tid;
+        const double ts[1] = {a.tsec[i]};  // (padded to whole tiles)
+        double u[1];
+        raw_flux<1, true, true, false>(cc, nullptr, sm.sctab, ts, u);
+        const bool valid = i < N;
+        nanflag |= valid & (u[0] != u[0]);
+        if (valid) sm.keys[i] = dkey(u[0]);
+    }
+    if (__syncthreads_or(nanflag)) return qnan;
+    int krank = (N % 2 == 0) ? N / 2 : N / 2 + 1;  // likelihood3.c:97-101 (quirk Q3)
+    if (krank > N - 1) krank = N - 1;
+    const SelectBuf bufs[2] = {{sm.bufA, kPtRunMaxPoints}, {sm.bufB, kPtRunMaxPoints}};
+    const double med = dunkey(block_select_key<kEvalThreads>(sm.keys, N, krank, sm.ctl, bufs, 2, (uint32_t)cc.seed ^ 0x9e3779b9u));
+    double S0 = 0.;
+    const double blend = cc.blend, ft = cc.ft;
+    for (int i = tid; i < N; i += kEvalThreads) {
+        const double2 v = a.fw[i];
+        const double r = (finish_template(dunkey(sm.keys[i]), med, blend, ft) - v.x) * v.y;
+        S0 = fma(r, r, S0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S0 += __shfl_xor_sync(0xffffffffu, S0, o);
+    if (lane == 0) sm.red[wid] = S0;
+    __syncthreads();
+    double t0 = 0.;
+    for (int i = 0; i < kEvalThreads / 32; i++) t0 += sm.red[i];
+    __syncthreads();
+    return -0.5 * (t0 + cc.chi2_extra);
+}
+
+__global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__ PtRunArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PtRunShared& sm = *reinterpret_cast<PtRunShared*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const PtConfig& cfg = *a.cfg;
+    const int T = cfg.n_temps;
+    const int r = blockIdx.x, ens = r / T, j = r - ens * T;  // this CTA's walker: local rung id, ladder, rung
+    const int n = lane < kPtNpars ? lane : kPtNpars - 1;
+    for (int i = tid; i < kSinTabN; i += kEvalThreads) sm.sctab[i] = a.sctab[i];
+    for (int s = tid; s < T; s += kEvalThreads) sm.s_idx[s] = a.index[(size_t)ens * T + s];
+    __syncthreads();
+    unsigned iter = a.d_iter[0];
+    const double* hist = a.history + (size_t)r * cfg.npast * kPtNpars;
+    for (long it = 0; it < a.n_iters; it++, iter++) {
+        const int slot = sm.s_idx[j], c = ens * T + slot;
+        if (wid == 0) {  // proposal and its folded constants
+            const double xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);  // (written by another CTA when the slot changed hands)
+            double lp;
+            int jt;
+            const double yn = pt_propose_warp(cfg, iter, r, j, lane, xn, hist, lp, jt);
+            if (lane < kPtNpars) {
+                sm.y[lane] = yn;
+                a.y[(size_t)c * kPtNpars + lane] = yn;
+            }
+            if (lane == 0) {
+                sm.logPy = lp;
+                sm.jump = jt;
+                a.logPy[c] = lp;
+                a.jump[c] = jt;
+            }
+            __syncwarp();
+            PrologueT P;
+            prologue_trans_warp(sm.y, a.ms, P, lane);
+            if (lane == 0) prologue_assemble(sm.y, a.ms, P, sm.cc);
+        }
+        __syncthreads();
+        const double logLy = pt_run_loglike(sm, a, tid);
+        if (wid == 0) {  // accept / reject, history ring
+            double xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);
+            const double logLx = __ldcg(&a.logLx[c]);
+            const bool acc = pt_accept_warp(cfg, iter, r, j, lane, xn, logLx, logLy, sm.logPy);
+            if (acc) {
+                xn = sm.y[n];
+                if (lane < kPtNpars) a.x[(size_t)c * kPtNpars + lane] = xn;
+            }
+            if (lane == 0) {
+                a.logLy[c] = logLy;
+                pt_count_step(a.counters + (size_t)ens * 8, slot, sm.jump, acc);
+                if (acc) a.logLx[c] = logLy;
+            }
+            if (lane < kPtNpars) a.history[((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars + lane] = xn;
+        }
+        // ---- every walker's new state and log-likelihood are published: one grid-wide barrier per iteration ----
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(a.barrier, 1u);
+            const unsigned want = (unsigned)(it + 1) * gridDim.x;
+            while (*((volatile unsigned*)a.barrier) < want) {}
+            __threadfence();
+        }
+        __syncthreads();
+        if (wid == 0) {  // the ladder's swap proposals, replayed identically by each of its CTAs
+            for (int s = lane; s < T; s += 32) sm.s_logL[s] = __ldcg(&a.logLx[(size_t)ens * T + s]);
+            __syncwarp();
+            const int nacc = pt_swap_warp(cfg, iter, ens, lane, sm.s_b, sm.s_beta, sm.s_dbeta, sm.s_idx, sm.s_logL);
+            if (j == 0) {  // rung 0's CTA keeps the ladder's books: counters and the MAP (mcmc_wrapper2.c:565-572)
+                if (lane == 0) {
+                    unsigned long long* cnt = a.counters + (size_t)ens * 8;
+                    cnt[5] += (unsigned long long)nacc;
+                    cnt[6] += (unsigned long long)T;
+                    cnt[7] += 1ull;
+                }
+                const int s0 = sm.s_idx[0], c0 = ens * T + s0;
+                const bool better = sm.s_logL[s0] > a.logLmap[ens];
+                __syncwarp();
+                if (better) {
+                    if (lane < kPtNpars) a.xmap[(size_t)ens * kPtNpars + lane] = __ldcg(&a.x[(size_t)c0 * kPtNpars + lane]);
+                    if (lane == 0) a.logLmap[ens] = sm.s_logL[s0];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (j == 0)
+        for (int s = tid; s < T; s += kEvalThreads) a.index[(size_t)ens * T + s] = sm.s_idx[s];
+    if (blockIdx.x == 0 && tid == 0) a.d_iter[0] = iter;
+}
+
+cudaError_t configure_pt_run()
+{
+    return cudaFuncSetAttribute(k_pt_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtRunShared));
+}
+
+// the most walkers one launch can hold (every CTA must be resident for the grid barrier)
+cudaError_t pt_run_max_walkers(int sm_count, int* out)
+{
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_run, kEvalThreads, sizeof(PtRunShared));
+    *out = per_sm * sm_count;
+    return e;
+}
+
+cudaError_t launch_pt_run(const PtRunArgs& a, int W, cudaStream_t s)
+{
+    void* params[1] = {const_cast<PtRunArgs*>(&a)};
+    return cudaLaunchCooperativeKernel((const void*)k_pt_run, dim3(W), dim3(kEvalThreads), params, sizeof(PtRunShared), s);
 }
 
 #define LAUNCH1D(kern, n, s, ...)                                         \

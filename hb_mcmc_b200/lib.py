@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "hb_pt_get_state", "hb_pt_get_proposal", "hb_pt_get_cold", "hb_pt_get_logL_by_rung", "hb_pt_get_map",
     "hb_pt_get_counters", "hb_pt_device_logL", "hb_pt_cold_logL_dev",
     "hb_pt_create_sharded", "hb_pt_set_eval_shard", "hb_pt_get_eval_shard", "hb_pt_set_comm", "hb_pt_step_begin",
-    "hb_pt_exchange_local", "hb_pt_step_end",
+    "hb_pt_exchange_local", "hb_pt_step_end", "hb_pt_set_one_launch",
     "hb_comm_unique_id", "hb_comm_create", "hb_comm_create_all", "hb_comm_destroy", "hb_comm_rank", "hb_comm_world",
     "hb_comm_nccl_version", "hb_comm_last_error", "hb_comm_allgather_f64",
     "hb_gaia_pt_create", "hb_gaia_pt_destroy", "hb_gaia_pt_set_data", "hb_gaia_pt_set_sigma", "hb_gaia_pt_init_random",
@@ -116,6 +116,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.hb_pt_step_begin.argtypes = [vp]
     L.hb_pt_exchange_local.argtypes = [C.POINTER(vp), i]
     L.hb_pt_step_end.argtypes = [vp]
+    L.hb_pt_set_one_launch.argtypes = [vp, i]
     L.hb_comm_unique_id.argtypes = [C.c_char_p]
     L.hb_comm_create.argtypes = [C.POINTER(vp), i, C.c_char_p, i, i]
     L.hb_comm_create_all.argtypes = [C.POINTER(vp), C.POINTER(i), i]

@@ -79,6 +79,10 @@ class PTSampler:
     def step(self, n_iters: int = 1):
         self._ck(self._L.hb_pt_step(self._h, int(n_iters)))
 
+    def set_one_launch(self, enable: bool):
+        """Short light curves: run whole step loops in one launch (default) or as stream-ordered kernels."""
+        self._ck(self._L.hb_pt_set_one_launch(self._h, int(enable)))
+
     # -- likelihood evaluation split over several samplers that hold the same state (see hb_b200.h) --------------
     def set_eval_shard(self, rank: int, world: int):
         self._ck(self._L.hb_pt_set_eval_shard(self._h, int(rank), int(world)))

@@ -112,6 +112,10 @@ int hb_pt_set_state(hb_pt* pt, const double* x);
  * current-state value is cached, the reference re-evaluates it, :488), accepts/rejects; then
  * n_temps swap proposals per ensemble (:554-563) and the MAP update (:565-572) */
 int hb_pt_step(hb_pt* pt, long n_iters);
+/* Light curves of at most 1024 points (the reference's real, folded ones have 163-763) with every walker resident at
+ * once: hb_pt_step runs the whole n_iters loop in ONE launch (a CTA per walker, one grid-wide barrier per iteration)
+ * instead of five stream-ordered kernels per iteration -- same chains bit for bit.  enable = 0 turns that off. */
+int hb_pt_set_one_launch(hb_pt* pt, int enable);
 long hb_pt_iteration(const hb_pt* pt);
 int hb_pt_get_state(hb_pt* pt, double* x, double* logL, int* index);       /* any may be NULL */
 int hb_pt_get_proposal(hb_pt* pt, double* y, double* logLy, double* logPy); /* last proposals, by slot */

@@ -125,6 +125,8 @@ def test_graph_replay_equals_single_steps(ctx, setup):
     t, flux, err = setup
     a = PTSampler(ctx, 7, 4, float(wl.TRUTH_A[2]), seed=99, npast=12)
     b = PTSampler(ctx, 7, 4, float(wl.TRUTH_A[2]), seed=99, npast=12)
+    for s in (a, b):
+        s.set_one_launch(False)  # the stream-ordered kernels (light curves this short would take the one-launch loop)
     a.init_random()
     b.init_random()
     for _ in range(40):
@@ -147,3 +149,32 @@ def test_graph_replay_equals_single_steps(ctx, setup):
     ctx.set_data(t, flux, err)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("T,E,N", [(50, 1, 375), (7, 4, 600), (64, 9, 1024), (12, 3, 163)])
+def test_one_launch_loop_equals_stream_ordered_steps(ctx, setup, T, E, N):
+    """Short light curves: hb_pt_step runs the whole loop in ONE launch (k_pt_run: a CTA per walker, one grid-wide
+    barrier per iteration).  Same device functions in the same order as the five stream-ordered kernels per iteration:
+    states, proposals, permutations, MAP and counters must be identical bit for bit -- in uneven chunks, across a
+    change of the data set, and for more walkers than fit one wave of the stream-ordered likelihood kernel."""
+    t, flux, err = setup
+    ctx.set_data(t[:N] if N <= len(t) else wl.time_grid(N), flux[:N] if N <= len(t) else np.resize(flux, N),
+                 err[:N] if N <= len(t) else np.resize(err, N))
+    a = PTSampler(ctx, T, E, float(wl.TRUTH_A[2]), seed=5, npast=10)
+    b = PTSampler(ctx, T, E, float(wl.TRUTH_A[2]), seed=5, npast=10)
+    b.set_one_launch(False)
+    a.init_random()
+    b.init_random()
+    done = 0
+    for chunk in (1, 2, 30, 7):  # past npast: DE proposals from the history rings
+        a.step(chunk)
+        b.step(chunk)
+        done += chunk
+        for u, v in zip(a.state() + a.proposal() + a.map(), b.state() + b.proposal() + b.map()):
+            assert np.array_equal(u, v, equal_nan=True), (chunk, done)
+        ca, cb = a.counters(), b.counters()
+        assert all(np.array_equal(ca[k], cb[k]) for k in ca) and a.iteration == b.iteration == done
+    assert ctx.evaluated_chains(reset=True) > 0
+    a.close()
+    b.close()
+    ctx.set_data(t, flux, err)
