@@ -1040,7 +1040,7 @@ int hb_pt_step(hb_pt* pt, long n_iters)
         if (pt->W <= pt->run_max_walkers) {
             PtRunArgs a;
             a.cfg = pt->d_cfg; a.d_iter = pt->d_iter; a.x = pt->x; a.y = pt->y; a.logLx = pt->logLx; a.logLy = pt->logLy;
-            a.logPy = pt->logPy; a.jump = pt->jump; a.index = pt->index; a.history = pt->history; a.counters = pt->counters;
+            a.logPy = pt->logPy; a.logPx = pt->tmp; a.jump = pt->jump; a.index = pt->index; a.history = pt->history; a.counters = pt->counters;
             a.xmap = pt->xmap; a.logLmap = pt->logLmap; a.tsec = ctx->d_t; a.fw = ctx->d_fw; a.N = (int)ctx->N;
             a.sctab = ctx->d_sctab; a.barrier = pt->d_barrier; a.evaluated = ctx->d_evaluated; a.n_iters = n_iters; a.ms = ctx->ms;
             CK(cudaMemsetAsync(pt->d_barrier, 0, sizeof(unsigned), ctx->stream));

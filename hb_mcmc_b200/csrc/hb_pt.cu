@@ -6,6 +6,8 @@
 // this permutation, not the states, mcmc_wrapper2.c:812-816); the DE history ring is per RUNG
 // (history[j], mcmc_wrapper2.c:424,543-546).  One iteration = k_pt_propose -> k_prologue ->
 // k_chain_eval (the likelihood of all E*T proposals, one batch) -> k_pt_accept -> k_pt_swap.
+#include <cstdio>
+
 #include "hb_kernels.h"
 #include "hb_select.cuh"
 #include "hb_device.cuh"
@@ -132,14 +134,20 @@ __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__
 // 2 DE accepted of slot 0, 3 accepted over all rungs, 4 proposals over all rungs, 5 swaps accepted,
 // 6 swaps proposed, 7 iterations
 // Metropolis-Hastings decision for the walker at local rung r (chain slot state xn per lane); mcmc_wrapper2.c:492-505.
-__device__ __forceinline__ bool pt_accept_warp(const PtConfig& cfg, unsigned iter, int r, int j, int lane, double xn,
-                                               double logLx, double logLy, double logPy)
+// log prior of a state by its warp (lane n holds component n); get_logP, mcmc_wrapper2.c:703-765
+__device__ __forceinline__ double pt_prior_warp(const PtConfig& cfg, int lane, double xn)
 {
     const int n = lane < kPtNpars ? lane : kPtNpars - 1;
     double mean, sig;
     pt_prior_of(n, mean, sig);
     const double term = (cfg.gauss[n] == 1) ? log(pt_gaussian(xn, mean, sig)) : 0.0;
-    const double logPx = warp_ordered_sum(term, kPtNpars);
+    return warp_ordered_sum(term, kPtNpars);
+}
+
+__device__ __forceinline__ bool pt_accept_warp(const PtConfig& cfg, unsigned iter, int r, int j, int lane, double xn,
+                                               double logLx, double logLy, double logPy)
+{
+    const double logPx = pt_prior_warp(cfg, lane, xn);
     return pt_accept(cfg, (uint32_t)(r + cfg.ens_offset * cfg.n_temps), iter, cfg.temp[j], logLx, logLy, logPx, logPy);
 }
 
@@ -191,18 +199,22 @@ __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ 
 // (swap s consumes exactly block s of the ensemble's Philox stream), lane 0 then applies them in
 // order -- each decision depends on the permutation left by the previous one (mcmc_wrapper2.c:554-563).
 // The n_temps swap proposals of one ensemble by one warp (mcmc_wrapper2.c:554-563, ptmcmc :768-817).  s_idx (rung ->
-// slot) and s_logL (by slot) are staged by the caller; on return s_idx holds the new permutation (every lane may read
+// slot), s_logL (by slot) and s_dbeta (pt_stage_dbeta) are staged by the caller; on return s_idx holds the new permutation (every lane may read
 // it after the trailing __syncwarp) and the accepted count is returned to lane 0.
-__device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* s_b, double* s_beta,
-                                            double* s_dbeta, int* s_idx, const double* s_logL)
+// (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop of pt_swap_warp
+// touches shared memory only (the ladder lives in global memory: a dependent load per swap otherwise)
+__device__ __forceinline__ void pt_stage_dbeta(const PtConfig& cfg, int lane, int nlanes, double* s_dbeta)
 {
-    const int T = cfg.n_temps;
-    // (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop below
-    // touches shared memory only (the ladder lives in global memory: a dependent load per swap otherwise)
-    for (int s = lane; s + 1 < T; s += 32) {
+    for (int s = lane; s + 1 < cfg.n_temps; s += nlanes) {
         const double heat1 = cfg.temp[s + 1], heat2 = cfg.temp[s];
         s_dbeta[s] = (heat2 - heat1) / (heat2 * heat1);
     }
+}
+
+__device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* s_b, double* s_beta,
+                                            const double* s_dbeta, int* s_idx, const double* s_logL)
+{
+    const int T = cfg.n_temps;
     for (int s = lane; s < T; s += 32) {
         U4 c; c.x = 0x80000000u | (uint32_t)(ens_local + cfg.ens_offset); c.y = iter; c.z = 2u; c.w = (uint32_t)s;
         const U4 r = philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
     __shared__ int s_idx[kPtMaxTemps];
     __shared__ double s_logL[kPtMaxTemps];
     __shared__ double s_dbeta[kPtMaxTemps];
+    pt_stage_dbeta(cfg, lane, 32, s_dbeta);
     for (int s = lane; s < T; s += 32) {
         s_idx[s] = index[(size_t)ens * T + s];
         s_logL[s] = logLx[(size_t)ens * T + s];
@@ -388,9 +401,21 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
     const int n = lane < kPtNpars ? lane : kPtNpars - 1;
     for (int i = tid; i < kSinTabN; i += kEvalThreads) sm.sctab[i] = a.sctab[i];
     for (int s = tid; s < T; s += kEvalThreads) sm.s_idx[s] = a.index[(size_t)ens * T + s];
+    pt_stage_dbeta(cfg, tid, kEvalThreads, sm.s_dbeta);  // once per launch
     __syncthreads();
+    if (wid == 0) {  // prior of the state this walker starts from (every slot is some rung's: all get theirs)
+        const int c = ens * T + sm.s_idx[j];
+        const double lp = pt_prior_warp(cfg, lane, a.x[(size_t)c * kPtNpars + n]);
+        if (lane == 0) a.logPx[c] = lp;
+    }
     unsigned iter = a.d_iter[0];
     const double* hist = a.history + (size_t)r * cfg.npast * kPtNpars;
+#ifdef HB_PT_PROF
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
+#define PT_MARK(k) do { t1 = clock64(); tp[k] += t1 - t0; t0 = t1; } while (0)
+#else
+#define PT_MARK(k) ((void)0)
+#endif
     for (long it = 0; it < a.n_iters; it++, iter++) {
         const int slot = sm.s_idx[j], c = ens * T + slot;
         if (wid == 0) {  // proposal and its folded constants
@@ -409,16 +434,22 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
                 a.jump[c] = jt;
             }
             __syncwarp();
+            PT_MARK(0);
             PrologueT P;
             prologue_trans_warp(sm.y, a.ms, P, lane);
             if (lane == 0) prologue_assemble(sm.y, a.ms, P, sm.cc);
         }
         __syncthreads();
+        PT_MARK(1);
         const double logLy = pt_run_loglike(sm, a, tid);
+        PT_MARK(2);
         if (wid == 0) {  // accept / reject, history ring
             double xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);
             const double logLx = __ldcg(&a.logLx[c]);
-            const bool acc = pt_accept_warp(cfg, iter, r, j, lane, xn, logLx, logLy, sm.logPy);
+            // the prior of the current state is the prior its proposal had when it was accepted: kept per slot
+            // (same function of the same numbers as the stream-ordered kernel evaluates afresh: same bits)
+            const double logPx = __ldcg(&a.logPx[c]);
+            const bool acc = pt_accept(cfg, (uint32_t)(r + cfg.ens_offset * T), iter, cfg.temp[j], logLx, logLy, logPx, sm.logPy);
             if (acc) {
                 xn = sm.y[n];
                 if (lane < kPtNpars) a.x[(size_t)c * kPtNpars + lane] = xn;
@@ -426,10 +457,14 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
             if (lane == 0) {
                 a.logLy[c] = logLy;
                 pt_count_step(a.counters + (size_t)ens * 8, slot, sm.jump, acc);
-                if (acc) a.logLx[c] = logLy;
+                if (acc) {
+                    a.logLx[c] = logLy;
+                    a.logPx[c] = sm.logPy;
+                }
             }
             if (lane < kPtNpars) a.history[((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars + lane] = xn;
         }
+        PT_MARK(3);
         // ---- every walker's new state and log-likelihood are published: one grid-wide barrier per iteration ----
         __threadfence();
         __syncthreads();
@@ -440,6 +475,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
             __threadfence();
         }
         __syncthreads();
+        PT_MARK(4);
         if (wid == 0) {  // the ladder's swap proposals, replayed identically by each of its CTAs
             for (int s = lane; s < T; s += 32) sm.s_logL[s] = __ldcg(&a.logLx[(size_t)ens * T + s]);
             __syncwarp();
@@ -461,7 +497,13 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
             }
         }
         __syncthreads();
+        PT_MARK(5);
     }
+#ifdef HB_PT_PROF
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 25) && a.n_iters >= 1000)
+        printf("k_pt_run block %d: cycles per iteration  propose %lld  prologue %lld  loglike %lld  accept %lld  barrier %lld  swap %lld\n",
+               (int)blockIdx.x, tp[0] / a.n_iters, tp[1] / a.n_iters, tp[2] / a.n_iters, tp[3] / a.n_iters, tp[4] / a.n_iters, tp[5] / a.n_iters);
+#endif
     if (j == 0)
         for (int s = tid; s < T; s += kEvalThreads) a.index[(size_t)ens * T + s] = sm.s_idx[s];
     if (blockIdx.x == 0 && tid == 0) a.d_iter[0] = iter;

@@ -13,6 +13,7 @@ struct PtRunArgs {
     const PtConfig* cfg;
     unsigned* d_iter;
     double *x, *y, *logLx, *logLy, *logPy;
+    double* logPx;                   // [W] log prior of the current state, by slot (filled at launch, kept by the loop)
     int *jump, *index;
     double* history;
     unsigned long long* counters;
