@@ -381,8 +381,18 @@ __device__ inline void prologue_trans_warp(const double* __restrict__ p, const M
 }
 #endif
 
-// pure arithmetic: PrologueT -> ChainConst
-__device__ inline void prologue_assemble(const double* __restrict__ p, const MagSetup& ms, const PrologueT& T, ChainConst& cc)
+// pure arithmetic: PrologueT -> ChainConst, in four independent sections (each writes its own fields of cc from p and T
+// alone), so that a caller with idle warps can run them side by side (k_pt_run); prologue_assemble runs all four.
+// The same expressions in the same order whichever way they are called: the same bits.
+constexpr unsigned kAsmStarA = 1u;  // K0 K1 a0 a1 a2 b0 b1: beaming, reflection, the R^3 ellipsoidal terms
+constexpr unsigned kAsmStarB = 2u;  // q1 q3 r0 d2 r4: the R^4 and R^5 ellipsoidal terms
+constexpr unsigned kAsmOrbit = 4u;  // orbit, geometry, eclipse scale, normalisation, flags
+constexpr unsigned kAsmAux = 8u;    // Gaia chi^2 term, seed, diagnostics
+constexpr unsigned kAsmAll = 15u;
+
+template <unsigned kSections>
+__device__ __forceinline__ void prologue_assemble_sections(const double* __restrict__ p, const MagSetup& ms, const PrologueT& T,
+                                                           ChainConst& cc)
 {
     const double Pd = T.Pd;
     const double e = p[3], T0 = p[6];
@@ -395,132 +405,148 @@ __device__ inline void prologue_assemble(const double* __restrict__ p, const Mag
     // luminosity fractions (likelihood3.c:612-614)
     const double L1 = sq(R[0]) * sq(sq(Te[0])), L2 = sq(R[1]) * sq(sq(Te[1]));
     const double Nrm[2] = {L1 / (L1 + L2), L2 / (L1 + L2)};
-    // beaming alphas (likelihood3.c:617-624)
-    const double ab[2] = {dev_alpha_beam(T.lTe[0]) * T.xb[0], dev_alpha_beam(T.lTe[1]) * T.xb[1]};
     const double si = T.si, ci = T.ci;
     const double si2 = si * si, si3 = si2 * si, si4 = si2 * si2;
-
-    cc.e = e;
-    cc.T0s = T0 * kSecDay;
-    cc.Ps = Pd * kSecDay;
-    cc.rPs = __drcp_rn(cc.Ps);
-    cc.cw = T.cw;
-    cc.sw = T.sw;
-    cc.tab_min_m = (e > kTableAllE) ? kTableMinM : 0.0;
-    cc.cwq = T.cw * T.sq1me2;
-    cc.swq = T.sw * T.sq1me2;
-    cc.ci = ci;
-    cc.si = si;
-    cc.ar = T.a / kRsun;  // semi-major axis as traj() forms it (likelihood3.c:141-142)
-
     const double ppm = 1.e-6;
-    const double Pm13 = 1.0 / T.cP, Pm43 = Pm13 / Pd, Pm83 = Pm43 * Pm43, Pm103 = Pm83 * Pm13 * Pm13;
-    const double Prot = Pd * ((1 - e) * T.sq1me);
 
-    double K0 = 0, K1 = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, c1 = 0, c3 = 0, d0 = 0, d2 = 0, d4 = 0;
+    if constexpr ((kSections & (kAsmStarA | kAsmStarB)) != 0) {
+        // beaming alphas (likelihood3.c:617-624)
+        const double ab[2] = {dev_alpha_beam(T.lTe[0]) * T.xb[0], dev_alpha_beam(T.lTe[1]) * T.xb[1]};
+        const double Pm13 = 1.0 / T.cP, Pm43 = Pm13 / Pd, Pm83 = Pm43 * Pm43, Pm103 = Pm83 * Pm13 * Pm13;
+        const double Prot = Pd * ((1 - e) * T.sq1me);
+        double K0 = 0, K1 = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, c1 = 0, c3 = 0, d0 = 0, d2 = 0, d4 = 0;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const double Ma = M[k], Mb = M[1 - k];
-        const double Rs = R[k], Ro = R[1 - k];  // own radius (ellipsoidal), companion radius (reflection)
-        const double sgn = (k == 0) ? 1.0 : -1.0;  // star 2 sees omega0 + pi: odd harmonics flip
-        const double N = Nrm[k];
-        const double q = Mb / Ma;
-        const double Ma13 = T.cM[k], q13 = T.cq[k];                          // Ma^(1/3), (1+q)^(1/3)
-        const double iMa23 = 1.0 / (Ma13 * Ma13), iq23 = 1.0 / (q13 * q13);  // ^(-2/3)
-        // beaming, likelihood3.c:224-236 (pow(1+q, 2/3) == 1, quirk Q1)
-        const double B = -2830. * ab[k] * q * Ma13 * Pm13 * si / T.sq1me2 * ppm;
-        // ellipsoidal coefficient set, likelihood3.c:258-264
-        const double al11 = 15 * mu[k] * (2 + tau[k]) / (32 * (3 - mu[k]));
-        const double al21 = 3 * (15 + mu[k]) * (1 + tau[k]) / (20 * (3 - mu[k]));
-        const double al2b1 = 15 * (1 - mu[k]) * (3 + tau[k]) / (64 * (3 - mu[k]));
-        const double al01 = al21 / 9, al0b1 = 3 * al2b1 / 20, al31 = 5 * al11 / 3, al41 = 7 * al2b1 / 4;
-        const double R3 = Rs * Rs * Rs, R4 = R3 * Rs, R5 = R4 * Rs;
-        const double qq = q / (1 + q);
-        const double Mm53 = (iMa23 / Ma) * q * (iq23 / (1 + q)) * Pm103;        // Ma^-5/3 q (1+q)^-5/3 P^-10/3
-        const double Mm43 = (iMa23 * iMa23) * q * (iq23 * iq23) * Pm83;         // Ma^-4/3 q (1+q)^-4/3 P^-8/3
-        const double AM1 = 13435. * 2 * al01 * (2 - 3 * si2) / Ma / sq(Prot) * R3 * ppm;
-        const double AM2 = 13435. * 3 * al01 * (2 - 3 * si2) / Ma * qq / sq(Pd) * R3 * ppm;       // x beta^3
-        const double C21 = 13435. * al21 * si2 / Ma * qq / sq(Pd) * R3 * ppm;                     // x beta^3 cos2x
-        const double AM3 = 759. * al0b1 * (8 - 40 * si2 + 35 * si4) * Mm53 * R5 * ppm;            // x beta^5
-        const double S1 = 3194. * al11 * (4 * si - 5 * si3) * Mm43 * R4 * ppm;                    // x beta^4 sin x
-        const double C22 = 759. * al2b1 * (6 * si2 - 7 * si4) * Mm53 * R5 * ppm;                  // x beta^5 cos2x
-        const double S3 = 3194. * al31 * si3 * Mm43 * R4 * ppm;                                   // x beta^4 sin3x
-        const double C4 = 759. * al41 * si4 * Mm53 * R5 * ppm;                                    // x beta^5 cos4x
-        // reflection, likelihood3.c:322-337
-        const double Rf = 56514. * aref[k] * iq23 * iMa23 * Pm43 * sq(Ro) * ppm;  // x beta^2
-
-        K0 += N * (1 + AM1);
-        K1 += sgn * N * B;
-        a0 += N * Rf * (0.64 + 0.18 * si2);
-        a1 += -sgn * N * Rf * si;
-        a2 += -N * Rf * 0.18 * si2;
-        b0 += N * AM2;
-        b1 += N * C21;
-        c1 += sgn * N * S1;
-        c3 += sgn * N * S3;
-        d0 += N * AM3;
-        d2 += N * C22;
-        d4 += N * C4;
+        for (int k = 0; k < 2; k++) {
+            const double Ma = M[k], Mb = M[1 - k];
+            const double Rs = R[k], Ro = R[1 - k];  // own radius (ellipsoidal), companion radius (reflection)
+            const double sgn = (k == 0) ? 1.0 : -1.0;  // star 2 sees omega0 + pi: odd harmonics flip
+            const double N = Nrm[k];
+            const double q = Mb / Ma;
+            const double Ma13 = T.cM[k], q13 = T.cq[k];                          // Ma^(1/3), (1+q)^(1/3)
+            const double iMa23 = 1.0 / (Ma13 * Ma13), iq23 = 1.0 / (q13 * q13);  // ^(-2/3)
+            // ellipsoidal coefficient set, likelihood3.c:258-264
+            const double al11 = 15 * mu[k] * (2 + tau[k]) / (32 * (3 - mu[k]));
+            const double al21 = 3 * (15 + mu[k]) * (1 + tau[k]) / (20 * (3 - mu[k]));
+            const double al2b1 = 15 * (1 - mu[k]) * (3 + tau[k]) / (64 * (3 - mu[k]));
+            const double al01 = al21 / 9, al0b1 = 3 * al2b1 / 20, al31 = 5 * al11 / 3, al41 = 7 * al2b1 / 4;
+            const double R3 = Rs * Rs * Rs, R4 = R3 * Rs, R5 = R4 * Rs;
+            if constexpr ((kSections & kAsmStarA) != 0) {
+                // beaming, likelihood3.c:224-236 (pow(1+q, 2/3) == 1, quirk Q1)
+                const double B = -2830. * ab[k] * q * Ma13 * Pm13 * si / T.sq1me2 * ppm;
+                const double qq = q / (1 + q);
+                const double AM1 = 13435. * 2 * al01 * (2 - 3 * si2) / Ma / sq(Prot) * R3 * ppm;
+                const double AM2 = 13435. * 3 * al01 * (2 - 3 * si2) / Ma * qq / sq(Pd) * R3 * ppm;       // x beta^3
+                const double C21 = 13435. * al21 * si2 / Ma * qq / sq(Pd) * R3 * ppm;                     // x beta^3 cos2x
+                // reflection, likelihood3.c:322-337
+                const double Rf = 56514. * aref[k] * iq23 * iMa23 * Pm43 * sq(Ro) * ppm;  // x beta^2
+                K0 += N * (1 + AM1);
+                K1 += sgn * N * B;
+                a0 += N * Rf * (0.64 + 0.18 * si2);
+                a1 += -sgn * N * Rf * si;
+                a2 += -N * Rf * 0.18 * si2;
+                b0 += N * AM2;
+                b1 += N * C21;
+            }
+            if constexpr ((kSections & kAsmStarB) != 0) {
+                const double Mm53 = (iMa23 / Ma) * q * (iq23 / (1 + q)) * Pm103;        // Ma^-5/3 q (1+q)^-5/3 P^-10/3
+                const double Mm43 = (iMa23 * iMa23) * q * (iq23 * iq23) * Pm83;         // Ma^-4/3 q (1+q)^-4/3 P^-8/3
+                const double AM3 = 759. * al0b1 * (8 - 40 * si2 + 35 * si4) * Mm53 * R5 * ppm;            // x beta^5
+                const double S1 = 3194. * al11 * (4 * si - 5 * si3) * Mm43 * R4 * ppm;                    // x beta^4 sin x
+                const double C22 = 759. * al2b1 * (6 * si2 - 7 * si4) * Mm53 * R5 * ppm;                  // x beta^5 cos2x
+                const double S3 = 3194. * al31 * si3 * Mm43 * R4 * ppm;                                   // x beta^4 sin3x
+                const double C4 = 759. * al41 * si4 * Mm53 * R5 * ppm;                                    // x beta^5 cos4x
+                c1 += sgn * N * S1;
+                c3 += sgn * N * S3;
+                d0 += N * AM3;
+                d2 += N * C22;
+                d4 += N * C4;
+            }
+        }
+        if constexpr ((kSections & kAsmStarA) != 0) {
+            cc.K0 = K0; cc.K1 = K1; cc.a0 = a0; cc.a1 = a1; cc.a2 = a2; cc.b0 = b0; cc.b1 = b1;
+        }
+        if constexpr ((kSections & kAsmStarB) != 0) {
+            cc.q1 = c1 + c3; cc.q3 = 2.0 * c3; cc.r0 = d0 - d4; cc.d2 = d2; cc.r4 = 2.0 * d4;
+        }
     }
-    cc.K0 = K0; cc.K1 = K1; cc.a0 = a0; cc.a1 = a1; cc.a2 = a2; cc.b0 = b0; cc.b1 = b1;
-    cc.q1 = c1 + c3; cc.q3 = 2.0 * c3; cc.r0 = d0 - d4; cc.d2 = d2; cc.r4 = 2.0 * d4;
 
-    cc.Rb = fmax(R[0], R[1]);
-    cc.Rs = fmin(R[0], R[1]);
-    cc.si2 = 0.5 * si * si;
-    cc.ci2 = ci * ci + 0.5 * si * si;
-    {
-        const double lim = (cc.Rb + cc.Rs) / cc.ar;
-        cc.thr = lim * lim * (1.0 + 1e-9);
+    if constexpr ((kSections & kAsmOrbit) != 0) {
+        cc.e = e;
+        cc.T0s = T0 * kSecDay;
+        cc.Ps = Pd * kSecDay;
+        cc.rPs = __drcp_rn(cc.Ps);
+        cc.cw = T.cw;
+        cc.sw = T.sw;
+        cc.tab_min_m = (e > kTableAllE) ? kTableMinM : 0.0;
+        cc.cwq = T.cw * T.sq1me2;
+        cc.swq = T.sw * T.sq1me2;
+        cc.ci = ci;
+        cc.si = si;
+        const double ar = T.a / kRsun;  // semi-major axis as traj() forms it (likelihood3.c:141-142)
+        cc.ar = ar;
+        const double Rb = fmax(R[0], R[1]), Rsm = fmin(R[0], R[1]);
+        cc.Rb = Rb;
+        cc.Rs = Rsm;
+        cc.si2 = 0.5 * si * si;
+        cc.ci2 = ci * ci + 0.5 * si * si;
+        {
+            const double lim = (Rb + Rsm) / ar;
+            cc.thr = lim * lim * (1.0 + 1e-9);
+        }
+        cc.ecl1 = Nrm[0] / (kPi * sq(R[0]));
+        cc.ecl2 = Nrm[1] / (kPi * sq(R[1]));
+        cc.blend = blending;
+        cc.ft = ft;
+        // Roche overflow (likelihood3.c:945-974)
+        int roche;
+        {
+            const double r1 = R[0] * kRsun / (T.sep * (1 - e));
+            const double r2 = R[1] * kRsun / (T.sep * (1 - e));
+            const double q23a = T.eq[0] * T.eq[0], q23b = T.eq[1] * T.eq[1];
+            const double RL1 = 0.49 * q23a / (0.6 * q23a + T.elog[0]);
+            const double RL2 = 0.49 * q23b / (0.6 * q23b + T.elog[1]);
+            roche = ((RL1 < r1) || (RL2 < r2)) ? 1 : 0;
+        }
+        // e >= 1 (reachable, quirk Q4) or NaN e: the reference's template is NaN at every sample
+        const int nan_model = !(e < 1.0) ? 1 : 0;
+        // d >= r_min |cos i| with r_min = a (1 - |e|): chains that can never eclipse skip the per-sample test
+        const int no_eclipse = (ar * (1 - fabs(e)) * fabs(ci) >= (Rb + Rsm) * (1.0 + 1e-9)) ? 1 : 0;
+        cc.flag = (double)(roche | (nan_model << 1) | (no_eclipse << 2));
     }
-    cc.ecl1 = Nrm[0] / (kPi * sq(R[0]));
-    cc.ecl2 = Nrm[1] / (kPi * sq(R[1]));
-    cc.blend = blending;
-    cc.ft = ft;
 
-    // Gaia magnitude / colour chi^2 terms (likelihood3.c:780-789, 834-860)
-    const double Bm = -2.5 * T.lf[0] - 48.6, Vm = -2.5 * T.lf[1] - 48.6, Gm = -2.5 * T.lf[2] - 48.6, Tm = -2.5 * T.lf[3] - 48.6;
-    const double mags[4] = {Gm, Bm - Vm, Vm - Gm, Gm - Tm};
-    double extra = 0.;
-    if (ms.use_gmag) {
-        double r = (mags[0] - ms.mag_data[1]) / ms.magerr[0];
-        extra += r * r;
-    }
-    if (ms.use_color) {
-        for (int i = 1; i < 4; i++) {
-            double r = (mags[i] - ms.mag_data[i + 1]) / ms.magerr[i];
+    if constexpr ((kSections & kAsmAux) != 0) {
+        // Gaia magnitude / colour chi^2 terms (likelihood3.c:780-789, 834-860)
+        const double Bm = -2.5 * T.lf[0] - 48.6, Vm = -2.5 * T.lf[1] - 48.6, Gm = -2.5 * T.lf[2] - 48.6, Tm = -2.5 * T.lf[3] - 48.6;
+        const double mags[4] = {Gm, Bm - Vm, Vm - Gm, Gm - Tm};
+        double extra = 0.;
+        if (ms.use_gmag) {
+            double r = (mags[0] - ms.mag_data[1]) / ms.magerr[0];
             extra += r * r;
         }
-    }
-    cc.chi2_extra = extra;
-
-    // Roche overflow (likelihood3.c:945-974)
-    int roche;
-    {
-        const double r1 = R[0] * kRsun / (T.sep * (1 - e));
-        const double r2 = R[1] * kRsun / (T.sep * (1 - e));
-        const double q23a = T.eq[0] * T.eq[0], q23b = T.eq[1] * T.eq[1];
-        const double RL1 = 0.49 * q23a / (0.6 * q23a + T.elog[0]);
-        const double RL2 = 0.49 * q23b / (0.6 * q23b + T.elog[1]);
-        roche = ((RL1 < r1) || (RL2 < r2)) ? 1 : 0;
-    }
-    // e >= 1 (reachable, quirk Q4) or NaN e: the reference's template is NaN at every sample
-    const int nan_model = !(e < 1.0) ? 1 : 0;
-    // d >= r_min |cos i| with r_min = a (1 - |e|): chains that can never eclipse skip the per-sample test
-    const int no_eclipse = (cc.ar * (1 - fabs(e)) * fabs(ci) >= (cc.Rb + cc.Rs) * (1.0 + 1e-9)) ? 1 : 0;
-    cc.flag = (double)(roche | (nan_model << 1) | (no_eclipse << 2));
-    {
-        uint32_t h = 0x811c9dc5u;
-        for (int i = 0; i < NPARS; i++) {
-            const unsigned long long b = (unsigned long long)__double_as_longlong(p[i]);
-            h = (h ^ (uint32_t)b) * 0x01000193u;
-            h = (h ^ (uint32_t)(b >> 32)) * 0x01000193u;
+        if (ms.use_color) {
+            for (int i = 1; i < 4; i++) {
+                double r = (mags[i] - ms.mag_data[i + 1]) / ms.magerr[i];
+                extra += r * r;
+            }
         }
-        cc.seed = (double)h;
+        cc.chi2_extra = extra;
+        {
+            uint32_t h = 0x811c9dc5u;
+            for (int i = 0; i < NPARS; i++) {
+                const unsigned long long b = (unsigned long long)__double_as_longlong(p[i]);
+                h = (h ^ (uint32_t)b) * 0x01000193u;
+                h = (h ^ (uint32_t)(b >> 32)) * 0x01000193u;
+            }
+            cc.seed = (double)h;
+        }
+        cc.info[0] = R[0]; cc.info[1] = R[1]; cc.info[2] = Te[0]; cc.info[3] = Te[1];
+        cc.info[4] = mags[0]; cc.info[5] = mags[1]; cc.info[6] = mags[2]; cc.info[7] = mags[3];
     }
+}
 
-    cc.info[0] = R[0]; cc.info[1] = R[1]; cc.info[2] = Te[0]; cc.info[3] = Te[1];
-    cc.info[4] = mags[0]; cc.info[5] = mags[1]; cc.info[6] = mags[2]; cc.info[7] = mags[3];
+__device__ inline void prologue_assemble(const double* __restrict__ p, const MagSetup& ms, const PrologueT& T, ChainConst& cc)
+{
+    prologue_assemble_sections<kAsmAll>(p, ms, T, cc);
 }
 
 // one thread per chain (host emulation, small helpers)

@@ -46,46 +46,69 @@ __device__ __forceinline__ double warp_ordered_sum(double term, int count)
     return acc;  // identical on every lane
 }
 
-// One walker's proposal by its warp (lane n owns parameter n): rung r (global rung id = r + ens_offset T for the random
-// streams), temperature rung j, this lane's component xn of the current state, the rung's history ring.  Returns this lane's component of y;
-// lane 0 also gets the prior term and the jump type.  mcmc_wrapper2.c:390-481.
-__device__ __forceinline__ double pt_propose_warp(const PtConfig& cfg, unsigned iter, int r, int j, int lane,
-                                                  const double xn, const double* __restrict__ hist,
-                                                  double& logP_out, int& jump_out)
+// The random part of one walker's proposal at iteration `iter`: everything that depends on the rung's Philox stream
+// alone, not on the walker's state -- so a sampler that keeps its walkers resident (k_pt_run) draws iteration i + 1
+// on an idle warp while iteration i is being evaluated.  Lane n holds the normals of parameter n; the scalars are
+// the same on every lane.  mcmc_wrapper2.c:390-436, :1062-1140.
+struct PtDraws {
+    double jscale;   // 10^(-6 + 6 alpha)
+    double z_gauss;  // this lane's normal of the Gaussian jump (meaningful when !de)
+    double z_de;     // this lane's normal of the scaled DE jump (meaningful when de && scaled)
+    int de, a, b, scaled;
+    uint32_t d_fallback;  // first draw of the Gaussian jump a degenerate DE proposal falls back to
+};
+
+__device__ __forceinline__ PtDraws pt_propose_draws(const PtConfig& cfg, unsigned iter, int r, int lane)
 {
-    const int T = cfg.n_temps;
     const int n = lane < kPtNpars ? lane : kPtNpars - 1;  // idle lanes shadow the last parameter
     const unsigned long long seed = cfg.seed;
-    const uint32_t id = (uint32_t)(r + cfg.ens_offset * T);  // global rung id
-    const double temp = cfg.temp[j];
-
+    const uint32_t id = (uint32_t)(r + cfg.ens_offset * cfg.n_temps);  // global rung id
+    PtDraws w;
     const double alpha = pt_draw(seed, id, iter, 0u, 0u);
-    const double jscale = pow(10., -6. + 6. * alpha);
-    const bool de = (pt_draw(seed, id, iter, 0u, 1u) < 0.5) && ((long long)iter > (long long)cfg.npast);
-    const double sqtemp = sqrt(temp);
-    double yn;
-    int jump_type = 1;
-    if (!de) {
-        yn = xn + pt_normal(seed, id, iter, 0u, 2u, n) * cfg.sigma[n] * sqtemp * jscale;
+    w.jscale = pow(10., -6. + 6. * alpha);
+    w.de = (pt_draw(seed, id, iter, 0u, 1u) < 0.5) && ((long long)iter > (long long)cfg.npast);
+    w.a = 0; w.b = 0; w.scaled = 0; w.d_fallback = 0u;
+    w.z_gauss = 0.; w.z_de = 0.;
+    if (!w.de) {
+        w.z_gauss = pt_normal(seed, id, iter, 0u, 2u, n);
     } else {
         uint32_t d = 2u;
-        int a = 0, b;
-        if (!cfg.quirks) a = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast);
-        do { b = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast); } while (b == a);
-        const bool scaled = pt_draw(seed, id, iter, 0u, d++) < 0.9;
+        if (!cfg.quirks) w.a = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast);
+        do { w.b = (int)(pt_draw(seed, id, iter, 0u, d++) * cfg.npast); } while (w.b == w.a);
+        w.scaled = pt_draw(seed, id, iter, 0u, d++) < 0.9;
+        if (w.scaled) w.z_de = pt_normal(seed, id, iter, 0u, d, n);
+        w.d_fallback = d + (w.scaled ? 22u : 0u);
+    }
+    return w;
+}
+
+// The state-dependent part: rung r at temperature rung j, this lane's component xn of the current state, the rung's
+// history ring, the draws of this iteration.  Returns this lane's component of y; lane 0 also gets the prior term and
+// the jump type.  mcmc_wrapper2.c:390-481.
+__device__ __forceinline__ double pt_propose_apply(const PtConfig& cfg, unsigned iter, int r, int j, int lane, const PtDraws& w,
+                                                   const double xn, const double* __restrict__ hist, double& logP_out,
+                                                   int& jump_out)
+{
+    const int n = lane < kPtNpars ? lane : kPtNpars - 1;
+    const double sqtemp = sqrt(cfg.temp[j]);
+    double yn;
+    int jump_type = 1;
+    if (!w.de) {
+        yn = xn + w.z_gauss * cfg.sigma[n] * sqtemp * w.jscale;
+    } else {
         const double eps_fac = cfg.quirks ? (pt_gaussian(0., 0., 1.e-4) - 0.5) : 0.0;
-        HB_CHK(a, cfg.npast, 30);
-        HB_CHK(b, cfg.npast, 30);
-        double dx = hist[b * kPtNpars + n] - hist[a * kPtNpars + n];
+        HB_CHK(w.a, cfg.npast, 30);
+        HB_CHK(w.b, cfg.npast, 30);
+        double dx = hist[w.b * kPtNpars + n] - hist[w.a * kPtNpars + n];
         const double eps = dx * eps_fac;
-        if (scaled) dx *= pt_normal(seed, id, iter, 0u, d, n) * cfg.gamma;
+        if (w.scaled) dx *= w.z_de * cfg.gamma;
         dx += eps;
         yn = xn + dx;
         const double dx_mag = warp_ordered_sum((xn - yn) * (xn - yn), kPtNpars);
         jump_type = 2;
         if (dx_mag < 1e-6) {  // mcmc_wrapper2.c:432-436; the Gaussian draws continue the stream
-            const uint32_t d2 = d + (scaled ? 22u : 0u);
-            yn = xn + pt_normal(seed, id, iter, 0u, d2, n) * cfg.sigma[n] * sqtemp * jscale;
+            const uint32_t id = (uint32_t)(r + cfg.ens_offset * cfg.n_temps);
+            yn = xn + pt_normal(cfg.seed, id, iter, 0u, w.d_fallback, n) * cfg.sigma[n] * sqtemp * w.jscale;
             jump_type = 1;
         }
     }
@@ -105,6 +128,15 @@ __device__ __forceinline__ double pt_propose_warp(const PtConfig& cfg, unsigned 
     logP_out = warp_ordered_sum(term, kPtNpars);
     jump_out = jump_type;
     return yn;
+}
+
+// One walker's proposal by its warp (lane n owns parameter n): draws, then their application to the state.
+__device__ __forceinline__ double pt_propose_warp(const PtConfig& cfg, unsigned iter, int r, int j, int lane,
+                                                  const double xn, const double* __restrict__ hist,
+                                                  double& logP_out, int& jump_out)
+{
+    const PtDraws w = pt_propose_draws(cfg, iter, r, lane);
+    return pt_propose_apply(cfg, iter, r, j, lane, w, xn, hist, logP_out, jump_out);
 }
 
 __global__ void __launch_bounds__(128) k_pt_propose(const PtConfig* __restrict__ cfgp, const unsigned* __restrict__ iter_ptr,
@@ -195,13 +227,12 @@ __global__ void __launch_bounds__(128) k_pt_accept(const PtConfig* __restrict__ 
     if (lane < kPtNpars) history[((size_t)r * cfg.npast + (iter % (unsigned)cfg.npast)) * kPtNpars + lane] = xn;
 }
 
-// One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
-// (swap s consumes exactly block s of the ensemble's Philox stream), lane 0 then applies them in
-// order -- each decision depends on the permutation left by the previous one (mcmc_wrapper2.c:554-563).
-// The n_temps swap proposals of one ensemble by one warp (mcmc_wrapper2.c:554-563, ptmcmc :768-817).  s_idx (rung ->
-// slot), s_logL (by slot) and s_dbeta (pt_stage_dbeta) are staged by the caller; on return s_idx holds the new permutation (every lane may read
-// it after the trailing __syncwarp) and the accepted count is returned to lane 0.
-// (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop of pt_swap_warp
+// The n_temps swap proposals of one ensemble by one warp (mcmc_wrapper2.c:554-563, ptmcmc :768-817): the lanes draw
+// the (pair, beta) of all proposals in parallel (swap s consumes exactly block s of the ensemble's Philox stream,
+// pt_swap_draws), lane 0 then applies them in order (pt_swap_apply).  s_idx (rung -> slot), s_logL (by slot) and
+// s_dbeta (pt_stage_dbeta) are staged by the caller; on return s_idx holds the new permutation (every lane may read it
+// after the trailing __syncwarp) and the accepted count is returned to lane 0.
+// pt_stage_dbeta: (heat_b - heat_{b+1}) / (heat_b heat_{b+1}) of every adjacent pair, staged so that the serial loop
 // touches shared memory only (the ladder lives in global memory: a dependent load per swap otherwise)
 __device__ __forceinline__ void pt_stage_dbeta(const PtConfig& cfg, int lane, int nlanes, double* s_dbeta)
 {
@@ -211,8 +242,10 @@ __device__ __forceinline__ void pt_stage_dbeta(const PtConfig& cfg, int lane, in
     }
 }
 
-__device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* s_b, double* s_beta,
-                                            const double* s_dbeta, int* s_idx, const double* s_logL)
+// The draws of the n_temps swap proposals of one ensemble at iteration `iter` (state-independent: a resident sampler
+// takes them on an idle warp ahead of time): pair b and log of the acceptance draw per proposal.
+__device__ __forceinline__ void pt_swap_draws(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* __restrict__ s_b,
+                                              double* __restrict__ s_beta)
 {
     const int T = cfg.n_temps;
     for (int s = lane; s < T; s += 32) {
@@ -225,22 +258,53 @@ __device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, 
         s_b[s] = b;
         s_beta[s] = log(u1);  // exp(x) >= beta  <=>  x >= log(beta): the log is taken here, in parallel
     }
+}
+
+// The proposals applied in order by lane 0 -- each decision depends on the permutation left by the previous one.
+// s_pl is work space: the log-likelihood BY RUNG POSITION, carried along with the permutation, so that a step is one
+// level of independent shared-memory loads, three FP64 instructions and the stores (the chain of 50 dependent steps
+// is the whole cost of this phase).  Same operands, same operations as logL[idx[b]] - logL[idx[a]]: same decisions.
+__device__ __forceinline__ int pt_swap_apply(const PtConfig& cfg, int lane, const int* __restrict__ s_b,
+                                             const double* __restrict__ s_beta, const double* __restrict__ s_dbeta,
+                                             int* __restrict__ s_idx, const double* __restrict__ s_logL,
+                                             double* __restrict__ s_pl)
+{
+    const int T = cfg.n_temps;
+    for (int s = lane; s < T; s += 32) s_pl[s] = s_logL[s_idx[s]];
     __syncwarp();
     int nacc = 0;
-    if (lane == 0) {
-        for (int s = 0; s < T && T > 1; s++) {
-            const int b = s_b[s], a = b + 1;
-            const int olda = s_idx[a], oldb = s_idx[b];
-            const double lalpha = (s_logL[oldb] - s_logL[olda]) * s_dbeta[b];
-            if (lalpha >= s_beta[s]) {
-                s_idx[a] = oldb;
-                s_idx[b] = olda;
-                nacc++;
+    if (lane == 0 && T > 1) {
+        int b_next = s_b[0];
+        double beta_next = s_beta[0];
+        for (int s = 0; s < T; s++) {
+            // (the next proposal's pair and draw are requested a step ahead: they do not depend on the permutation)
+            const int b = b_next, a = b + 1;
+            const double beta = beta_next;
+            if (s + 1 < T) {
+                b_next = s_b[s + 1];
+                beta_next = s_beta[s + 1];
             }
+            const double Lb = s_pl[b], La = s_pl[a];
+            const int ib = s_idx[b], ia = s_idx[a];
+            const double lalpha = (Lb - La) * s_dbeta[b];
+            const bool acc = lalpha >= beta;
+            s_pl[b] = acc ? La : Lb;
+            s_pl[a] = acc ? Lb : La;
+            s_idx[b] = acc ? ia : ib;
+            s_idx[a] = acc ? ib : ia;
+            nacc += acc;
         }
     }
     __syncwarp();
     return nacc;
+}
+
+__device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* s_b, double* s_beta,
+                                            const double* s_dbeta, int* s_idx, const double* s_logL, double* s_pl)
+{
+    pt_swap_draws(cfg, iter, ens_local, lane, s_b, s_beta);
+    __syncwarp();
+    return pt_swap_apply(cfg, lane, s_b, s_beta, s_dbeta, s_idx, s_logL, s_pl);
 }
 
 // One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
@@ -261,13 +325,14 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
     __shared__ int s_idx[kPtMaxTemps];
     __shared__ double s_logL[kPtMaxTemps];
     __shared__ double s_dbeta[kPtMaxTemps];
+    __shared__ double s_pl[kPtMaxTemps];
     pt_stage_dbeta(cfg, lane, 32, s_dbeta);
     for (int s = lane; s < T; s += 32) {
         s_idx[s] = index[(size_t)ens * T + s];
         s_logL[s] = logLx[(size_t)ens * T + s];
     }
     __syncwarp();
-    const int nacc = pt_swap_warp(cfg, iter, ens, lane, s_b, s_beta, s_dbeta, s_idx, s_logL);
+    const int nacc = pt_swap_warp(cfg, iter, ens, lane, s_b, s_beta, s_dbeta, s_idx, s_logL, s_pl);
     if (lane == 0) {
         unsigned long long* cnt = counters + (size_t)ens * 8;
         cnt[5] += (unsigned long long)nacc;
@@ -337,7 +402,8 @@ struct PtRunShared {
     int jump;
     int s_b[kPtMaxTemps];
     int s_idx[kPtMaxTemps];
-    double s_beta[kPtMaxTemps], s_dbeta[kPtMaxTemps], s_logL[kPtMaxTemps];
+    double s_beta[kPtMaxTemps], s_dbeta[kPtMaxTemps], s_logL[kPtMaxTemps], s_pl[kPtMaxTemps];
+    PtDraws draws[2][32];  // the proposal's random part per lane: [iteration parity] (drawn one iteration ahead)
     double2 sctab[kSinTabN];
     uint64_t keys[kPtRunMaxPoints];  // template keys of the proposal's light curve
     uint64_t bufA[kPtRunMaxPoints], bufB[kPtRunMaxPoints];  // survivor buffers of the select
@@ -347,8 +413,9 @@ size_t pt_run_smem_bytes() { return sizeof(PtRunShared); }
 
 // likelihood of the chain whose constants sit in sm.cc (the small-light-curve path of k_chain_eval: template stored,
 // exact order statistic, chi^2 summed in the reference's own form, likelihood3.c:681-685,809-873)
-__device__ __forceinline__ double pt_run_loglike(PtRunShared& sm, const PtRunArgs& a, int tid)
+__device__ __forceinline__ double pt_run_loglike(PtRunShared& sm, const PtRunArgs& a, int tid, long long* prof = nullptr)
 {
+    [[maybe_unused]] long long q0 = clock64();
     const ChainConst& cc = sm.cc;
     const int lane = tid & 31, wid = tid >> 5;
     const int N = a.N;
@@ -359,26 +426,65 @@ __device__ __forceinline__ double pt_run_loglike(PtRunShared& sm, const PtRunArg
     if (tid == 0 && a.evaluated != nullptr) atomicAdd(a.evaluated, 1ull);
     int nanflag = 0;
     const int n_tiles = (N + kEvalThreads - 1) / kEvalThreads;
-    for (int tile = 0; tile < n_tiles; tile++) {
-        const int i = tile * kEvalThreads + tid;
-        const double ts[1] = {a.tsec[i]};  // (padded to whole tiles)
-        double u[1];
-        raw_flux<1, true, true, false>(cc, nullptr, sm.sctab, ts, u);
-        const bool valid = i < N;
-        nanflag |= valid & (u[0] != u[0]);
-        if (valid) sm.keys[i] = dkey(u[0]);
-    }
-    if (__syncthreads_or(nanflag)) return qnan;
     int krank = (N % 2 == 0) ? N / 2 : N / 2 + 1;  // likelihood3.c:97-101 (quirk Q3)
     if (krank > N - 1) krank = N - 1;
-    const SelectBuf bufs[2] = {{sm.bufA, kPtRunMaxPoints}, {sm.bufB, kPtRunMaxPoints}};
-    const double med = dunkey(block_select_key<kEvalThreads>(sm.keys, N, krank, sm.ctl, bufs, 2, (uint32_t)cc.seed ^ 0x9e3779b9u));
-    double S0 = 0.;
     const double blend = cc.blend, ft = cc.ft;
-    for (int i = tid; i < N; i += kEvalThreads) {
-        const double2 v = a.fw[i];
-        const double r = (finish_template(dunkey(sm.keys[i]), med, blend, ft) - v.x) * v.y;
-        S0 = fma(r, r, S0);
+    double S0 = 0.;
+    if (n_tiles <= 2) {
+        // the reference's folded light curves (163-763 points; here up to 512): two samples per thread, template
+        // and data in registers, the whole template sorted in one go (block_sort2)
+        double2 v[2];
+        uint64_t key[2];
+#pragma unroll
+        for (int tile = 0; tile < 2; tile++) {
+            const int i = tile * kEvalThreads + tid;
+            key[tile] = ~0ull;  // padding sorts above every number
+            v[tile] = make_double2(0., 0.);
+            if (tile < n_tiles) {  // (uniform)
+                const double ts[1] = {a.tsec[i]};  // (padded to whole tiles)
+                v[tile] = a.fw[i];                 // (likewise, weight 0) -- asked for ahead of the sort that hides it
+                double u[1];
+                raw_flux<1, true, true, false>(cc, nullptr, sm.sctab, ts, u);
+                const bool valid = i < N;
+                nanflag |= valid & (u[0] != u[0]);
+                if (valid) key[tile] = dkey(u[0]);
+            }
+        }
+        if (__syncthreads_or(nanflag)) return qnan;
+        if (prof) { long long q1 = clock64(); prof[0] += q1 - q0; q0 = q1; }
+        const KeyPair srt = block_sort2<kEvalThreads>(key[0], key[1], sm.bufA);
+        if (tid == (krank & (kEvalThreads - 1))) sm.ctl.result = krank < kEvalThreads ? srt.a : srt.b;
+        __syncthreads();
+        const double med = dunkey(sm.ctl.result);
+        if (prof) { long long q1 = clock64(); prof[1] += q1 - q0; q0 = q1; }
+#pragma unroll
+        for (int tile = 0; tile < 2; tile++) {  // in the order of the strided loop below
+            const int i = tile * kEvalThreads + tid;
+            if (i < N) {
+                const double r = (finish_template(dunkey(key[tile]), med, blend, ft) - v[tile].x) * v[tile].y;
+                S0 = fma(r, r, S0);
+            }
+        }
+    } else {
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int i = tile * kEvalThreads + tid;
+            const double ts[1] = {a.tsec[i]};  // (padded to whole tiles)
+            double u[1];
+            raw_flux<1, true, true, false>(cc, nullptr, sm.sctab, ts, u);
+            const bool valid = i < N;
+            nanflag |= valid & (u[0] != u[0]);
+            if (valid) sm.keys[i] = dkey(u[0]);
+        }
+        if (__syncthreads_or(nanflag)) return qnan;
+        if (prof) { long long q1 = clock64(); prof[0] += q1 - q0; q0 = q1; }
+        const SelectBuf bufs[2] = {{sm.bufA, kPtRunMaxPoints}, {sm.bufB, kPtRunMaxPoints}};
+        const double med = dunkey(block_select_key<kEvalThreads>(sm.keys, N, krank, sm.ctl, bufs, 2, (uint32_t)cc.seed ^ 0x9e3779b9u));
+        if (prof) { long long q1 = clock64(); prof[1] += q1 - q0; q0 = q1; }
+        for (int i = tid; i < N; i += kEvalThreads) {
+            const double2 v = a.fw[i];
+            const double r = (finish_template(dunkey(sm.keys[i]), med, blend, ft) - v.x) * v.y;
+            S0 = fma(r, r, S0);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) S0 += __shfl_xor_sync(0xffffffffu, S0, o);
@@ -387,6 +493,7 @@ __device__ __forceinline__ double pt_run_loglike(PtRunShared& sm, const PtRunArg
     double t0 = 0.;
     for (int i = 0; i < kEvalThreads / 32; i++) t0 += sm.red[i];
     __syncthreads();
+    if (prof) { long long q1 = clock64(); prof[2] += q1 - q0; prof[3] += 1; }
     return -0.5 * (t0 + cc.chi2_extra);
 }
 
@@ -411,18 +518,32 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
     unsigned iter = a.d_iter[0];
     const double* hist = a.history + (size_t)r * cfg.npast * kPtNpars;
 #ifdef HB_PT_PROF
-    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
-#define PT_MARK(k) do { t1 = clock64(); tp[k] += t1 - t0; t0 = t1; } while (0)
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
+    int nbig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long lprof[4] = {0, 0, 0, 0};
+#define PT_MARK(k) do { t1 = clock64(); tp[k] += t1 - t0; if (t1 - t0 > tq[k]) tq[k] = t1 - t0; if (k == 2 && t1 - t0 > 12000) nbig[2]++; if (k == 0 && t1 - t0 > 10000) nbig[0]++; if (k == 6 && t1 - t0 > 15000) nbig[6]++; t0 = t1; } while (0)
 #else
 #define PT_MARK(k) ((void)0)
 #endif
+    // The random numbers of an iteration do not depend on the walkers' states: while warp 0 works through the
+    // dependent chain of iteration i (proposal -> constants), warp 1 draws the swap proposals of iteration i and warp 2
+    // the proposal of iteration i + 1 (the barriers of the iteration publish both).
+    if (wid == 2) sm.draws[iter & 1u][lane] = pt_propose_draws(cfg, iter, r, lane);
+    __syncthreads();
     for (long it = 0; it < a.n_iters; it++, iter++) {
         const int slot = sm.s_idx[j], c = ens * T + slot;
-        if (wid == 0) {  // proposal and its folded constants
-            const double xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);  // (written by another CTA when the slot changed hands)
+        double xn = 0., logLx = 0., logPx = 0.;  // (warp 0) the walker's current state: read once, ahead of their use
+        if (wid == 1) pt_swap_draws(cfg, iter, ens, lane, sm.s_b, sm.s_beta);
+        if (wid == 2) sm.draws[(iter + 1u) & 1u][lane] = pt_propose_draws(cfg, iter + 1u, r, lane);
+        if (wid == 0) {  // proposal
+            xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);  // (written by another CTA when the slot changed hands)
+            logLx = __ldcg(&a.logLx[c]);
+            // the prior of the current state is the prior its proposal had when it was accepted: kept per slot
+            // (same function of the same numbers as the stream-ordered kernel evaluates afresh: same bits)
+            logPx = __ldcg(&a.logPx[c]);
             double lp;
             int jt;
-            const double yn = pt_propose_warp(cfg, iter, r, j, lane, xn, hist, lp, jt);
+            const double yn = pt_propose_apply(cfg, iter, r, j, lane, sm.draws[iter & 1u][lane], xn, hist, lp, jt);
             if (lane < kPtNpars) {
                 sm.y[lane] = yn;
                 a.y[(size_t)c * kPtNpars + lane] = yn;
@@ -433,22 +554,31 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
                 a.logPy[c] = lp;
                 a.jump[c] = jt;
             }
-            __syncwarp();
-            PT_MARK(0);
+        }
+        __syncthreads();
+        PT_MARK(0);
+        // the proposal's folded constants (chain prologue): four warps each take the libm levels (lanes = calls; the
+        // same calls on every warp, side by side on the four sub-partitions) and then one section of the assembly
+        if (wid < 4) {
             PrologueT P;
             prologue_trans_warp(sm.y, a.ms, P, lane);
-            if (lane == 0) prologue_assemble(sm.y, a.ms, P, sm.cc);
+            PT_MARK(6);
+            if (lane == 0) {
+                if (wid == 0) prologue_assemble_sections<kAsmStarA>(sm.y, a.ms, P, sm.cc);
+                else if (wid == 1) prologue_assemble_sections<kAsmStarB>(sm.y, a.ms, P, sm.cc);
+                else if (wid == 2) prologue_assemble_sections<kAsmOrbit>(sm.y, a.ms, P, sm.cc);
+                else prologue_assemble_sections<kAsmAux>(sm.y, a.ms, P, sm.cc);
+            }
         }
         __syncthreads();
         PT_MARK(1);
+#ifdef HB_PT_PROF
+        const double logLy = pt_run_loglike(sm, a, tid, lprof);
+#else
         const double logLy = pt_run_loglike(sm, a, tid);
+#endif
         PT_MARK(2);
         if (wid == 0) {  // accept / reject, history ring
-            double xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);
-            const double logLx = __ldcg(&a.logLx[c]);
-            // the prior of the current state is the prior its proposal had when it was accepted: kept per slot
-            // (same function of the same numbers as the stream-ordered kernel evaluates afresh: same bits)
-            const double logPx = __ldcg(&a.logPx[c]);
             const bool acc = pt_accept(cfg, (uint32_t)(r + cfg.ens_offset * T), iter, cfg.temp[j], logLx, logLy, logPx, sm.logPy);
             if (acc) {
                 xn = sm.y[n];
@@ -479,7 +609,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
         if (wid == 0) {  // the ladder's swap proposals, replayed identically by each of its CTAs
             for (int s = lane; s < T; s += 32) sm.s_logL[s] = __ldcg(&a.logLx[(size_t)ens * T + s]);
             __syncwarp();
-            const int nacc = pt_swap_warp(cfg, iter, ens, lane, sm.s_b, sm.s_beta, sm.s_dbeta, sm.s_idx, sm.s_logL);
+            const int nacc = pt_swap_apply(cfg, lane, sm.s_b, sm.s_beta, sm.s_dbeta, sm.s_idx, sm.s_logL, sm.s_pl);
             if (j == 0) {  // rung 0's CTA keeps the ladder's books: counters and the MAP (mcmc_wrapper2.c:565-572)
                 if (lane == 0) {
                     unsigned long long* cnt = a.counters + (size_t)ens * 8;
@@ -500,9 +630,12 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
         PT_MARK(5);
     }
 #ifdef HB_PT_PROF
-    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 25) && a.n_iters >= 1000)
-        printf("k_pt_run block %d: cycles per iteration  propose %lld  prologue %lld  loglike %lld  accept %lld  barrier %lld  swap %lld\n",
-               (int)blockIdx.x, tp[0] / a.n_iters, tp[1] / a.n_iters, tp[2] / a.n_iters, tp[3] / a.n_iters, tp[4] / a.n_iters, tp[5] / a.n_iters);
+    if (tid == 0 && a.n_iters >= 1000)
+        printf("k_pt_run block %d: cycles per iteration  propose %lld  prologue: libm levels %lld + assembly %lld  loglike %lld  accept %lld  barrier %lld  swap %lld | max: propose %lld libm %lld asm %lld loglike %lld accept %lld | share of iterations: propose > 10k %.3f  libm > 15k %.3f  loglike > 12k %.3f\n",
+               (int)blockIdx.x, tp[0] / a.n_iters, tp[6] / a.n_iters, tp[1] / a.n_iters, tp[2] / a.n_iters, tp[3] / a.n_iters, tp[4] / a.n_iters, tp[5] / a.n_iters,
+               tq[0], tq[6], tq[1], tq[2], tq[3], (double)nbig[0] / a.n_iters, (double)nbig[6] / a.n_iters, (double)nbig[2] / a.n_iters);
+    if (tid == 0 && a.n_iters >= 1000 && lprof[3] > 0)
+        printf("   block %d evaluated %lld times: model %lld  select %lld  chi2 %lld cycles\n", (int)blockIdx.x, lprof[3], lprof[0] / lprof[3], lprof[1] / lprof[3], lprof[2] / lprof[3]);
 #endif
     if (j == 0)
         for (int s = tid; s < T; s += kEvalThreads) a.index[(size_t)ens * T + s] = sm.s_idx[s];

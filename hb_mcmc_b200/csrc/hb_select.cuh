@@ -134,6 +134,56 @@ __device__ __noinline__ uint64_t block_sort(uint64_t key, uint64_t* xch)
     return key;
 }
 
+// Bitonic sort of TWO keys per thread (elements tid and kThreads + tid of a 2 kThreads array): afterwards thread t
+// gets sorted[t] and sorted[kThreads + t] back.  Both halves go through the network of block_sort side by
+// side (the second half descending at the last level), then one in-thread exchange and a merge: a light curve of up
+// to 2 kThreads points is sorted whole in ~3 k cycles, where sampling rounds take two full sorts and a compaction.
+// xch2 holds 2 kThreads keys.
+struct KeyPair { uint64_t a, b; };
+template <int kThreads>
+__device__ __noinline__ KeyPair block_sort2(uint64_t a, uint64_t b, uint64_t* xch2)
+{
+    static_assert((kThreads & (kThreads - 1)) == 0, "block size must be a power of two");
+    const int tid = threadIdx.x;
+    auto exchange = [&](uint64_t key, int j, uint64_t* xch) -> uint64_t {  // the key of thread tid ^ j (j < 32: shuffles)
+        const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)key, j);
+        const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
+        return ((uint64_t)hi << 32) | lo;
+    };
+#pragma unroll
+    for (int k = 2; k <= 2 * kThreads; k <<= 1) {
+        // element index of a is tid, of b kThreads + tid: the direction bit of b differs from a's at k == kThreads only
+        const bool desc_a = (k < 2 * kThreads) && ((tid & k) != 0);
+        const bool desc_b = (k < kThreads) ? desc_a : (k == kThreads);
+        if (k == 2 * kThreads) {  // partner distance kThreads: in the thread (ascending)
+            const uint64_t mn = a < b ? a : b, mx = a < b ? b : a;
+            a = mn;
+            b = mx;
+        }
+#pragma unroll
+        for (int j = (k == 2 * kThreads ? kThreads : k) >> 1; j > 0; j >>= 1) {
+            uint64_t oa, ob;
+            if (j >= 32) {
+                xch2[tid] = a;
+                xch2[kThreads + tid] = b;
+                __syncthreads();
+                HB_CHK(tid ^ j, kThreads, 21);
+                oa = xch2[tid ^ j];
+                ob = xch2[kThreads + (tid ^ j)];
+                __syncthreads();
+            } else {
+                oa = exchange(a, j, xch2);
+                ob = exchange(b, j, xch2);
+            }
+            const bool upper = (tid & j) != 0;
+            // the lower partner of an ascending pair keeps the minimum
+            a = ((oa < a) == (desc_a == upper)) ? oa : a;
+            b = ((ob < b) == (desc_b == upper)) ? ob : b;
+        }
+    }
+    return KeyPair{a, b};
+}
+
 // Bracket ranks (in a sorted sample of S) around the target quantile q = (k + 0.5) / n.
 __device__ __forceinline__ void bracket_ranks(int S, int n, int k, float z, int& r_lo, int& r_hi, int& r_mid)
 {

@@ -50,7 +50,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB
+    path = path or os.environ.get("HB_B200_LIB") or _build.LIB  # (HB_B200_LIB: a -D variant of the library, for tools/)
     if not os.path.exists(path):
         try:
             _build.build_lib()
