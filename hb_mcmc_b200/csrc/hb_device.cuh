@@ -314,7 +314,7 @@ __device__ inline void prologue_trans_seq(const double* __restrict__ p, const Ma
 #ifndef HB_HOST_EMUL
 // warp fill: the lanes of one warp call each libm routine ONCE, on different arguments, and
 // exchange the results by shuffle -- five dependent levels instead of ~50 sequential calls.
-__device__ inline void prologue_trans_warp(const double* __restrict__ p, const MagSetup& ms, PrologueT& T, int lane)
+__device__ __forceinline__ void prologue_trans_warp(const double* __restrict__ p, const MagSetup& ms, PrologueT& T, int lane)
 {
     const unsigned full = 0xffffffffu;
     const double e = p[3];

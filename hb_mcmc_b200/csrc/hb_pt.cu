@@ -243,9 +243,12 @@ __device__ __forceinline__ void pt_stage_dbeta(const PtConfig& cfg, int lane, in
 }
 
 // The draws of the n_temps swap proposals of one ensemble at iteration `iter` (state-independent: a resident sampler
-// takes them on an idle warp ahead of time): pair b and log of the acceptance draw per proposal.
-__device__ __forceinline__ void pt_swap_draws(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* __restrict__ s_b,
-                                              double* __restrict__ s_beta)
+// takes them on an idle warp ahead of time): pair b and log of the acceptance draw per proposal, and the BATCHES of the
+// proposal sequence -- maximal runs of consecutive proposals whose pairs {b, b + 1} are disjoint.  Proposals of a run
+// commute, so pt_swap_apply decides a whole run at once, one lane per proposal (~5 proposals per run at 50 rungs).
+// s_batch[i] .. s_batch[i + 1] - 1 are the proposals of run i; returns the number of runs (uniform).
+__device__ __forceinline__ int pt_swap_draws(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* __restrict__ s_b,
+                                             double* __restrict__ s_beta, int* __restrict__ s_batch)
 {
     const int T = cfg.n_temps;
     for (int s = lane; s < T; s += 32) {
@@ -258,53 +261,73 @@ __device__ __forceinline__ void pt_swap_draws(const PtConfig& cfg, unsigned iter
         s_b[s] = b;
         s_beta[s] = log(u1);  // exp(x) >= beta  <=>  x >= log(beta): the log is taken here, in parallel
     }
+    __syncwarp();
+    int nb = 0;
+    if (lane == 0 && T > 1) {
+        unsigned long long occ[2] = {0ull, 0ull};  // rung positions taken by the current run (kPtMaxTemps = 128 bits)
+        int len = 0;
+        for (int s = 0; s < T; s++) {
+            const int b = s_b[s];
+            const unsigned long long m0 = (b < 64) ? (3ull << b) : 0ull;                                // bits b, b + 1
+            const unsigned long long m1 = (b >= 64) ? (3ull << (b - 64)) : ((b == 63) ? 1ull : 0ull);
+            if (len == 32 || ((occ[0] & m0) | (occ[1] & m1)) != 0ull || s == 0) {
+                s_batch[nb++] = s;
+                occ[0] = occ[1] = 0ull;
+                len = 0;
+            }
+            occ[0] |= m0;
+            occ[1] |= m1;
+            len++;
+        }
+        s_batch[nb] = T;
+    }
+    return __shfl_sync(0xffffffffu, nb, 0);
 }
 
-// The proposals applied in order by lane 0 -- each decision depends on the permutation left by the previous one.
-// s_pl is work space: the log-likelihood BY RUNG POSITION, carried along with the permutation, so that a step is one
-// level of independent shared-memory loads, three FP64 instructions and the stores (the chain of 50 dependent steps
-// is the whole cost of this phase).  Same operands, same operations as logL[idx[b]] - logL[idx[a]]: same decisions.
-__device__ __forceinline__ int pt_swap_apply(const PtConfig& cfg, int lane, const int* __restrict__ s_b,
-                                             const double* __restrict__ s_beta, const double* __restrict__ s_dbeta,
-                                             int* __restrict__ s_idx, const double* __restrict__ s_logL,
-                                             double* __restrict__ s_pl)
+// The proposals applied run by run (a lane per proposal of the run), the runs in order -- each decision depends on the
+// permutation left by the previous runs.  s_pl is work space: the log-likelihood BY RUNG POSITION, carried along with
+// the permutation, so that a step is one level of independent shared-memory loads, three FP64 instructions and the
+// stores.  Same operands, same operations as logL[idx[b]] - logL[idx[a]] taken one proposal at a time: same decisions.
+__device__ __forceinline__ int pt_swap_apply(const PtConfig& cfg, int lane, int n_batch, const int* __restrict__ s_batch,
+                                             const int* __restrict__ s_b, const double* __restrict__ s_beta,
+                                             const double* __restrict__ s_dbeta, int* __restrict__ s_idx,
+                                             const double* __restrict__ s_logL, double* __restrict__ s_pl)
 {
     const int T = cfg.n_temps;
     for (int s = lane; s < T; s += 32) s_pl[s] = s_logL[s_idx[s]];
     __syncwarp();
     int nacc = 0;
-    if (lane == 0 && T > 1) {
-        int b_next = s_b[0];
-        double beta_next = s_beta[0];
-        for (int s = 0; s < T; s++) {
-            // (the next proposal's pair and draw are requested a step ahead: they do not depend on the permutation)
-            const int b = b_next, a = b + 1;
-            const double beta = beta_next;
-            if (s + 1 < T) {
-                b_next = s_b[s + 1];
-                beta_next = s_beta[s + 1];
-            }
+    int s0 = n_batch > 0 ? s_batch[0] : 0;
+    for (int i = 0; i < n_batch; i++) {
+        const int s1 = s_batch[i + 1];
+        const int s = s0 + lane;
+        bool acc = false;
+        if (s < s1) {
+            const int b = s_b[s], a = b + 1;
             const double Lb = s_pl[b], La = s_pl[a];
             const int ib = s_idx[b], ia = s_idx[a];
             const double lalpha = (Lb - La) * s_dbeta[b];
-            const bool acc = lalpha >= beta;
-            s_pl[b] = acc ? La : Lb;
-            s_pl[a] = acc ? Lb : La;
-            s_idx[b] = acc ? ia : ib;
-            s_idx[a] = acc ? ib : ia;
-            nacc += acc;
+            acc = lalpha >= s_beta[s];
+            if (acc) {
+                s_pl[b] = La;
+                s_pl[a] = Lb;
+                s_idx[b] = ia;
+                s_idx[a] = ib;
+            }
         }
+        nacc += __popc(__ballot_sync(0xffffffffu, acc));
+        __syncwarp();
+        s0 = s1;
     }
-    __syncwarp();
     return nacc;
 }
 
 __device__ __forceinline__ int pt_swap_warp(const PtConfig& cfg, unsigned iter, int ens_local, int lane, int* s_b, double* s_beta,
-                                            const double* s_dbeta, int* s_idx, const double* s_logL, double* s_pl)
+                                            const double* s_dbeta, int* s_idx, const double* s_logL, double* s_pl, int* s_batch)
 {
-    pt_swap_draws(cfg, iter, ens_local, lane, s_b, s_beta);
+    const int nb = pt_swap_draws(cfg, iter, ens_local, lane, s_b, s_beta, s_batch);
     __syncwarp();
-    return pt_swap_apply(cfg, lane, s_b, s_beta, s_dbeta, s_idx, s_logL, s_pl);
+    return pt_swap_apply(cfg, lane, nb, s_batch, s_b, s_beta, s_dbeta, s_idx, s_logL, s_pl);
 }
 
 // One warp per ensemble: the lanes draw the (pair, beta) of all n_temps swap proposals in parallel
@@ -326,13 +349,14 @@ __global__ void __launch_bounds__(32) k_pt_swap(const PtConfig* __restrict__ cfg
     __shared__ double s_logL[kPtMaxTemps];
     __shared__ double s_dbeta[kPtMaxTemps];
     __shared__ double s_pl[kPtMaxTemps];
+    __shared__ int s_batch[kPtMaxTemps + 1];
     pt_stage_dbeta(cfg, lane, 32, s_dbeta);
     for (int s = lane; s < T; s += 32) {
         s_idx[s] = index[(size_t)ens * T + s];
         s_logL[s] = logLx[(size_t)ens * T + s];
     }
     __syncwarp();
-    const int nacc = pt_swap_warp(cfg, iter, ens, lane, s_b, s_beta, s_dbeta, s_idx, s_logL, s_pl);
+    const int nacc = pt_swap_warp(cfg, iter, ens, lane, s_b, s_beta, s_dbeta, s_idx, s_logL, s_pl, s_batch);
     if (lane == 0) {
         unsigned long long* cnt = counters + (size_t)ens * 8;
         cnt[5] += (unsigned long long)nacc;
@@ -401,6 +425,8 @@ struct PtRunShared {
     double logPy, logLy;
     int jump;
     int s_b[kPtMaxTemps];
+    int s_batch[kPtMaxTemps + 1];  // runs of commuting swap proposals (pt_swap_draws)
+    int n_batch;
     int s_idx[kPtMaxTemps];
     double s_beta[kPtMaxTemps], s_dbeta[kPtMaxTemps], s_logL[kPtMaxTemps], s_pl[kPtMaxTemps];
     PtDraws draws[2][32];  // the proposal's random part per lane: [iteration parity] (drawn one iteration ahead)
@@ -533,7 +559,10 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
     for (long it = 0; it < a.n_iters; it++, iter++) {
         const int slot = sm.s_idx[j], c = ens * T + slot;
         double xn = 0., logLx = 0., logPx = 0.;  // (warp 0) the walker's current state: read once, ahead of their use
-        if (wid == 1) pt_swap_draws(cfg, iter, ens, lane, sm.s_b, sm.s_beta);
+        if (wid == 1) {
+            const int nb = pt_swap_draws(cfg, iter, ens, lane, sm.s_b, sm.s_beta, sm.s_batch);
+            if (lane == 0) sm.n_batch = nb;
+        }
         if (wid == 2) sm.draws[(iter + 1u) & 1u][lane] = pt_propose_draws(cfg, iter + 1u, r, lane);
         if (wid == 0) {  // proposal
             xn = __ldcg(&a.x[(size_t)c * kPtNpars + n]);  // (written by another CTA when the slot changed hands)
@@ -609,7 +638,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
         if (wid == 0) {  // the ladder's swap proposals, replayed identically by each of its CTAs
             for (int s = lane; s < T; s += 32) sm.s_logL[s] = __ldcg(&a.logLx[(size_t)ens * T + s]);
             __syncwarp();
-            const int nacc = pt_swap_apply(cfg, lane, sm.s_b, sm.s_beta, sm.s_dbeta, sm.s_idx, sm.s_logL, sm.s_pl);
+            const int nacc = pt_swap_apply(cfg, lane, sm.n_batch, sm.s_batch, sm.s_b, sm.s_beta, sm.s_dbeta, sm.s_idx, sm.s_logL, sm.s_pl);
             if (j == 0) {  // rung 0's CTA keeps the ladder's books: counters and the MAP (mcmc_wrapper2.c:565-572)
                 if (lane == 0) {
                     unsigned long long* cnt = a.counters + (size_t)ens * 8;

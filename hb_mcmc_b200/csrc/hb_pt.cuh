@@ -143,7 +143,8 @@ HB_HD void pt_prior_of(int i, double& mean, double& sig)
 // mcmc_wrapper2.c:1175-1178 with SQRT_2PI of mcmc_wrapper2.h:10
 HB_HD double pt_gaussian(double x, double mean, double sigma)
 {
-    return (1 / sigma / 2.5066282746) * exp(-pow((x - mean) / sigma, 2.) / 2.);
+    const double z = (x - mean) / sigma;  // (z * z is the correctly rounded pow(z, 2.) of the reference's expression)
+    return (1 / sigma / 2.5066282746) * exp(-(z * z) / 2.);
 }
 
 // Boundary handling of parameter i (mcmc_wrapper2.c:440-467): reflect at sides with mode 1, wrap
