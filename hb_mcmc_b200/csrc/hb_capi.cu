@@ -187,7 +187,7 @@ int ensure_scratch(hb_ctx* ctx, long n_points)
 // shorter tail gives back.)
 int choose_parts(const hb_ctx* ctx, long n_chains, long N, bool hot)
 {
-    if (!hot || N <= kCandA / 2) return 1;
+    if (!hot || N <= kCandA / 2 || n_chains > 2 * kEvalThreads) return 1;  // (the kernel lists a shared batch's chains in 2 x threads slots)
     const int nseg = eval_segments(N);
     int p = 1;
     while (2 * p <= nseg && 2 * p <= ctx->max_parts && n_chains * 2 * p <= ctx->grid) p *= 2;  // (p need not divide nseg)
@@ -249,8 +249,10 @@ int run_eval(hb_ctx* ctx, const double* d_params, long n, const double* d_t, con
     a.nseg = eval_segments(N);
     a.seg_shift = eval_seg_shift(N);
     a.nparts = choose_parts(ctx, n, N, d_fw != nullptr && d_lc == nullptr);
+    a.max_parts = ctx->max_parts;
     const long n_work = n * a.nparts;
-    const int grid = (int)std::min<long>(ctx->grid, n_work);
+    // (a shared batch of several chains gets the whole grid: the kernel hands the CTAs of chains it skips to the others)
+    const int grid = (a.nparts > 1 && n > 1) ? ctx->grid : (int)std::min<long>(ctx->grid, n_work);
     CK(launch_prologue(d_params, (int)n, ctx->ms, ctx->d_cc, ctx->d_counter, grid, ctx->stream));
     if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     CK(launch_chain_eval(a, grid, ctx->stream));

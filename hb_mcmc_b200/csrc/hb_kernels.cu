@@ -161,14 +161,16 @@ __device__ __forceinline__ int median_rank(int N)
 // Between chains a CTA sits at barriers while its latency-bound neighbours on the SM cannot speed up, so
 // the per-chain phases count in full: clock64 gives table 3 k, pre-sample 6-8 k, pass 120-220 k, select
 // 8-13 k, final 2 k cycles at N = 20 000.
-template <int kThreads>
+// kShared: the launch hands every chain to several CTAs (a batch smaller than the grid); compiled apart so that the
+// pass of a batch that fills the grid carries none of the hand-over code.
+template <int kThreads, bool kShared>
 __global__ void __launch_bounds__(kThreads, kEvalCtasPerSm)
 k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* __restrict__ tsec,
              const double2* __restrict__ fw, int N, uint64_t* __restrict__ scratch,
              size_t region_stride, size_t key_stride, double* __restrict__ logL, double* __restrict__ lc_out,
              int* __restrict__ counter, float bracket_sigma, const double2* __restrict__ sctab_g, int hot_hi_limit,
              double sum_w2, unsigned long long* __restrict__ evaluated, ChainSync* __restrict__ sync_all, int nparts,
-             int nseg, int seg_shift)
+             int nseg, int seg_shift, int max_parts)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -177,7 +179,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int krank = median_rank(N);
     const int n_tiles = (N + kTile - 1) / kTile;
-    const int n_work = n_chains * nparts;
+    int n_work = n_chains * nparts;
     static_assert((kTile & (kTile - 1)) == 0, "segment ends are read off the bits of the sample index");
     const int seg_bits = ((1 << seg_shift) - 1) * kTile;  // the tile-in-segment bits of a sample index
     for (int i = tid; i < kSinTabN; i += kThreads) sm.sctab[i] = sctab_g[i];  // published by the first barrier below
@@ -195,6 +197,56 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     const uint32_t tile_bytes = kTile * sizeof(double);
 #endif
 
+    // ---- shared batches: only the chains that will be evaluated get CTAs ----
+    // A batch smaller than the grid (nparts > 1) is a ladder of a sampler more often than not, and the hot rungs of a
+    // ladder propose Roche-overflowing or unphysical states about every other step (quirk Q13: no evaluation).  Every
+    // CTA reads the flags of the batch, numbers the chains that need the model (in chain order: no atomics, nothing to
+    // reset) and spreads the grid over THOSE: each gets gridDim.x / n_eval CTAs instead of gridDim.x / n_chains.  The
+    // skipped chains' results are written here.  A chain's value does not depend on its number of parts (see above).
+    int shared_chain = 0;
+    if (kShared && n_chains > 1) {
+        static_assert(kThreads * sizeof(uint64_t) >= 2 * kThreads * sizeof(int), "the sort's exchange buffer holds the list");
+        int* const s_list = reinterpret_cast<int*>(sm.ctl.xch);  // [2 kThreads] >= n_chains (the host side sees to that)
+        int* const s_wcnt = sm.ctl.ired;                          // [2][kThreads / 32]
+        bool ev[2];
+        unsigned below[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int c = h * kThreads + tid;
+            ev[h] = false;
+            if (c < n_chains) {
+                const int f = (int)cc_all[c].flag;
+                ev[h] = (f & 3) == 0;  // neither Roche overflow nor a model that is NaN by construction
+                if (!ev[h] && logL != nullptr && c % (int)gridDim.x == (int)blockIdx.x)
+                    logL[c] = (f & 1) ? -0.5 * kBig : qnan;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ev[h]);
+            below[h] = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) s_wcnt[h * (kThreads / 32) + (tid >> 5)] = __popc(m);
+        }
+        __syncthreads();
+        int n_eval = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int base = n_eval;  // chains of the lower half come first: chain order
+            for (int w = 0; w < kThreads / 32; w++) {
+                const int cw = s_wcnt[h * (kThreads / 32) + w];
+                if (w < (tid >> 5)) base += cw;
+                n_eval += cw;
+            }
+            if (ev[h]) s_list[base + (int)below[h]] = h * kThreads + tid;
+        }
+        __syncthreads();
+        if (n_eval == 0) return;
+        const int p_room = min(min(nseg, max_parts), (int)gridDim.x / n_eval);  // (>= the host's nparts: n_eval <= n_chains)
+        const int spp = (nseg + p_room - 1) / p_room;
+        nparts = (nseg + spp - 1) / spp;  // parts that get at least one segment
+        n_work = n_eval * nparts;
+        if ((int)blockIdx.x >= n_work) return;
+        shared_chain = s_list[(int)blockIdx.x / nparts];
+        __syncthreads();  // (the list lives in the sort's exchange buffer)
+    }
+
     for (int round = 0;; round++) {
         // dynamic scheduler: chains differ in cost (eclipse fraction, Roche early-out).  The first work item of
         // a CTA is its own index (the counter starts at gridDim.x), so a batch that fits one wave -- a PT step
@@ -207,10 +259,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         const int work = round == 0 ? (int)blockIdx.x : s_work;
         if (work >= n_work) break;
         // (a shared chain's work item is always the block index: chains x parts never exceeds the grid)
-        const int chain = nparts == 1 ? work : (int)blockIdx.x / nparts;
-        const int part = nparts == 1 ? 0 : (int)blockIdx.x % nparts;
+        const int chain = !kShared ? work : (n_chains > 1 ? shared_chain : 0);
+        const int part = !kShared ? 0 : (int)blockIdx.x % nparts;
         // scratch region: the CTA's own, or -- when several CTAs share a chain -- the chain's
-        uint64_t* tmpl = scratch + (size_t)(nparts == 1 ? (int)blockIdx.x : chain) * region_stride;
+        uint64_t* tmpl = scratch + (size_t)(!kShared ? (int)blockIdx.x : chain) * region_stride;
         uint64_t* gbufB = tmpl + key_stride;
         uint64_t* gbufC = tmpl + 2 * key_stride;
         double* partials = reinterpret_cast<double*>(tmpl + 3 * key_stride);  // [nseg][2][kThreads]
@@ -260,7 +312,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             int r_lo, r_hi, r_mid;
             bracket_ranks(kThreads, N, krank, bracket_sigma, r_lo, r_hi, r_mid);
             const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)kThreads);
-            if (nparts > 1 || (int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // survivors go to global scratch
+            if (kShared || (int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // survivors go to global scratch
                 cand = gbufB;
                 cand_cap = (int)key_stride;
                 cand_small = false;
@@ -297,7 +349,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         constexpr int V = kPointsPerThread;
         static_assert(V == 1, "the segment bookkeeping of the pass is written for one sample per thread and iteration");
         int hi_acc = 0;  // largest sincos argument exponent of the hot pass (checked once, below)
-        ChainSync* const sync = sync_all + (nparts == 1 ? 0 : chain);
+        ChainSync* const sync = sync_all + (!kShared ? 0 : chain);
         auto model_pass = [&](auto store_tag, auto data_tag, auto part_tag) {
         constexpr bool kStore = decltype(store_tag)::value;
         constexpr bool kHot = !kStore;  // the logL-only pass defers the sincos range check to the end of the chain
@@ -480,13 +532,13 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             c_in = sm.ctl.cnt;
             load_sums(false);
         } else {
-            if (nparts == 1) model_pass(std::false_type{}, std::true_type{}, std::false_type{});
+            if constexpr (!kShared) model_pass(std::false_type{}, std::true_type{}, std::false_type{});
             else model_pass(std::false_type{}, std::true_type{}, std::true_type{});
             // a Newton iterate left the table sincos' range somewhere in this chain (e -> 1 only): the sums are
             // not trustworthy; the chain is evaluated again with the per-sample check and the library fallback
             int redo = __syncthreads_or(hi_acc > hot_hi_limit);
             c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
-            if (nparts > 1) {
+            if constexpr (kShared) {
                 // hand-over: this part's counts and flags to the chain's sync words; the last part to arrive
                 // finishes the chain.  Every thread's stores (segment sums, candidate keys) are fenced before the
                 // barrier in front of thread 0's ticket.
@@ -522,7 +574,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 c_in = sm.ctl.cnt;
                 load_sums(false);
             } else {
-                load_sums(nparts > 1);
+                load_sums(kShared);
             }
         }
         const int any_nan = __syncthreads_or(nanflag);  // (also the barrier between reading cnt and the select's reset of it)
@@ -790,7 +842,10 @@ cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, Cha
 
 cudaError_t configure_eval()
 {
-    return cudaFuncSetAttribute(k_chain_eval<kEvalThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_chain_eval<kEvalThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(EvalShared));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_chain_eval<kEvalThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(EvalShared));
 }
 
@@ -814,9 +869,14 @@ cudaError_t launch_chain_eval(const EvalArgs& a, int grid, cudaStream_t s)
 {
     if (a.n_chains <= 0) return cudaSuccess;
     // *counter was set to this grid by the k_prologue launch in front of this one
-    k_chain_eval<kEvalThreads><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(
-        a.cc, a.n_chains, a.tsec, a.fw, a.N, a.scratch, a.region_stride, a.key_stride, a.logL, a.lc_out, a.counter, a.bracket_sigma,
-        a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, a.nparts, a.nseg, a.seg_shift);
+    if (a.nparts > 1)
+        k_chain_eval<kEvalThreads, true><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(
+            a.cc, a.n_chains, a.tsec, a.fw, a.N, a.scratch, a.region_stride, a.key_stride, a.logL, a.lc_out, a.counter, a.bracket_sigma,
+            a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, a.nparts, a.nseg, a.seg_shift, a.max_parts);
+    else
+        k_chain_eval<kEvalThreads, false><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(
+            a.cc, a.n_chains, a.tsec, a.fw, a.N, a.scratch, a.region_stride, a.key_stride, a.logL, a.lc_out, a.counter, a.bracket_sigma,
+            a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, 1, a.nseg, a.seg_shift, a.max_parts);
     return cudaGetLastError();
 }
 

@@ -59,7 +59,9 @@ struct EvalArgs {
     const double2* sctab;
     float bracket_sigma;
     int hot_hi_limit;
-    int nparts;            // CTAs per chain (each takes a contiguous run of segments)
+    int nparts;            // CTAs per chain (each takes a contiguous run of segments); > 1: the kernel raises it to what
+                           // the chains that are really evaluated leave room for
+    int max_parts;         // ... up to this many
     int nseg;              // eval_segments(N)
     int seg_shift;         // eval_seg_shift(N): a segment is 2^seg_shift tiles
 };

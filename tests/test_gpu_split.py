@@ -88,5 +88,14 @@ def test_nan_roche_and_counts_in_shared_chains(ctx, golden, restore):
     n_eval = ctx.evaluated_chains(reset=True)
     early = int(np.sum(ctx.roche_overflow(P) == 1) + np.sum(~(P[:, 3] < 1.0) & (ctx.roche_overflow(P) == 0)))
     assert n_eval == len(P) - early, (n_eval, early)
+    # a shared batch spreads the grid over the chains it really evaluates (the kernel lists them from their flags, in
+    # two half-lists of 256): early-outs scattered through a batch that reaches into the second half
+    big = np.vstack([P] * 25)[:290][np.random.default_rng(5).permutation(290)]
+    ctx.set_max_parts(1)
+    base_big = ctx.loglikelihood(big)
+    for parts in (2, 64):
+        ctx.set_max_parts(parts)
+        assert np.array_equal(ctx.loglikelihood(big), base_big, equal_nan=True), parts
+        assert np.array_equal(ctx.loglikelihood(big[:37]), base_big[:37], equal_nan=True), parts
     with pytest.raises(Exception):
         ctx.set_max_parts(3)

@@ -2,7 +2,7 @@
 (backward branch) that holds the 16-byte {flux, 1/sigma} load is listed with its size and opcode histogram, and
 written in full to <out>.loopK.sass.  Cold blocks inside the span (eclipse, append, fmod repair, further Newton
 steps) are part of the count -- compare builds with each other, not with the executed counts of an ncu capture.
-    python tools/hotloop.py hb_mcmc_b200/csrc/libhb_b200.so [/tmp/out]"""
+    python tools/hotloop.py hb_mcmc_b200/csrc/libhb_b200.so [/tmp/out [shared]]"""
 import collections
 import re
 import subprocess
@@ -10,6 +10,8 @@ import sys
 
 path = sys.argv[1]
 out = sys.argv[2] if len(sys.argv) > 2 else "/tmp/hotloop"
+# the instantiation: batches that fill the grid (default), or "shared" for the one whose chains are shared by CTAs
+WHICH = "k_chain_evalILi256ELb1" if len(sys.argv) > 3 and sys.argv[3] == "shared" else "k_chain_evalILi256ELb0"
 sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
 fn = None
 ins = []  # (addr, text) of k_chain_eval<256>
@@ -18,7 +20,7 @@ for line in sass.splitlines():
     if m:
         fn = m.group(1)
         continue
-    if fn and "k_chain_evalILi256" in fn:
+    if fn and WHICH in fn:
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
         if m:
             ins.append((int(m.group(1), 16), m.group(2).strip()))
