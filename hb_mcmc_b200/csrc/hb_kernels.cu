@@ -21,6 +21,10 @@ namespace hb {
 // ---------------------------------------------------------------------------
 // One warp per chain: the lanes share out the ~50 libm calls (prologue_trans_warp), lane 0 assembles
 // and the warp stores the 47 doubles of ChainConst together.
+#ifndef HB_PROLOGUE_SMALL_MAX
+#define HB_PROLOGUE_SMALL_MAX 148  // chains up to which a batch gets four warps per chain (k_prologue_small; measured: a gain up to ~150 chains, a loss at 500)
+#endif
+constexpr int kPrologueSmallMax = HB_PROLOGUE_SMALL_MAX;
 #ifndef HB_PROLOGUE_BLOCKS
 #define HB_PROLOGUE_BLOCKS 4  // 128 registers: 16 warps per SM; fewer (184 registers) leaves 4096 chains waiting in 3.5 waves
 #endif
@@ -43,6 +47,33 @@ __global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const doub
     const double* src = reinterpret_cast<const double*>(&cc);
     double* dst = reinterpret_cast<double*>(out + c);
     for (int i = lane; i < (int)(sizeof(ChainConst) / sizeof(double)); i += 32) dst[i] = src[i];
+}
+
+// The same for a batch that leaves the machine idle anyway (a ladder, the calls of one OpenMP team, C1): a CTA of
+// four warps per chain.  Every warp takes the libm levels for itself -- the same calls side by side on the four
+// sub-partitions -- and then one of the four sections of the assembly (~45 IEEE divisions in all), so the chain's
+// assembly takes a third of the time it takes one lane (measured: a 50-rung ladder's call 1-3 us shorter).  Same
+// expressions in the same order: same bits.
+__global__ void __launch_bounds__(128) k_prologue_small(const double* __restrict__ params, int n, MagSetup ms,
+                                                        ChainConst* __restrict__ out, int* __restrict__ eval_counter, int eval_grid)
+{
+    if (eval_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *eval_counter = eval_grid;
+    const int c = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= n) return;
+    __shared__ ChainConst cc;
+    const double* p = params + (size_t)c * NPARS;
+    PrologueT T;
+    prologue_trans_warp(p, ms, T, lane);
+    if (lane == 0) {
+        if (wid == 0) prologue_assemble_sections<kAsmStarA>(p, ms, T, cc);
+        else if (wid == 1) prologue_assemble_sections<kAsmStarB>(p, ms, T, cc);
+        else if (wid == 2) prologue_assemble_sections<kAsmOrbit>(p, ms, T, cc);
+        else prologue_assemble_sections<kAsmAux>(p, ms, T, cc);
+    }
+    __syncthreads();
+    const double* src = reinterpret_cast<const double*>(&cc);
+    double* dst = reinterpret_cast<double*>(out + c);
+    for (int i = threadIdx.x; i < (int)(sizeof(ChainConst) / sizeof(double)); i += 128) dst[i] = src[i];
 }
 
 // ---- staging of the data stream ---------------------------------------------------------------
@@ -836,7 +867,8 @@ cudaError_t launch_prologue(const double* params, int n, const MagSetup& ms, Cha
                             int eval_grid, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter, eval_grid);
+    if (n <= kPrologueSmallMax) k_prologue_small<<<n, 128, 0, s>>>(params, n, ms, out, eval_counter, eval_grid);
+    else k_prologue<<<(n + 3) / 4, 128, 0, s>>>(params, n, ms, out, eval_counter, eval_grid);
     return cudaGetLastError();
 }
 
