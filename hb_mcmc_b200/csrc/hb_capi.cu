@@ -180,18 +180,19 @@ int ensure_scratch(hb_ctx* ctx, long n_points)
     return HB_OK;
 }
 
-// CTAs per chain: 1 when the batch fills more than half the grid (or the pass has to store the template), else the
-// largest power of two that keeps chains x parts within the grid, does not exceed the light curve's segment count
-// and respects hb_set_max_parts.  The result never depends on it (see k_chain_eval).  (Sharing only the chains of a
-// large batch's last, partial wave was built and measured: the per-item decode costs the main path more than the
-// shorter tail gives back.)
+// CTAs per chain: 1 when the batch fills more than half the grid (or the pass has to store the template), else as
+// many as keep chains x parts within the grid, do not exceed the light curve's segment count and respect
+// hb_set_max_parts (the kernel raises it further for the chains of the batch it skips).  The result never depends
+// on it (see k_chain_eval).  (Sharing only the chains of a large batch's last, partial wave was built and measured:
+// the per-item decode costs the main path more than the shorter tail gives back.)
 int choose_parts(const hb_ctx* ctx, long n_chains, long N, bool hot)
 {
     if (!hot || N <= kCandA / 2 || n_chains > 2 * kEvalThreads) return 1;  // (the kernel lists a shared batch's chains in 2 x threads slots)
     const int nseg = eval_segments(N);
-    int p = 1;
-    while (2 * p <= nseg && 2 * p <= ctx->max_parts && n_chains * 2 * p <= ctx->grid) p *= 2;  // (p need not divide nseg)
-    return p;
+    const int room = (int)std::min<long>(std::min(nseg, ctx->max_parts), ctx->grid / n_chains);
+    if (room < 2) return 1;
+    const int spp = (nseg + room - 1) / room;  // segments per part
+    return (nseg + spp - 1) / spp;             // parts that get at least one segment (need not divide nseg)
 }
 
 // true when p points into page-locked host memory the device can DMA from / to directly
