@@ -419,6 +419,7 @@ __global__ void k_pt_logL_by_rung(const PtConfig* __restrict__ cfgp, const int* 
 // the stream-ordered kernels: the chains are identical bit for bit (tests/test_gpu_pt.py).  mcmc_wrapper2.c:378-572.
 struct PtRunShared {
     ChainConst cc;
+    PrologueT P;
     SelectCtl<kEvalThreads> ctl;
     double red[32];
     double y[kPtNpars + 3];
@@ -588,6 +589,21 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
         PT_MARK(0);
         // the proposal's folded constants (chain prologue): four warps each take the libm levels (lanes = calls; the
         // same calls on every warp, side by side on the four sub-partitions) and then one section of the assembly
+#ifdef HB_PT_ONE_TRANS
+        if (wid == 0) {
+            PrologueT P;
+            prologue_trans_warp(sm.y, a.ms, P, lane);
+            if (lane == 0) sm.P = P;
+        }
+        __syncthreads();
+        PT_MARK(6);
+        if (wid < 4 && lane == 0) {
+            if (wid == 0) prologue_assemble_sections<kAsmStarA>(sm.y, a.ms, sm.P, sm.cc);
+            else if (wid == 1) prologue_assemble_sections<kAsmStarB>(sm.y, a.ms, sm.P, sm.cc);
+            else if (wid == 2) prologue_assemble_sections<kAsmOrbit>(sm.y, a.ms, sm.P, sm.cc);
+            else prologue_assemble_sections<kAsmAux>(sm.y, a.ms, sm.P, sm.cc);
+        }
+#else
         if (wid < 4) {
             PrologueT P;
             prologue_trans_warp(sm.y, a.ms, P, lane);
@@ -599,6 +615,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
                 else prologue_assemble_sections<kAsmAux>(sm.y, a.ms, P, sm.cc);
             }
         }
+#endif
         __syncthreads();
         PT_MARK(1);
 #ifdef HB_PT_PROF
