@@ -483,6 +483,19 @@ int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, dou
     int rc;
     if ((rc = ensure_chains(ctx, n_chains)) != HB_OK) return rc;
     const size_t np = (size_t)n_chains * NPARS;
+    if (n_chains <= prologue_small_max()) {
+        // A small batch (the calls of one OpenMP team through the shim, a ladder, C1) is latency, and the two DMA
+        // copies are a third of it: the kernels read the parameters from the pinned staging buffer and write the
+        // results into it directly instead (page-locked memory is mapped into the device's address space under
+        // unified addressing; k_prologue_small fetches a chain's 21 parameters in one coalesced read).
+        CK(grow_pin(ctx, np + (size_t)n_chains));
+        std::memcpy(ctx->h_pin, params, np * sizeof(double));
+        double* h_out = ctx->h_pin + np;
+        if ((rc = run_eval(ctx, ctx->h_pin, n_chains, ctx->d_t, ctx->d_fw, ctx->N, h_out, nullptr)) != HB_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(logL, h_out, (size_t)n_chains * sizeof(double));
+        return HB_OK;
+    }
     // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are DMA'd in place;
     // pageable ones go through the context's pinned staging buffer in chunks, so that the host copy of
     // chunk k+1 overlaps the transfer of chunk k.

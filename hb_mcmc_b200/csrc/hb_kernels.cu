@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(128) k_prologue_small(const double* __restrict
     const int c = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= n) return;
     __shared__ ChainConst cc;
-    const double* p = params + (size_t)c * NPARS;
+    __shared__ double sp[NPARS];  // the chain's parameters: one coalesced read (they may sit in mapped host memory)
+    if (threadIdx.x < NPARS) sp[threadIdx.x] = params[(size_t)c * NPARS + threadIdx.x];
+    __syncthreads();
+    const double* p = sp;
     PrologueT T;
     prologue_trans_warp(p, ms, T, lane);
     if (lane == 0) {
@@ -150,6 +153,7 @@ static_assert(kCandB * sizeof(uint64_t) >= 2 * kEvalThreads * sizeof(double), "c
 static_assert(HB_TMA_STAGING || kEvalCtasPerSm != 4 || sizeof(EvalShared) <= 56 * 1024, "EvalShared no longer fits four CTAs per SM");
 
 size_t eval_smem_bytes() { return sizeof(EvalShared); }
+int prologue_small_max() { return kPrologueSmallMax; }
 int eval_tile() { return kTile; }
 
 // Median rank of likelihood3.c:97-101 (quirk Q3): even N -> N/2, odd N -> N/2 + 1.  N == 1

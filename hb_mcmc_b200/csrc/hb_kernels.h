@@ -67,6 +67,7 @@ struct EvalArgs {
 };
 
 size_t eval_smem_bytes();
+int prologue_small_max();  // batches up to this many chains take k_prologue_small (and, from host buffers, no DMA copies)
 int eval_tile();  // samples per tile: device time / flux / weight arrays are padded to whole tiles plus one
 int eval_segments(long n_points);
 int eval_seg_shift(long n_points);

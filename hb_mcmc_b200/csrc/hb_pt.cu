@@ -419,7 +419,6 @@ __global__ void k_pt_logL_by_rung(const PtConfig* __restrict__ cfgp, const int* 
 // the stream-ordered kernels: the chains are identical bit for bit (tests/test_gpu_pt.py).  mcmc_wrapper2.c:378-572.
 struct PtRunShared {
     ChainConst cc;
-    PrologueT P;
     SelectCtl<kEvalThreads> ctl;
     double red[32];
     double y[kPtNpars + 3];
@@ -524,7 +523,10 @@ __device__ __forceinline__ double pt_run_loglike(PtRunShared& sm, const PtRunArg
     return -0.5 * (t0 + cc.chi2_extra);
 }
 
-__global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__ PtRunArgs a)
+#ifndef HB_PT_RUN_MIN_BLOCKS
+#define HB_PT_RUN_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kEvalThreads, HB_PT_RUN_MIN_BLOCKS) k_pt_run(const __grid_constant__ PtRunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PtRunShared& sm = *reinterpret_cast<PtRunShared*>(smem_raw);
@@ -589,21 +591,6 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
         PT_MARK(0);
         // the proposal's folded constants (chain prologue): four warps each take the libm levels (lanes = calls; the
         // same calls on every warp, side by side on the four sub-partitions) and then one section of the assembly
-#ifdef HB_PT_ONE_TRANS
-        if (wid == 0) {
-            PrologueT P;
-            prologue_trans_warp(sm.y, a.ms, P, lane);
-            if (lane == 0) sm.P = P;
-        }
-        __syncthreads();
-        PT_MARK(6);
-        if (wid < 4 && lane == 0) {
-            if (wid == 0) prologue_assemble_sections<kAsmStarA>(sm.y, a.ms, sm.P, sm.cc);
-            else if (wid == 1) prologue_assemble_sections<kAsmStarB>(sm.y, a.ms, sm.P, sm.cc);
-            else if (wid == 2) prologue_assemble_sections<kAsmOrbit>(sm.y, a.ms, sm.P, sm.cc);
-            else prologue_assemble_sections<kAsmAux>(sm.y, a.ms, sm.P, sm.cc);
-        }
-#else
         if (wid < 4) {
             PrologueT P;
             prologue_trans_warp(sm.y, a.ms, P, lane);
@@ -615,7 +602,6 @@ __global__ void __launch_bounds__(kEvalThreads) k_pt_run(const __grid_constant__
                 else prologue_assemble_sections<kAsmAux>(sm.y, a.ms, P, sm.cc);
             }
         }
-#endif
         __syncthreads();
         PT_MARK(1);
 #ifdef HB_PT_PROF
