@@ -1000,9 +1000,11 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
 __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab,
                                          const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V],
-                                         int* hi_acc = nullptr)
+                                         int* hi_acc = nullptr, int flag_known = -1)
 {
-    const bool may_eclipse = (((int)cc.flag) & 4) == 0;
+    // (flag_known >= 0 in the kDeferRange pass: the caller's register copy of cc.flag -- a loop that stores to
+    // shared memory would otherwise re-read and re-convert the flag at every sample)
+    const bool may_eclipse = ((kDeferRange ? flag_known : (int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
     kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cc.tab_min_m, sctab, cE, sE, den, bet, hi_acc);
 #pragma unroll

@@ -205,7 +205,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
              size_t region_stride, size_t key_stride, double* __restrict__ logL, double* __restrict__ lc_out,
              int* __restrict__ counter, float bracket_sigma, const double2* __restrict__ sctab_g, int hot_hi_limit,
              double sum_w2, unsigned long long* __restrict__ evaluated, ChainSync* __restrict__ sync_all, int nparts,
-             int nseg, int seg_shift, int max_parts)
+             int nseg, int seg_shift, int max_parts, int seg_mask)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalShared& sm = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -216,7 +216,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
     const int n_tiles = (N + kTile - 1) / kTile;
     int n_work = n_chains * nparts;
     static_assert((kTile & (kTile - 1)) == 0, "segment ends are read off the bits of the sample index");
-    const int seg_bits = ((1 << seg_shift) - 1) * kTile;  // the tile-in-segment bits of a sample index
+    // (seg_mask = 2^seg_shift - 1, the tile-in-segment bits of a tile index, comes as a parameter: a constant-bank operand)
     for (int i = tid; i < kSinTabN; i += kThreads) sm.sctab[i] = sctab_g[i];  // published by the first barrier below
     const double2* sctab = sm.sctab;
 #if HB_TMA_STAGING
@@ -454,8 +454,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             for (int j = 0; j < V; j++) {
                 idx[j] = i0 + j * kThreads;
                 ts[j] = ts_next[j];
-                HB_CHK(idx[j] + (tile + 1 < tile_last ? kTile : 0), (size_t)(n_tiles + 1) * kTile, 6);
-                if (tile + 1 < tile_last) ts_next[j] = tsec[idx[j] + kTile];
+                HB_CHK(idx[j] + kTile, (size_t)(n_tiles + 1) * kTile, 6);
+                ts_next[j] = tsec[idx[j] + kTile];  // (the array is padded with a whole tile beyond the last one)
                 fl[j] = wv[j] = 0.0;
                 if (kData) {  // one 16-byte load: {flux, 1/sigma} are interleaved
                     const double2 v = fw[idx[j]];
@@ -464,7 +464,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
 #endif
-            raw_flux<V, true, true, kHot>(cc, ktab, sctab, ts, u, &hi_acc);
+            raw_flux<V, true, true, kHot>(cc, ktab, sctab, ts, u, &hi_acc, flag);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -510,7 +510,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
 #else
             const int i_here = i0;
 #endif
-            if (kData && ((((i_here + kTile) & seg_bits) == 0) || tile + 1 == tile_last)) {
+            if (kData && ((((tile + 1) & seg_mask) == 0) || tile + 1 == tile_last)) {
                 if (kPart) {
                     const int seg = tile >> seg_shift;
                     HB_CHK(seg, nseg, 8);
@@ -908,11 +908,11 @@ cudaError_t launch_chain_eval(const EvalArgs& a, int grid, cudaStream_t s)
     if (a.nparts > 1)
         k_chain_eval<kEvalThreads, true><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(
             a.cc, a.n_chains, a.tsec, a.fw, a.N, a.scratch, a.region_stride, a.key_stride, a.logL, a.lc_out, a.counter, a.bracket_sigma,
-            a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, a.nparts, a.nseg, a.seg_shift, a.max_parts);
+            a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, a.nparts, a.nseg, a.seg_shift, a.max_parts, (1 << a.seg_shift) - 1);
     else
         k_chain_eval<kEvalThreads, false><<<grid, kEvalThreads, sizeof(EvalShared), s>>>(
             a.cc, a.n_chains, a.tsec, a.fw, a.N, a.scratch, a.region_stride, a.key_stride, a.logL, a.lc_out, a.counter, a.bracket_sigma,
-            a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, 1, a.nseg, a.seg_shift, a.max_parts);
+            a.sctab, a.hot_hi_limit, a.sum_w2, a.evaluated, a.sync, 1, a.nseg, a.seg_shift, a.max_parts, (1 << a.seg_shift) - 1);
     return cudaGetLastError();
 }
 
