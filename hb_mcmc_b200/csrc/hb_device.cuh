@@ -892,15 +892,19 @@ template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
                                               const double rPs, const double* __restrict__ ktab, const double tab_min_m,
                                               const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
-                                              double (&den)[V], double (&beta)[V], int* hi_acc = nullptr)
+                                              double (&den)[V], double (&beta)[V], int* hi_acc = nullptr,
+                                              int flag_known = -1)
 {
     double M[V], E[V], dE[V], yr[V];
+    // (kDeferRange: bit 3 of the caller's register copy of the chain's flags says tab_min_m > 0 -- no load, no FP64
+    // compare per sample for it)
+    const bool window = kDeferRange ? ((flag_known & 8) != 0) : (tab_min_m > 0.0);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         M[j] = mean_anomaly(tsec[j], T0s, Ps, rPs);
         if (ktab == nullptr) {
             E[j] = kepler_starter(M[j], e);
-        } else if (tab_min_m > 0.0) {  // eccentric chain: the reference's own path inside the periastron window
+        } else if (window) {  // eccentric chain: the reference's own path inside the periastron window
             const double am = fabs(M[j]);
             const bool far = fmin(am, kTwoPi - am) >= tab_min_m;
             E[j] = far ? kepler_table_guess(ktab, M[j]) : kepler_starter(M[j], e);
@@ -1002,11 +1006,11 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
                                          const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V],
                                          int* hi_acc = nullptr, int flag_known = -1)
 {
-    // (flag_known >= 0 in the kDeferRange pass: the caller's register copy of cc.flag -- a loop that stores to
-    // shared memory would otherwise re-read and re-convert the flag at every sample)
+    // (flag_known in the kDeferRange pass: the caller's register copy of cc.flag, bit 3 = tab_min_m > 0 added -- a
+    // loop that stores to shared memory would otherwise re-read and re-convert the flag at every sample)
     const bool may_eclipse = ((kDeferRange ? flag_known : (int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
-    kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cc.tab_min_m, sctab, cE, sE, den, bet, hi_acc);
+    kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cc.tab_min_m, sctab, cE, sE, den, bet, hi_acc, flag_known);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)

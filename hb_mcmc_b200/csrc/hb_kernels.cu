@@ -384,6 +384,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         constexpr int V = kPointsPerThread;
         static_assert(V == 1, "the segment bookkeeping of the pass is written for one sample per thread and iteration");
         int hi_acc = 0;  // largest sincos argument exponent of the hot pass (checked once, below)
+        const int flag_pass = flag | (cc.tab_min_m > 0.0 ? 8 : 0);  // what the sample loop asks per sample, in a register
         ChainSync* const sync = sync_all + (!kShared ? 0 : chain);
         auto model_pass = [&](auto store_tag, auto data_tag, auto part_tag) {
         constexpr bool kStore = decltype(store_tag)::value;
@@ -464,7 +465,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
 #endif
-            raw_flux<V, true, true, kHot>(cc, ktab, sctab, ts, u, &hi_acc, flag);
+            raw_flux<V, true, true, kHot>(cc, ktab, sctab, ts, u, &hi_acc, flag_pass);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -476,10 +477,13 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                     HB_CHK(i, key_stride, 4);
                     tmpl[i] = dkey(uj);
                 }
-                if (valid & (uj < lo)) c_lt++;
+                // #(u < lo): one compare of the index, one FP64 compare taking it as a predicate input, one predicated
+                // add (the compiler turns `if (valid & (uj < lo)) c_lt++` into a select and two moves)
+                asm("{\n .reg .pred pv, pl;\n setp.lt.s32 pv, %3, %4;\n setp.lt.and.f64 pl, %1, %2, pv;\n @pl add.s32 %0, %0, 1;\n}"
+                    : "+r"(c_lt) : "d"(uj), "d"(lo), "r"(i), "r"(N));
                 const bool inr = valid & (uj >= lo) & (uj <= hi);
-                const unsigned mask = __ballot_sync(0xffffffffu, inr);
-                if (mask) {
+                if (__any_sync(0xffffffffu, inr)) {  // (the vote goes straight to a predicate; the mask only where it is used)
+                    const unsigned mask = __ballot_sync(0xffffffffu, inr);
                     const int leader = __ffs(mask) - 1;
                     int basepos = 0;
                     if (lane == leader) basepos = kPart ? atomicAdd(&sync->cnt, __popc(mask)) : atomicAdd(&sm.ctl.cnt, __popc(mask));
@@ -503,13 +507,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             }
             // a segment (or the pass) ends with this tile: this thread's sums of the segment join the running
             // sums in segment order -- here, or (a part) through the chain's scratch at the hands of the finisher
-            // (the segment's end is read off the bits of the sample index, the pass's end off the tile counter: the
-            // latter then serves loop control alone and stays in a uniform register)
-#if HB_TMA_STAGING
-            const int i_here = tile * kTile + tid;
-#else
-            const int i_here = i0;
-#endif
+            // (the segment's end is read off the tile counter against seg_mask, a constant-bank operand)
             if (kData && ((((tile + 1) & seg_mask) == 0) || tile + 1 == tile_last)) {
                 if (kPart) {
                     const int seg = tile >> seg_shift;
