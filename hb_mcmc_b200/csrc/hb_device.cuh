@@ -733,15 +733,8 @@ __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* 
     }
 }
 
-// rare tail of fmod_twopi: quotient off by one (|M| within rounding of a multiple of 2 pi), or
-// huge / inf / NaN input
-static __device__ __noinline__ double fmod_twopi_fix(double q, double r, double am)
-{
-    const double y = kTwoPi;
-    if (!(am < 1.0e15)) return fmod(am, y);
-    q += (r < 0.0) ? -1.0 : 1.0;
-    return fma(-q, y, am);  // exact: 0 <= r < y is representable
-}
+// rarest tail of fmod_twopi: huge / inf / NaN input
+static __device__ __noinline__ double fmod_twopi_lib(double am) { return fmod(am, kTwoPi); }
 
 // Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153): a rounded quotient
 // from the magic-number trick and one exact FMA remainder; one range test catches both the
@@ -751,9 +744,18 @@ __device__ __forceinline__ double fmod_twopi(double M)
     const double am = fabs(M);
     // floor(am / y): the magic-number trick with the FMA rounding toward -inf (at 1.5 * 2^52 one ulp is 1).
     // Adding `magic - 0.5` in round-to-nearest does NOT work: that constant is not representable.
-    const double q = __fma_rd(am, kMisc[1], kMagic) - kMagic;
+    double q = __fma_rd(am, kMisc[1], kMagic) - kMagic;
     double r = fma(-q, kMisc[0], am);
-    if (!(r >= 0.0 && r < kMisc[0])) r = fmod_twopi_fix(q, r, am);
+    if (!(r >= 0.0 && r < kMisc[0])) {
+        // rare: quotient off by one (|M| within rounding of a multiple of 2 pi) -- repaired in line, so that the
+        // sample loop does not marshal registers around a call at every sample -- or huge / inf / NaN input
+        if (am < 1.0e15) {
+            q += (r < 0.0) ? -1.0 : 1.0;
+            r = fma(-q, kMisc[0], am);  // exact: 0 <= r < y is representable
+        } else {
+            r = fmod_twopi_lib(am);
+        }
+    }
     return copysign(r, M);
 }
 
