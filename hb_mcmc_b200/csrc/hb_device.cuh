@@ -739,7 +739,12 @@ static __device__ __noinline__ double fmod_twopi_lib(double am) { return fmod(am
 // Exact fmod(M, fl(2 pi)) keeping the dividend's sign (likelihood3.c:153): a rounded quotient
 // from the magic-number trick and one exact FMA remainder; one range test catches both the
 // off-by-one quotient and non-finite input.
-__device__ __forceinline__ double fmod_twopi(double M)
+// kNoCall (the hot pass): the huge / inf / NaN tail raises *hi_acc beyond every limit instead of going to the
+// library -- the caller's deferred range check then has the chain evaluated again by the general pass.  A CALL on the
+// sample's path, even one that is never taken, makes ptxas rebuild the shared-memory window address (uniform
+// registers do not survive calls) for everything that follows it in the iteration.
+template <bool kNoCall = false>
+__device__ __forceinline__ double fmod_twopi(double M, int* hi_acc = nullptr)
 {
     const double am = fabs(M);
     // floor(am / y): the magic-number trick with the FMA rounding toward -inf (at 1.5 * 2^52 one ulp is 1).
@@ -752,6 +757,9 @@ __device__ __forceinline__ double fmod_twopi(double M)
         if (am < 1.0e15) {
             q += (r < 0.0) ? -1.0 : 1.0;
             r = fma(-q, kMisc[0], am);  // exact: 0 <= r < y is representable
+        } else if (kNoCall) {
+            *hi_acc = 0x7fffffff;
+            r = 0.0;
         } else {
             r = fmod_twopi_lib(am);
         }
@@ -762,11 +770,12 @@ __device__ __forceinline__ double fmod_twopi(double M)
 // Mean anomaly of likelihood3.c:149-153, bit-identical with the reference's 2 pi (t - T0) / P:
 // the two products are explicitly rounded and the division is the correctly rounded Markstein
 // sequence on rP = RN(1/P).  tsec = t * 86400 exactly as the reference forms it.
-__device__ __forceinline__ double mean_anomaly(double tsec, double T0s, double Ps, double rPs)
+template <bool kNoCall = false>
+__device__ __forceinline__ double mean_anomaly(double tsec, double T0s, double Ps, double rPs, int* hi_acc = nullptr)
 {
     const double x = __dmul_rn(kMisc[0], __dsub_rn(tsec, T0s));
     const double q0 = __dmul_rn(x, rPs);
-    return fmod_twopi(fma(fma(-Ps, q0, x), rPs, q0));
+    return fmod_twopi<kNoCall>(fma(fma(-Ps, q0, x), rPs, q0), hi_acc);
 }
 
 // Starter of likelihood3.c:154-157: E0 = M + 0.85 e sign(sin M) (E0 = M when sin M == 0).
@@ -903,7 +912,7 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
     const bool window = kDeferRange ? ((flag_known & 8) != 0) : (tab_min_m > 0.0);
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        M[j] = mean_anomaly(tsec[j], T0s, Ps, rPs);
+        M[j] = mean_anomaly<kDeferRange>(tsec[j], T0s, Ps, rPs, hi_acc);
         if (ktab == nullptr) {
             E[j] = kepler_starter(M[j], e);
         } else if (window) {  // eccentric chain: the reference's own path inside the periastron window

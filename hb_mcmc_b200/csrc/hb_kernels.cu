@@ -508,7 +508,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             // a segment (or the pass) ends with this tile: this thread's sums of the segment join the running
             // sums in segment order -- here, or (a part) through the chain's scratch at the hands of the finisher
             // (the segment's end is read off the tile counter against seg_mask, a constant-bank operand)
-            if (kData && ((((tile + 1) & seg_mask) == 0) || tile + 1 == tile_last)) {
+            if (kData && (((tile + 1) & seg_mask) == 0)) {  // (a last, partial segment is handed over behind the loop)
                 if (kPart) {
                     const int seg = tile >> seg_shift;
                     HB_CHK(seg, nseg, 8);
@@ -520,6 +520,18 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
                 S0 = S1 = 0.;
             }
+        }
+        if (kData && (tile_last & seg_mask) != 0) {  // the light curve's last segment is a partial one
+            if (kPart) {
+                const int seg = (tile_last - 1) >> seg_shift;
+                HB_CHK(seg, nseg, 8);
+                partials[(size_t)(2 * seg) * kThreads + tid] = S0;
+                partials[(size_t)(2 * seg + 1) * kThreads + tid] = S1;
+            } else {
+                tsum[tid] += S0;
+                tsum[kThreads + tid] += S1;
+            }
+            S0 = S1 = 0.;
         }
         };
         // instantiations: the hot logL-only pass (whole chain / one part), and a general one (template stored) for

@@ -56,6 +56,26 @@ def test_non_finite_parameters_give_nan_not_garbage(ctx, orc):
     assert np.all(clean == got[0])
 
 
+def test_huge_times_take_the_library_fmod(ctx, orc):
+    """Times so large that the mean anomaly leaves the range of the in-line fmod (|M| >= 1e15): the hot pass does not
+    call the library from inside its sample loop -- it flags the chain, which is evaluated again by the general pass
+    with the library's exact fmod (likelihood3.c:153).  Same value as the reference, hot pass (N = 20 000, shared and
+    unshared) or small-N path."""
+    for N in (20000, 600):
+        t = 3.0e15 + 2.0 * np.arange(N)  # days; ulp(3e15) = 0.5
+        rng = np.random.default_rng(8)
+        flux = 1 + 1e-3 * rng.standard_normal(N)
+        err = np.full(N, 5e-4)
+        ctx.set_data(t, flux, err)
+        P = wl.draw_chains(700 if N == 20000 else 8, wl.TRUTH_A, lambda P: ctx.roche_overflow(P), seed=6)
+        want = orc.loglikelihood_batch(t, flux, err, P[:8])
+        for k in (8, len(P)):  # a shared batch, and (N = 20 000) one that fills the grid
+            got = ctx.loglikelihood(P[:k])
+            assert np.array_equal(np.isnan(got[:8]), np.isnan(want))
+            fin = np.isfinite(want)
+            assert np.allclose(got[:8][fin], want[fin], rtol=1e-10), (N, k)
+
+
 def test_context_reuse_across_data_sets(ctx, orc):
     """Buffers are re-sized and re-padded on every hb_set_data: alternate long and short light curves."""
     rng = np.random.default_rng(3)
