@@ -877,8 +877,15 @@ static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab
         // (0 <= M <= pi + h and e <= 0.99: Newton from the reference starter converges from above, every iterate stays
         // below 2 pi -- far inside the table sincos' range; the largest argument seen is not tracked)
         sincos_tab<2>(E, sctab, s, c, hi);
+        bool small = true;
 #pragma unroll
-        for (int i = 0; i < 2; i++) E[i] -= div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
+        for (int i = 0; i < 2; i++) {
+            const double step = div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
+            E[i] -= step;
+            small &= fabs(step) < 1e-6;  // the NEXT step is then ~C step^2 < 1e-11: this iterate is a starter already
+        }
+        // (warp-uniform: low eccentricities are there after three steps; every CTA of a chain builds the same table)
+        if (__all_sync(0xffffffffu, small)) break;
     }
     HB_CHK(j[0], kTableSize, 3);
     HB_CHK(j[1], kTableSize, 3);
