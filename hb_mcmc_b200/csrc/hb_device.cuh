@@ -711,13 +711,13 @@ constexpr double kT4 = 0x1.55555p-5;
 // (an FMA takes one immediate at most: where two constants meet, one comes from here)
 __constant__ double kTabC[6] = {162.97466172610082624, 1.57079632679489655800e+00 / 256.0, 6.12323399573676603587e-17 / 256.0,
                                 -0.5, -1.0 / 6.0, 0.0};
-template <int V>
+template <int V, bool kTrack = true>
 __device__ __forceinline__ void sincos_tab(const double (&x)[V], const double2* __restrict__ tab, double (&s_out)[V],
                                            double (&c_out)[V], int& hi_max)
 {
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        hi_max = max(hi_max, __double2hiint(x[j]) & 0x7fffffff);
+        if (kTrack) hi_max = max(hi_max, __double2hiint(x[j]) & 0x7fffffff);
         const double t = fma(x[j], kTabC[0], kMagic);
         const int k = __double2loint(t) & (kSinTabN - 1);  // nearest node, periodic (two's complement for x < 0)
         const double kd = t - kMagic;
@@ -906,7 +906,10 @@ static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab
 // kDeferRange: do not test the fast sincos' argument range per sample; the largest exponent word seen is
 // accumulated into *hi_acc and the CALLER checks it once (and redoes its work without kDeferRange if it
 // is out of range -- wild Newton iterates at e -> 1 are rare).
-template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
+// kLowE: the caller knows that the chain takes the table starter at EVERY sample (ktab != nullptr, tab_min_m == 0,
+// i.e. e <= kTableAllE): no starter choice per sample, and no tracking of the sincos arguments -- from the table
+// starter every Newton iterate stays within a step of [-2 pi, 2 pi], far inside the table sincos' range.
+template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false, bool kLowE = false>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
                                               const double rPs, const double* __restrict__ ktab, const double tab_min_m,
                                               const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
@@ -920,7 +923,9 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
 #pragma unroll
     for (int j = 0; j < V; j++) {
         M[j] = mean_anomaly<kDeferRange>(tsec[j], T0s, Ps, rPs, hi_acc);
-        if (ktab == nullptr) {
+        if (kLowE) {
+            E[j] = kepler_table_guess(ktab, M[j]);
+        } else if (ktab == nullptr) {
             E[j] = kepler_starter(M[j], e);
         } else if (window) {  // eccentric chain: the reference's own path inside the periastron window
             const double am = fabs(M[j]);
@@ -940,7 +945,7 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
     int hi_max = 0;
 #pragma unroll kNewtonUnroll
     for (int k = 0; k < 5; k++) {
-        if (kSinTab) sincos_tab<V>(E, sctab, sE, cE, hi_max);
+        if (kSinTab) sincos_tab<V, !kLowE>(E, sctab, sE, cE, hi_max);
         else sincos_lean<V>(E, sE, cE, hi_max);
         tiny = true;
 #pragma unroll
@@ -967,7 +972,7 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
             beta[j] = fma(yr[j], fma(-den[j], yr[j], 1.0), yr[j]);
         }
     } else {
-        if (kSinTab) sincos_tab<V>(E, sctab, sE, cE, hi_max);
+        if (kSinTab) sincos_tab<V, !kLowE>(E, sctab, sE, cE, hi_max);
         else sincos_lean<V>(E, sE, cE, hi_max);
 #pragma unroll
         for (int j = 0; j < V; j++) {
@@ -975,7 +980,8 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
             beta[j] = rcp_fast(den[j]);
         }
     }
-    if (kDeferRange) {
+    if (kLowE) {
+    } else if (kDeferRange) {
         *hi_acc = max(*hi_acc, hi_max);
     } else if (hi_max > (kSinTab ? kSincosTabHiLimit : kSincosHiLimit)) {  // an iterate left the fast sincos' range: library
 #pragma unroll
@@ -1019,7 +1025,7 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 
 // Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
-template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false>
+template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false, bool kLowE = false>
 __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab,
                                          const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V],
                                          int* hi_acc = nullptr, int flag_known = -1)
@@ -1028,7 +1034,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
     // loop that stores to shared memory would otherwise re-read and re-convert the flag at every sample)
     const bool may_eclipse = ((kDeferRange ? flag_known : (int)cc.flag) & 4) == 0;
     double cE[V], sE[V], den[V], bet[V];
-    kepler_points<V, kFullWarp, kSinTab, kDeferRange>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cc.tab_min_m, sctab, cE, sE, den, bet, hi_acc, flag_known);
+    kepler_points<V, kFullWarp, kSinTab, kDeferRange, kLowE>(tsec, cc.e, cc.T0s, cc.Ps, cc.rPs, ktab, cc.tab_min_m, sctab, cE, sE, den, bet, hi_acc, flag_known);
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const double beta = bet[j];  // (1 + e cos nu)/(1 - e^2) == 1/(1 - e cos E)

@@ -386,7 +386,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         int hi_acc = 0;  // largest sincos argument exponent of the hot pass (checked once, below)
         const int flag_pass = flag | (cc.tab_min_m > 0.0 ? 8 : 0);  // what the sample loop asks per sample, in a register
         ChainSync* const sync = sync_all + (!kShared ? 0 : chain);
-        auto model_pass = [&](auto store_tag, auto data_tag, auto part_tag) {
+        auto model_pass = [&](auto store_tag, auto data_tag, auto part_tag, auto lowe_tag) {
+        constexpr bool kLowE = decltype(lowe_tag)::value;  // table starter at every sample (see kepler_points)
         constexpr bool kStore = decltype(store_tag)::value;
         constexpr bool kHot = !kStore;  // the logL-only pass defers the sincos range check to the end of the chain
         constexpr bool kData = decltype(data_tag)::value;  // fw != nullptr, known at compile time in the hot variant
@@ -465,7 +466,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
                 }
             }
 #endif
-            raw_flux<V, true, true, kHot>(cc, ktab, sctab, ts, u, &hi_acc, flag_pass);
+            raw_flux<V, true, true, kHot, kLowE>(cc, ktab, sctab, ts, u, &hi_acc, flag_pass);
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const int i = idx[j];
@@ -540,8 +541,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         auto general_pass = [&]() {  // the whole chain, by this CTA alone
             if (tid == 0) sm.ctl.cnt = 0;
             __syncthreads();
-            if (fw != nullptr) model_pass(std::true_type{}, std::true_type{}, std::false_type{});
-            else model_pass(std::true_type{}, std::false_type{}, std::false_type{});
+            if (fw != nullptr) model_pass(std::true_type{}, std::true_type{}, std::false_type{}, std::false_type{});
+            else model_pass(std::true_type{}, std::false_type{}, std::false_type{}, std::false_type{});
         };
         auto load_sums = [&](bool from_parts) {  // this thread's chi^2 sums: its segment sums added in segment order
             if (fw == nullptr) return;
@@ -577,8 +578,20 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             c_in = sm.ctl.cnt;
             load_sums(false);
         } else {
-            if constexpr (!kShared) model_pass(std::false_type{}, std::true_type{}, std::false_type{});
-            else model_pass(std::false_type{}, std::true_type{}, std::true_type{});
+#ifndef HB_LOWE_MAX_N
+#define HB_LOWE_MAX_N 65536
+#endif
+            // (a second copy of the sample loop for chains that take the table starter everywhere -- 96 % of prior
+            // draws -- without the starter choice and the argument tracking: 2 % on light curves of 20-50 k points;
+            // on 200 k points the same copy LOSES 3 %, so it is taken by the light curve's length)
+            if constexpr (!kShared) {
+                if (N <= HB_LOWE_MAX_N && use_table && !(cc.tab_min_m > 0.0))
+                    model_pass(std::false_type{}, std::true_type{}, std::false_type{}, std::true_type{});
+                else
+                    model_pass(std::false_type{}, std::true_type{}, std::false_type{}, std::false_type{});
+            } else {
+                model_pass(std::false_type{}, std::true_type{}, std::true_type{}, std::false_type{});
+            }
             // a Newton iterate left the table sincos' range somewhere in this chain (e -> 1 only): the sums are
             // not trustworthy; the chain is evaluated again with the per-sample check and the library fallback
             int redo = __syncthreads_or(hi_acc > hot_hi_limit);
