@@ -632,10 +632,10 @@ __constant__ double kSinC[6] = {-1.66666666666666324348e-01, 8.33333333332248946
 __constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                 -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
 // Scalar constants of the per-sample code as constant-bank operands (a literal double with a non-zero
-// low word costs two moves per use): 0 fl(2 pi)  1 1/fl(2 pi)  4 E(M)-table nodes per radian  6 1/6
-// 7 fl(pi)  (2, 3, 5: unused since the magic number became an instruction immediate)
+// low word costs two moves per use): 0 fl(2 pi)  1 1/fl(2 pi)  4 E(M)-table nodes per radian
+// 7 fl(pi)  (2, 3, 5, 6: unused since the magic number became an instruction immediate)
 __constant__ double kMisc[8] = {6.283185307179586476925, 0.15915494309189534561, 0.0, 0.0,
-                                162.97466172610083, 0.0, 1.0 / 6.0, 3.14159265358979323846};
+                                122.23099629457562, 0.0, 0.0, 3.14159265358979323846};
 // pi/2 split in three (Cody-Waite), 2/pi, and the round-to-integer magic number 1.5 * 2^52
 __constant__ double kRed[5] = {1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983880e-33,
                                6.36619772367581382433e-01, 6755399441055744.0};
@@ -814,87 +814,114 @@ static __device__ __noinline__ void kepler_point_careful(double m, double e, dou
 // For 0 <= e <= kTableMaxE the reference's five Newton steps reach the root of Kepler's equation
 // to rounding for every M (scanned on the CPU: max |E5 - E*| = 2.6e-15 at e = 0.8, 3.4e-15 at
 // 0.85; the un-converged tail only starts between 0.85 and 0.90).  The converged root does not
-// depend on the starter, so such chains may start Newton from anything convergent: a cubic
-// Lagrange interpolation in a shared-memory table of E on kTableN+1 uniform nodes of M in
-// [0, 2 pi] (the upper half is the mirror image E(2 pi - M) = 2 pi - E(M) of the solved lower
-// half, negative M uses E(-M) = -E(M)).  Interpolation error <= 5e-9 for e <= 0.6 and
-// <= 3.4e-7 at e = 0.8, so the warp-uniform exit of the Newton loop fires after ONE step
+// depend on the starter, so such chains may start Newton from anything convergent: the cubic
+// Taylor polynomial of E(M) about the NEAREST of kTableN+1 uniform nodes of M on [0, 2 pi], whose
+// four coefficients -- E, E1 h, E2 h^2/2, E3 h^3/6 with the derivatives E1 = beta = 1/(1 - e cos E),
+// E2 = -e sin E beta^3, E3 = beta^4 (3 e^2 sin^2 E beta - e cos E) -- sit in 32 bytes of shared
+// memory per node (two 16-byte loads, three FMAs; negative M uses E(-M) = -E(M), the upper half of
+// the table is the mirror image E(2 pi - M) = 2 pi - E(M) of the solved lower half).  Truncation error
+// (h/2)^4/24 E4 = 1.9e-10 E4: a third of what cubic Lagrange interpolation on 1024 intervals gave
+// (rounds 1-2) at half its arithmetic, so the warp-uniform exit of the Newton loop fires after ONE step
 // (two near periastron at the high end) instead of three to four from the reference starter.
-constexpr int kTableN = 1024;              // intervals on [0, 2 pi]  (h = pi / 512)
-constexpr int kTableSize = kTableN + 3;    // nodes -1 .. kTableN+1
-constexpr int kTableSolved = kTableN / 2 + 2;  // entries 0 .. kTableN/2+1 are solved, the rest mirrored
+constexpr int kTableN = 768;                   // intervals on [0, 2 pi]  (h = 2 pi / 768)
+constexpr int kTableNodes = kTableN + 1;       // nodes 0 .. kTableN
+constexpr int kTableSolved = kTableN / 2 + 1;  // nodes 0 .. kTableN/2 are solved, the rest mirrored
+constexpr int kTableMinN = 4108;               // light curves shorter than this do not pay for a table
 // (kTableAllE, kTableMaxE, kTableMinM: see the top of this file)
 
-__device__ __forceinline__ double kepler_table_node(int j, double e);
-
-// starter from the table: tab[j + 1] = E(2 pi j / kTableN), |m| < 2 pi
-__device__ __forceinline__ double kepler_table_guess(const double* __restrict__ tab, double m)
+// The two 16-byte halves {E, c1}, {c2, c3} of a node from the root E and sin/cos E there.
+__device__ __forceinline__ void kepler_table_coeffs(double e, double E, double sE, double cE, double2& a, double2& b)
 {
-    const double x = fabs(m) * kMisc[4];
-    int j = __double2int_rd(x);
-    j = min(j, kTableN - 1);
-    const double t = x - (double)j;  // in [0, 1]
-    // cubic Lagrange on the nodes -1, 0, 1, 2 with the weights paired up:
-    //   E = a/6 (y3 (t+1) - y0 (t-2)) + b/2 (y1 (t-1) - y2 t),  a = t (t-1),  b = (t+1)(t-2) = a - 2
-    HB_CHK(j, kTableSize - 3, 2);
-    const double y0 = tab[j], y1 = tab[j + 1], y2 = tab[j + 2], y3 = tab[j + 3];
-    const double a = fma(t, t, -t);
-    const double p = fma(t, y3 - y0, fma(2.0, y0, y3));
-    const double q = fma(t, y1 - y2, -y1);
-    // (a/2 - 1) q + (a/6) p, arranged so that no FMA carries two constant operands (one of them would
-    // have to be built in registers with two moves)
-    const double E = fma(a, 0.5 * q, fma(a * kMisc[6], p, -q));
+    constexpr double h = kTwoPi / (double)kTableN;
+    const double beta = rcp_fast(fma(-e, cE, 1.0));
+    const double es = e * sE, ec = e * cE, b2 = beta * beta;
+    a.x = E;
+    a.y = h * beta;
+    b.x = (-0.5 * h * h) * (es * (b2 * beta));
+    b.y = (h * h * h / 6.0) * ((b2 * b2) * fma(3.0 * es * es, beta, -ec));
+}
+// node n of the table from node kTableN - n
+__device__ __forceinline__ void kepler_table_mirror(const double2& a, const double2& b, double2& am, double2& bm)
+{
+    am.x = kTwoPi - a.x;
+    am.y = a.y;
+    bm.x = -b.x;
+    bm.y = b.y;
+}
+
+// starter from the table: tab[2 k], tab[2 k + 1] = node k (M = 2 pi k / kTableN), |m| < 2 pi.
+// kClamp: m may be NaN (the general pass; the hot pass hands over finite |m| < 2 pi only).
+template <bool kClamp = true>
+__device__ __forceinline__ double kepler_table_guess(const double2* __restrict__ tab, double m)
+{
+    const double am = fabs(m);
+    const double t = fma(am, kMisc[4], kMagic);  // the nearest node's number in the low word (at 1.5 * 2^52 one ulp is 1)
+    int k = __double2loint(t);
+    if (kClamp) k = (int)min((unsigned)k, (unsigned)kTableN);
+    const double d = fma(am, kMisc[4], kMagic - t);  // distance from the node in node spacings, |d| <= 1/2
+    HB_CHK(k, kTableNodes, 2);
+    const double2 a = tab[2 * k], b = tab[2 * k + 1];
+    const double E = fma(d, fma(d, fma(d, b.y, b.x), a.y), a.x);
     return copysign(E, m);
 }
 
-__device__ __forceinline__ double kepler_table_node(int j, double e)
+// One node for the host emulation (library-free, node by node).
+__device__ __forceinline__ void kepler_table_node(int k, double e, double2& a, double2& b)
 {
-    const double m = (double)(j - 1) * (kTwoPi / (double)kTableN);
+    const double m = (double)k * (kTwoPi / (double)kTableN);
     double E[1] = {kepler_starter(m, e)}, s[1], c[1];
     int hi = 0;
-    for (int k = 0; k < 6; k++) {  // quadratic convergence: a starter only needs ~1e-10
+    for (int it = 0; it < 6; it++) {  // quadratic convergence: a starter only needs ~1e-10
         sincos_lean<1>(E, s, c, hi);
         E[0] -= div_fast(fma(-e, s[0], E[0]) - m, fma(-e, c[0], 1.0));
     }
-    return E[0];
+    sincos_lean<1>(E, s, c, hi);
+    kepler_table_coeffs(e, E[0], s[0], c[0], a, b);
 }
 
-// The whole table of one chain, built by the CTA (blockDim.x = kThreads threads, all of them call).  Entry j
-// holds node j - 1.  Nodes 1 .. N/2 are solved, two per thread as ONE interleaved latency chain (entries
-// 2 + tid and 2 + kThreads + tid); node 0 is E = 0, node -1 mirrors node 1, nodes above N/2 mirror N - n.
+// The whole table of one chain, built by the CTA (blockDim.x = kThreads threads, all of them call).  Nodes
+// 0 .. N/2 are solved, two per thread as ONE interleaved latency chain (nodes tid and kThreads + tid); every
+// thread also writes the mirror images of its nodes.
 // Out of line: it runs once per chain and must not weigh on the register allocation of the sample loop.
 #ifndef HB_HOST_EMUL  // (the host emulation fills its table node by node with kepler_table_node)
 template <int kThreads>
-static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab, double e, const double2* __restrict__ sctab)
+static __device__ __noinline__ void build_kepler_table(double2* __restrict__ ktab, double e, const double2* __restrict__ sctab)
 {
-    static_assert(2 + 2 * kThreads >= kTableSolved, "two table entries per thread must cover the solved half");
+    static_assert(2 * kThreads >= kTableSolved, "two table nodes per thread must cover the solved half");
     const int tid = threadIdx.x;
-    const int j[2] = {2 + tid, min(2 + kThreads + tid, kTableSolved - 1)};
-    const double m[2] = {(double)(j[0] - 1) * (kTwoPi / (double)kTableN), (double)(j[1] - 1) * (kTwoPi / (double)kTableN)};
-    double E[2] = {kepler_starter(m[0], e), kepler_starter(m[1], e)}, s[2], c[2];
+    const int j[2] = {tid, min(kThreads + tid, kTableSolved - 1)};
+    const double m[2] = {(double)j[0] * (kTwoPi / (double)kTableN), (double)j[1] * (kTwoPi / (double)kTableN)};
+    double E[2] = {kepler_starter(m[0], e), kepler_starter(m[1], e)}, s[2], c[2], step[2] = {0.0, 0.0};
     int hi = 0;
     for (int k = 0; k < 6; k++) {  // quadratic convergence: a starter only needs ~1e-10
-        // (0 <= M <= pi + h and e <= 0.99: Newton from the reference starter converges from above, every iterate stays
+        // (0 <= M <= pi and e <= 0.99: Newton from the reference starter converges from above, every iterate stays
         // below 2 pi -- far inside the table sincos' range; the largest argument seen is not tracked)
         sincos_tab<2>(E, sctab, s, c, hi);
         bool small = true;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-            const double step = div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
-            E[i] -= step;
-            small &= fabs(step) < 1e-6;  // the NEXT step is then ~C step^2 < 1e-11: this iterate is a starter already
+            step[i] = div_fast(fma(-e, s[i], E[i]) - m[i], fma(-e, c[i], 1.0));
+            E[i] -= step[i];
+            small &= fabs(step[i]) < 1e-6;  // the NEXT step is then ~C step^2 < 1e-11: this iterate is a starter already
         }
         // (warp-uniform: low eccentricities are there after three steps; every CTA of a chain builds the same table)
         if (__all_sync(0xffffffffu, small)) break;
     }
-    HB_CHK(j[0], kTableSize, 3);
-    HB_CHK(j[1], kTableSize, 3);
-    ktab[j[0]] = E[0];
-    ktab[j[1]] = E[1];
-    if (tid == 0) ktab[1] = 0.0;
-    __syncthreads();
-    if (tid == 0) ktab[0] = -ktab[2];
-    for (int i = kTableSolved + tid; i < kTableSize; i += kThreads) ktab[i] = kTwoPi - ktab[kTableN + 2 - i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        // sin/cos of the last iterate to first order in the last step (1e-12 where the loop left early; nodes that
+        // did not get there in six steps lie inside the periastron window of e -> 1, where the table is not used)
+        const double cE = fma(s[i], step[i], c[i]), sE = fma(-c[i], step[i], s[i]);
+        double2 a, b, am, bm;
+        kepler_table_coeffs(e, E[i], sE, cE, a, b);
+        kepler_table_mirror(a, b, am, bm);
+        HB_CHK(j[i], kTableNodes, 3);
+        HB_CHK(kTableN - j[i], kTableNodes, 3);
+        ktab[2 * (kTableN - j[i])] = am;  // (node N/2 is its own image: the node itself is written last)
+        ktab[2 * (kTableN - j[i]) + 1] = bm;
+        ktab[2 * j[i]] = a;
+        ktab[2 * j[i] + 1] = b;
+    }
     __syncthreads();
 }
 #endif
@@ -911,7 +938,7 @@ static __device__ __noinline__ void build_kepler_table(double* __restrict__ ktab
 // starter every Newton iterate stays within a step of [-2 pi, 2 pi], far inside the table sincos' range.
 template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false, bool kLowE = false>
 __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const double e, const double T0s, const double Ps,
-                                              const double rPs, const double* __restrict__ ktab, const double tab_min_m,
+                                              const double rPs, const double2* __restrict__ ktab, const double tab_min_m,
                                               const double2* __restrict__ sctab, double (&cE)[V], double (&sE)[V],
                                               double (&den)[V], double (&beta)[V], int* hi_acc = nullptr,
                                               int flag_known = -1)
@@ -924,15 +951,15 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
     for (int j = 0; j < V; j++) {
         M[j] = mean_anomaly<kDeferRange>(tsec[j], T0s, Ps, rPs, hi_acc);
         if (kLowE) {
-            E[j] = kepler_table_guess(ktab, M[j]);
+            E[j] = kepler_table_guess<!kDeferRange>(ktab, M[j]);
         } else if (ktab == nullptr) {
             E[j] = kepler_starter(M[j], e);
         } else if (window) {  // eccentric chain: the reference's own path inside the periastron window
             const double am = fabs(M[j]);
             const bool far = fmin(am, kTwoPi - am) >= tab_min_m;
-            E[j] = far ? kepler_table_guess(ktab, M[j]) : kepler_starter(M[j], e);
+            E[j] = far ? kepler_table_guess<!kDeferRange>(ktab, M[j]) : kepler_starter(M[j], e);
         } else {
-            E[j] = kepler_table_guess(ktab, M[j]);
+            E[j] = kepler_table_guess<!kDeferRange>(ktab, M[j]);
         }
     }
     // The reference always takes five Newton steps.  Once a step is below 2^-27 the next iterate
@@ -998,6 +1025,14 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
 // contact points (d == dc, d == R1 +- R2) h/R reaches 1 and a differently rounded h_sq
 // would turn asin() into NaN where the reference is finite (quirk Q10).  Only in-eclipse
 // samples come here, so the few extra instructions are free.
+// kGuard (the model pass): next to d == dc = sqrt(R1^2 - R2^2), h^2 comes out of a cancelling difference of numbers
+// ~4 d^2 R1^2 and its rounding noise can push h/R2 above 1 or R2^2 - h^2 below 0 -- by 8e-12 at R1/R2 = 300,
+// anywhere within 1.4e-8 dc of the contact.  Whether the reference returns NaN there is decided by the last bit of ITS
+// separation (libm tan/atan/sin/cos against the algebraic form here), i.e. it cannot be followed: a seeded scan met one
+// chain in 21 000 where this kernel had the NaN and the reference had not.  With the guard the model pass takes
+// the formula's limit (asin 1, sqrt 0) wherever only rounding left its domain; genuine NaN input still propagates
+// (every test is false on NaN), and the stand-alone entry point (hb_scalar op 5) keeps the reference's bits.
+template <bool kGuard = false>
 static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, double d)
 {
     const double R1s = __dmul_rn(R1, R1), R2s = __dmul_rn(R2, R2);
@@ -1013,11 +1048,19 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
         const double four_dd = __dmul_rn(__dmul_rn(4., d), d);
         const double a = __dmul_rn(__dmul_rn(four_dd, R1), R1);                 // 4 d d R1 R1
         const double b = __dadd_rn(__dsub_rn(dd, R2s), R1s);                    // d d - R2 R2 + R1 R1
-        const double h_sq = __ddiv_rn(__dsub_rn(a, __dmul_rn(b, b)), four_dd);
+        double h_sq = __ddiv_rn(__dsub_rn(a, __dmul_rn(b, b)), four_dd);
+        if (kGuard && h_sq < 0.0) h_sq = 0.0;
         const double h = sqrt(h_sq);
         const double hh = __dmul_rn(h, h);
-        const double A1 = __dsub_rn(__dmul_rn(R1s, asin(__ddiv_rn(h, R1))), __dmul_rn(h, sqrt(__dsub_rn(R1s, hh))));
-        const double A2 = __dsub_rn(__dmul_rn(R2s, asin(__ddiv_rn(h, R2))), __dmul_rn(h, sqrt(__dsub_rn(R2s, hh))));
+        double q1 = __ddiv_rn(h, R1), q2 = __ddiv_rn(h, R2), r1 = __dsub_rn(R1s, hh), r2 = __dsub_rn(R2s, hh);
+        if (kGuard) {
+            q1 = q1 > 1.0 ? 1.0 : q1;
+            q2 = q2 > 1.0 ? 1.0 : q2;
+            r1 = r1 < 0.0 ? 0.0 : r1;
+            r2 = r2 < 0.0 ? 0.0 : r2;
+        }
+        const double A1 = __dsub_rn(__dmul_rn(R1s, asin(q1)), __dmul_rn(h, sqrt(r1)));
+        const double A2 = __dsub_rn(__dmul_rn(R2s, asin(q2)), __dmul_rn(h, sqrt(r2)));
         area = partial_out ? __dadd_rn(A1, A2) : __dsub_rn(full, __dadd_rn(-A1, A2));
     }
     return area;
@@ -1026,7 +1069,7 @@ static __device__ __noinline__ double eclipse_area_dev(double R1, double R2, dou
 // Raw (un-normalised) template values Amag1 + Amag2 of likelihood3.c:649-675 at V samples
 // (tsec = t * 86400, formed once per data set).
 template <int V, bool kFullWarp, bool kSinTab = false, bool kDeferRange = false, bool kLowE = false>
-__device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __restrict__ ktab,
+__device__ __forceinline__ void raw_flux(const ChainConst& cc, const double2* __restrict__ ktab,
                                          const double2* __restrict__ sctab, const double (&tsec)[V], double (&u)[V],
                                          int* hi_acc = nullptr, int flag_known = -1)
 {
@@ -1061,7 +1104,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
             const double lim = cc.Rb + cc.Rs;
             const double d = fabs(rr * sqrt(proj2));
             if (!(d >= lim)) {
-                const double area = eclipse_area_dev(cc.Rb, cc.Rs, d);
+                const double area = eclipse_area_dev<true>(cc.Rb, cc.Rs, d);
                 const double zz = s * cc.si;  // sign of ZZ (likelihood3.c:173,669-670)
                 if (zz < 0.0) uj -= area * cc.ecl2;
                 else if (zz > 0.0) uj -= area * cc.ecl1;
@@ -1072,7 +1115,7 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double* __r
 }
 
 template <bool kFullWarp, bool kSinTab = false>
-__device__ __forceinline__ double raw_flux1(const ChainConst& cc, const double* __restrict__ ktab,
+__device__ __forceinline__ double raw_flux1(const ChainConst& cc, const double2* __restrict__ ktab,
                                             const double2* __restrict__ sctab, double tsec)
 {
     const double t[1] = {tsec};

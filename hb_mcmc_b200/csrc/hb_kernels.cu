@@ -133,6 +133,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// doubles pairs of the E(M) table that do not fit into candA
+constexpr int kKtabHead = 2 * kTableNodes - kCandA / 2 > 0 ? 2 * kTableNodes - kCandA / 2 : 1;
 struct EvalShared {
 #if HB_TMA_STAGING
     alignas(16) TileStage stage[kStages];
@@ -143,12 +145,17 @@ struct EvalShared {
     double red[2 * 32];
     double pivot;  // chi^2 expansion point u0 (a template value near the median)
     int bcast[4];  // block-wide broadcasts of the CTA that finishes a shared chain
-    double ktab[kTableSize];  // the chain's E(M) starter table (hb_device.cuh)
     double2 sctab[kSinTabN];  // {sin, cos}(2 pi k / 1024) for sincos_tab, copied once per CTA
+    // The chain's E(M) starter table (hb_device.cuh: kTableNodes x 32 bytes) begins here and runs on THROUGH candA: a
+    // chain that takes the table keeps its candidates in global scratch, and the select -- the other user of candA --
+    // only starts when the last model pass of the chain is over (the next chain builds its own table).
+    alignas(16) double2 ktab_head[kKtabHead];
     uint64_t candA[kCandA];
     uint64_t candB[kCandB];   // work area of the select; during the model pass: the running chi^2 sums [2][threads]
 };
 static_assert(kCandB * sizeof(uint64_t) >= 2 * kEvalThreads * sizeof(double), "candB holds the running sums of the pass");
+static_assert(offsetof(EvalShared, candA) == offsetof(EvalShared, ktab_head) + sizeof(double2) * kKtabHead,
+              "the E(M) table runs from ktab_head into candA without a gap");
 // four CTAs per SM: 228 KB of shared memory less 1 KB reserved per CTA
 static_assert(HB_TMA_STAGING || kEvalCtasPerSm != 4 || sizeof(EvalShared) <= 56 * 1024, "EvalShared no longer fits four CTAs per SM");
 
@@ -326,10 +333,10 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         if (tid == 0 && part == 0 && evaluated != nullptr) atomicAdd(evaluated, 1ull);
 
         // ---- E(M) starter table for chains whose solve is path-independent where the table is used ----
-        const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= 4 * kTableSize);
-        const double* ktab = use_table ? sm.ktab : nullptr;
+        const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= kTableMinN);
+        const double2* ktab = use_table ? sm.ktab_head : nullptr;
         if (use_table) {
-            build_kepler_table<kThreads>(sm.ktab, cc.e, sctab);
+            build_kepler_table<kThreads>(sm.ktab_head, cc.e, sctab);
         }
 
         // ---- pre-sample: bracket of the median rank + expansion point ----
@@ -347,7 +354,8 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             int r_lo, r_hi, r_mid;
             bracket_ranks(kThreads, N, krank, bracket_sigma, r_lo, r_hi, r_mid);
             const float frac = fminf(1.0f, (float)(r_hi - r_lo + 1) / (float)kThreads);
-            if (kShared || (int)(frac * (float)N * 1.5f) + 64 > kCandA) {  // survivors go to global scratch
+            // survivors go to global scratch (always when the E(M) table occupies candA)
+            if (kShared || use_table || (int)(frac * (float)N * 1.5f) + 64 > kCandA) {
                 cand = gbufB;
                 cand_cap = (int)key_stride;
                 cand_small = false;

@@ -89,11 +89,18 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out, 
     ChainConst cc;
     chain_prologue(p, default_mags(md, me, 1, 0), cc);
     // the kernel's starter table for chains with 0 <= e <= kTableMaxE (use_table != 0)
-    static double tab[kTableSize];
-    const double* ktab = nullptr;
+    static double2 tab[2 * kTableNodes];
+    const double2* ktab = nullptr;
     if ((use_table & 1) && cc.e >= 0.0 && cc.e <= kTableMaxE) {
-        for (int j = 0; j < kTableSolved; j++) tab[j] = kepler_table_node(j, cc.e);
-        for (int j = kTableSolved; j < kTableSize; j++) tab[j] = kTwoPi - tab[kTableN + 2 - j];
+        for (int k = 0; k < kTableSolved; k++) {
+            double2 a, b, am, bm;
+            kepler_table_node(k, cc.e, a, b);
+            kepler_table_mirror(a, b, am, bm);
+            tab[2 * (kTableN - k)] = am;
+            tab[2 * (kTableN - k) + 1] = bm;
+            tab[2 * k] = a;
+            tab[2 * k + 1] = b;
+        }
         ktab = tab;
     }
     long i = 0;

@@ -54,3 +54,23 @@ def test_pinned_outlier_chains(ctx, checker):
         got = ctx.loglikelihood(P)
         assert np.isfinite(got).all()
         assert rel_err(got, want).max() <= 1e-9
+
+
+def test_contact_chain_is_finite(ctx, checker):
+    """Quirk Q10 in the model pass: one sample of this pinned chain (set B, N = 20 000, seed 5902, chain 309) sits
+    1.2e-8 dc from the contact d = sqrt(R1^2 - R2^2), where the rounding noise of h^2 decides whether asin(h/R2) is
+    NaN.  The reference is finite; the kernel takes the formula's limit there (eclipse_area_dev<kGuard>) instead of
+    rolling the same dice with other bits -- it answered NaN on this chain before the guard."""
+    from hb_mcmc_b200 import workload as wl
+    rec = json.load(open(os.path.join(HERE, "golden", "contact_chain_v1.json")))[0]
+    truth = ps.TRUTHS[rec["truth"]]
+    t, fl, er = wl.make_dataset(rec["N"], truth, checker.calc_light_curve)
+    P = np.array([[float.fromhex(v) for v in rec["params"]]])
+    want = float.fromhex(rec["logL_ref"])
+    assert checker.loglikelihood_batch(t, fl, er, P)[0] == want
+    ctx.set_data(t, fl, er)
+    got = ctx.loglikelihood(P)[0]
+    assert np.isfinite(got) and abs(got - want) <= 1e-9 * abs(want), (got, want)
+    lc = ctx.light_curves(P)[0]
+    assert np.isfinite(lc).all()
+    assert abs(lc[rec["sample"]] - float.fromhex(rec["lc_ref_at_sample"])) < 1e-8

@@ -210,3 +210,22 @@ def test_prologue_flags(emul, orc, golden):
         assert (int(cc[i_flag]) & 1) == int(flag)
         R1, R2, T1, T2 = orc.radii_teffs(p)
         np.testing.assert_allclose(cc[i_info:i_info + 4], [R1, R2, T1, T2], rtol=1e-14)
+
+
+def test_contact_sample_takes_the_limit_of_the_area_formula(emul, orc):
+    """Quirk Q10 in the model pass (hb_device.cuh, eclipse_area_dev<kGuard>): the pinned chain of
+    tests/golden/contact_chain_v1.json has one sample 1.2e-8 dc from the contact d = sqrt(R1^2 - R2^2) of a 33 / 0.10
+    Rsun pair, where the rounding noise of h^2 decides whether asin(h/R2) is NaN.  The reference is finite there;
+    the device source must be too (it was NaN before the guard), and within the amplified-ulp bound of the tail."""
+    import json
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "contact_chain_v1.json")))[0]
+    p = np.array([float.fromhex(v) for v in rec["params"]])
+    t = wl.time_grid(rec["N"])
+    _, want = orc.calc_light_curve(t, p, raw=True)
+    assert np.isfinite(want).all()
+    for use_table in (3, 2, 1):
+        got = raw(emul, p, t, use_table)
+        assert np.isfinite(got).all(), (use_table, np.nonzero(~np.isfinite(got))[0][:5])
+        i = rec["sample"]
+        assert abs(got[i] - want[i]) < 1e-8 and np.abs(got - want).max() < 1e-8
+        assert np.abs(np.delete(got - want, i)).max() < 1e-12
