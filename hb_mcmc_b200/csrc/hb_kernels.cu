@@ -16,6 +16,22 @@
 #include "hb_select.cuh"
 #include "hb_device.cuh"
 
+// -DHB_PHASE_PROF (tools/phase_time.py, never in the product build): thread 0 of every CTA adds the clock64 cycles of
+// each per-chain phase of k_chain_eval to g_phase[] -- 0 table, 1 pre-sample, 2 model pass, 3 sums / hand-over, 4 select.
+#ifdef HB_PHASE_PROF
+__device__ unsigned long long g_phase[8];
+#define HB_T0() long long t_prev_ = clock64()
+#define HB_T(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase[k], (unsigned long long)(now_ - t_prev_)); t_prev_ = now_; } } while (0)
+extern "C" void hb_phase_read(unsigned long long* out)
+{
+    cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+}
+#else
+#define HB_T0() ((void)0)
+#define HB_T(k) ((void)0)
+#endif
 namespace hb {
 
 // ---------------------------------------------------------------------------
@@ -332,6 +348,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
         }
         if (tid == 0 && part == 0 && evaluated != nullptr) atomicAdd(evaluated, 1ull);
 
+        HB_T0();
         // ---- E(M) starter table for chains whose solve is path-independent where the table is used ----
         const bool use_table = (cc.e >= 0.0) && (cc.e <= kTableMaxE) && (N >= kTableMinN);
         const double2* ktab = use_table ? sm.ktab_head : nullptr;
@@ -339,6 +356,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             build_kepler_table<kThreads>(sm.ktab_head, cc.e, sctab);
         }
 
+        HB_T(0);
         // ---- pre-sample: bracket of the median rank + expansion point ----
         // small light curves fit the shared-memory candidate list whole: no bracket, no pre-sample
         const bool bracketed = N > kCandA / 2;
@@ -380,6 +398,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             }
             __syncthreads();
         }
+        HB_T(1);
         const double u0 = sm.pivot;
         const double A = cc.ft * (1.0 - cc.blend), ft = cc.ft;
 
@@ -613,6 +632,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             }
             // a Newton iterate left the table sincos' range somewhere in this chain (e -> 1 only): the sums are
             // not trustworthy; the chain is evaluated again with the per-sample check and the library fallback
+            HB_T(2);
             int redo = __syncthreads_or(hi_acc > hot_hi_limit);
             c_lt = block_sum_int<kThreads>(c_lt, sm.ctl.ired);
             if constexpr (kShared) {
@@ -663,6 +683,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             continue;
         }
 
+        HB_T(3);
         // ---- exact order statistic ----
         const uint32_t seed2 = (uint32_t)cc.seed ^ 0x9e3779b9u;
         uint64_t mkey;
@@ -684,6 +705,7 @@ k_chain_eval(const ChainConst* __restrict__ cc_all, int n_chains, const double* 
             }
             mkey = block_select_key<kThreads>(tmpl, N, krank, sm.ctl, bufs, 4, seed2);
         }
+        HB_T(4);
         const double med = dunkey(mkey);
 
         // ---- results ----
