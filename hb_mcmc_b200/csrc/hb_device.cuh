@@ -822,7 +822,10 @@ static __device__ __noinline__ void kepler_point_careful(double m, double e, dou
 // the table is the mirror image E(2 pi - M) = 2 pi - E(M) of the solved lower half).  Truncation error
 // (h/2)^4/24 E4 = 1.9e-10 E4: a third of what cubic Lagrange interpolation on 1024 intervals gave
 // (rounds 1-2) at half its arithmetic, so the warp-uniform exit of the Newton loop fires after ONE step
-// (two near periastron at the high end) instead of three to four from the reference starter.
+// (two near periastron at the high end) instead of three to four from the reference starter.  Measured
+// (tests/test_host_emul.py): |E0 - E| <= 1.8e-9 for every M at e <= 0.6 -- below the 2^-27 = 7.45e-9 of the
+// exit test, i.e. one step everywhere --, 1.1e-8 at e = 0.7 (0.15 % of M take a second step), 1.2e-7 at
+// e = 0.8 (1.2 %), 1.4e-7 at e = 0.95 outside the periastron window.
 constexpr int kTableN = 768;                   // intervals on [0, 2 pi]  (h = 2 pi / 768)
 constexpr int kTableNodes = kTableN + 1;       // nodes 0 .. kTableN
 constexpr int kTableSolved = kTableN / 2 + 1;  // nodes 0 .. kTableN/2 are solved, the rest mirrored

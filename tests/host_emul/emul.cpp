@@ -117,6 +117,22 @@ extern "C" void emul_raw(const double* p, const double* t, long n, double* out, 
                        : raw_flux1<false, false>(cc, ktab, sctab, __dmul_rn(t[i], kSecDay));
 }
 
+// the E(M) starter of the hot loop: the chain's Taylor table built as emul_raw builds it, evaluated at m[0..n)
+extern "C" void emul_table_guess(double e, const double* m, long n, double* out)
+{
+    static double2 tab[2 * kTableNodes];
+    for (int k = 0; k < kTableSolved; k++) {
+        double2 a, b, am, bm;
+        kepler_table_node(k, e, a, b);
+        kepler_table_mirror(a, b, am, bm);
+        tab[2 * (kTableN - k)] = am;
+        tab[2 * (kTableN - k) + 1] = bm;
+        tab[2 * k] = a;
+        tab[2 * k + 1] = b;
+    }
+    for (long i = 0; i < n; i++) out[i] = kepler_table_guess(tab, m[i]);
+}
+
 extern "C" void emul_finish(const double* u, long n, double med, double blend, double ft, double* out)
 {
     for (long i = 0; i < n; i++) out[i] = finish_template(u[i], med, blend, ft);

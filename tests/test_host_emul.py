@@ -229,3 +229,35 @@ def test_contact_sample_takes_the_limit_of_the_area_formula(emul, orc):
         i = rec["sample"]
         assert abs(got[i] - want[i]) < 1e-8 and np.abs(got - want).max() < 1e-8
         assert np.abs(np.delete(got - want, i)).max() < 1e-12
+
+
+def test_table_starter_is_within_one_newton_step_of_the_root(emul):
+    """The E(M) starter of the hot loop (hb_device.cuh: cubic Taylor polynomial about the nearest of 769 nodes).  The
+    warp-uniform exit of the Newton loop fires when a step is below 2^-27: the starter's error is that first step, so
+    'one step' needs |E0 - E| < 7.45e-9.  Asserted here for every M at e <= 0.6 (the bulk of prior draws), with the
+    measured bounds at e = 0.8 (two steps next to periastron) and, at e = 0.95, outside the 0.1 rad window in which the
+    table is not used; odd symmetry and the mirrored upper half are covered by the sign and range of M."""
+    emul.emul_table_guess.argtypes = [C.c_double, dp, C.c_long, dp]
+    rng = np.random.default_rng(11)
+    two_pi = 2 * 3.14159265358979323846
+    m = np.concatenate([rng.uniform(-two_pi, two_pi, 200000), np.linspace(0, two_pi, 7001)[:-1], [0.0, 1e-12, -1e-12, 3.14159265358979]])
+    m = m[np.abs(m) < two_pi]
+
+    def root(e, M):
+        E = M + e * np.sin(M)
+        for _ in range(60):
+            E = E - (E - e * np.sin(E) - M) / (1 - e * np.cos(E))
+        return E
+
+    worst = {}
+    for e in (0.0, 0.1, 0.3, 0.5, 0.6, 0.7, 0.8, 0.95):
+        out = np.empty_like(m)
+        emul.emul_table_guess(e, m.ctypes.data_as(dp), m.size, out.ctypes.data_as(dp))
+        err = np.abs(out - root(e, m))
+        if e > 0.8:  # window chains: the table serves |M| >= 0.1 rad from periastron only (kTableMinM)
+            am = np.abs(m)
+            err = err[np.minimum(am, two_pi - am) >= 0.1]
+        worst[e] = err.max()
+    assert all(worst[e] < 7.45e-9 for e in (0.0, 0.1, 0.3, 0.5, 0.6)), worst
+    # measured: 1.1e-8 at e = 0.7 (0.15 % of M take a second step), 1.2e-7 at 0.8 (1.2 %), 1.4e-7 at 0.95 outside the window
+    assert worst[0.7] < 2e-8 and worst[0.8] < 2e-7 and worst[0.95] < 3e-7, worst
