@@ -66,9 +66,13 @@ struct ChainConst {
     // with the two highest harmonics rewritten in c2 = cos 2x:  sin 3x = s (1 + 2 c2),  cos 4x = 2 c2^2 - 1
     //   c1 s + c3 s3 = s (q1 + q3 c2),          q1 = c1 + c3,  q3 = 2 c3
     //   d0 + d2 c2 + d4 c4 = r0 + c2 (d2 + r4 c2),  r0 = d0 - d4,  r4 = 2 d4
+    // STORED for h = c2 / 2 = c^2 - 1/2, which the sample loop forms in one operation (cos 2x takes two): a2, b1, d2
+    // and q3 hold twice, r4 four times the coefficient named above -- exact scalings, so every FMA of the polynomial
+    // rounds the very number it would round with c2.
     double K0, K1, a0, a1, a2, b0, b1, q1, q3, r0, d2, r4;
     // eclipse pre-test on squared quantities: (1 - e cos E)^2 (cos^2 i + sin^2 i c^2) < thr with
-    // c^2 = (1 + c2)/2: si2 = sin^2 i / 2, ci2 = cos^2 i + sin^2 i / 2, thr = ((R1 + R2)/ar)^2 (1 + 1e-9)
+    // c^2 = (1 + c2)/2 = 1/2 + h: si2 = sin^2 i (multiplies h), ci2 = cos^2 i + sin^2 i / 2, thr = ((R1 + R2)/ar)^2 (1 + 1e-9);
+    // tested as cos^2 i + sin^2 i c^2 < thr beta^2 (beta = 1/(1 - e cos E), whose square the flux needs anyway)
     double si2, ci2, thr;
     // eclipse (radii in Rsun, sorted big/small as eclipse_area does)
     double Rb, Rs, ecl1, ecl2;  // ecl_k = Norm_k / (pi R_k^2)
@@ -463,10 +467,12 @@ __device__ __forceinline__ void prologue_assemble_sections(const double* __restr
             }
         }
         if constexpr ((kSections & kAsmStarA) != 0) {
-            cc.K0 = K0; cc.K1 = K1; cc.a0 = a0; cc.a1 = a1; cc.a2 = a2; cc.b0 = b0; cc.b1 = b1;
+            // (the sample loop works with h = cos 2x / 2 = c^2 - 1/2, one operation less than cos 2x: the coefficients of
+            // cos 2x carry the factor 2 -- exact, so every FMA of the polynomial rounds the same number as before)
+            cc.K0 = K0; cc.K1 = K1; cc.a0 = a0; cc.a1 = a1; cc.a2 = 2.0 * a2; cc.b0 = b0; cc.b1 = 2.0 * b1;
         }
         if constexpr ((kSections & kAsmStarB) != 0) {
-            cc.q1 = c1 + c3; cc.q3 = 2.0 * c3; cc.r0 = d0 - d4; cc.d2 = d2; cc.r4 = 2.0 * d4;
+            cc.q1 = c1 + c3; cc.q3 = 4.0 * c3; cc.r0 = d0 - d4; cc.d2 = 2.0 * d2; cc.r4 = 8.0 * d4;  // (x 2 per power of h)
         }
     }
 
@@ -487,7 +493,7 @@ __device__ __forceinline__ void prologue_assemble_sections(const double* __restr
         const double Rb = fmax(R[0], R[1]), Rsm = fmin(R[0], R[1]);
         cc.Rb = Rb;
         cc.Rs = Rsm;
-        cc.si2 = 0.5 * si * si;
+        cc.si2 = 2.0 * (0.5 * si * si);  // (multiplies h = cos 2x / 2)
         cc.ci2 = ci * ci + 0.5 * si * si;
         {
             const double lim = (Rb + Rsm) / ar;
@@ -1088,19 +1094,22 @@ __device__ __forceinline__ void raw_flux(const ChainConst& cc, const double2* __
         const double X = cE[j] - cc.e;
         const double c = fma(-cc.swq, sE[j], cc.cw * X) * beta;  // cos(omega0 + nu)
         const double s = fma(cc.cwq, sE[j], cc.sw * X) * beta;   // sin(omega0 + nu)
-        const double c2 = fma(c + c, c, -1.0);                   // cos 2x
+        const double c2 = fma(c, c, -0.5);                       // h = cos 2x / 2 (the factor 2 sits in the coefficients)
 
         const double P5 = fma(fma(cc.r4, c2, cc.d2), c2, cc.r0);
         const double P4 = s * fma(cc.q3, c2, cc.q1);
         const double P3 = fma(cc.b1, c2, cc.b0);
         const double P2 = fma(cc.a2, c2, fma(cc.a1, s, cc.a0));
         const double poly = fma(beta, fma(beta, fma(beta, P5, P4), P3), P2);
-        double uj = fma(beta * beta, poly, fma(cc.K1, c, cc.K0));
+        const double bb = beta * beta;
+        double uj = fma(bb, poly, fma(cc.K1, c, cc.K0));
 
         // eclipse: the squared projected separation over a^2 against the chain's threshold (s^2 = 1 - c^2 to
         // rounding; the 1e-9 slack of thr absorbs that); the rare in-eclipse sample then forms the
         // separation exactly as the reference does (likelihood3.c:173-176, 365)
-        if (may_eclipse && den[j] * den[j] * fma(c2, cc.si2, cc.ci2) < cc.thr) {
+        // (den^2 g < thr as g < thr beta^2: beta^2 is there already, and den is not kept alive for the test -- the 1e-9
+        // slack of thr is seven orders of magnitude above what the two forms differ by)
+        if (may_eclipse && fma(c2, cc.si2, cc.ci2) < cc.thr * bb) {
             const double sc = s * cc.ci;
             const double proj2 = fma(c, c, sc * sc);
             const double rr = cc.ar * den[j];
