@@ -339,7 +339,10 @@ def gpu_arm(args, cfg, rank, local_rank, world):
     logL_dev = d_logL.cpu().numpy()
 
     # ---- end to end through the host-buffer C ABI ("e2e") ----
-    # page-locked host buffers, as the contract asks: the library DMAs them in place
+    # page-locked host buffers, as the contract asks.  The library moves them without a copy engine: k_prologue reads the
+    # parameter array over the bus (one coalesced read per chain, behind the other warps' libm work) and k_chain_eval
+    # writes logL into the result array; the same bytes cross the bus inside the timed region (HB_ZERO_COPY=0 in the
+    # environment selects cudaMemcpyAsync both ways: 25 us per step slower)
     P_pin = torch.from_numpy(P).clone().pin_memory()
     out_pin = torch.empty(n, dtype=torch.float64).pin_memory()
     P, out = P_pin.numpy(), out_pin.numpy()
@@ -384,7 +387,9 @@ def gpu_arm(args, cfg, rank, local_rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_block(args, cfg),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes), "d2h_bytes_per_step": int(out.nbytes)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                    "transfer": ("cudaMemcpyAsync both ways" if os.environ.get("HB_ZERO_COPY", "1")[:1] == "0" else
+                                 "in place: the kernels read the page-locked parameters and write the page-locked results over the bus")},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(t_begin, t_end),
             "roofline": roofline_block(args, n, N, k_ms, ms_per_step, peak_tf),

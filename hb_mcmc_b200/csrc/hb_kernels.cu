@@ -55,7 +55,13 @@ __global__ void __launch_bounds__(128, HB_PROLOGUE_BLOCKS) k_prologue(const doub
     if (c >= n) return;
     __shared__ ChainConst s_cc[4];
     ChainConst& cc = s_cc[threadIdx.x >> 5];
-    const double* p = params + (size_t)c * NPARS;
+    // the chain's parameters: ONE coalesced read into shared memory -- a caller's page-locked buffer is read in place
+    // (mapped host memory, hb_loglikelihood_batch), where every further access would cross the bus again
+    __shared__ double s_p[4][NPARS];
+    double* const sp = s_p[threadIdx.x >> 5];
+    if (lane < NPARS) sp[lane] = params[(size_t)c * NPARS + lane];
+    __syncwarp();
+    const double* p = sp;
     PrologueT T;
     prologue_trans_warp(p, ms, T, lane);
     if (lane == 0) prologue_assemble(p, ms, T, cc);

@@ -57,8 +57,9 @@ int hb_set_mags(hb_ctx* ctx, const double* mag_data, const double* magerr, int u
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* logL[c] = loglikelihood(t, flux, err, N, params[c], mag_data, magerr)   (likelihood3.c:809-873)
  * for c < n_chains; params row-major [n_chains][21].  Host buffers; returns after the result
- * is in logL.  Roche-overflow chains give exactly -5e14 (likelihood3.c:863-869).  Page-locked buffers
- * (cudaHostAlloc / cudaHostRegister) are DMA'd in place; pageable ones are staged in chunks. */
+ * is in logL.  Roche-overflow chains give exactly -5e14 (likelihood3.c:863-869).  When params and logL are both
+ * page-locked (cudaHostAlloc / cudaHostRegister) the kernels read and write them in place over the bus -- no copy
+ * (HB_ZERO_COPY=0 in the environment: cudaMemcpyAsync both ways); pageable ones are staged in chunks. */
 int hb_loglikelihood_batch(hb_ctx* ctx, const double* params, long n_chains, double* logL);
 /* Same with DEVICE buffers, asynchronous on the context's stream (no copies, no sync). */
 int hb_loglikelihood_batch_dev(hb_ctx* ctx, const double* d_params, long n_chains, double* d_logL);
