@@ -91,7 +91,9 @@ def test_context_reuse_across_data_sets(ctx, orc):
 
 
 def test_pinned_and_pageable_host_buffers_agree(ctx):
-    """hb_loglikelihood_batch DMAs page-locked caller buffers in place and stages pageable ones in chunks."""
+    """hb_loglikelihood_batch reads and writes page-locked caller buffers in place over the bus when both sides are
+    page-locked (k_prologue / k_chain_eval on mapped host memory, no copy), DMAs a page-locked input when only that side
+    is, and stages pageable ones in chunks: the same bits every way, below and above the small-batch limit."""
     import torch
     t, flux, err = wl.make_dataset(2000, wl.TRUTH_A, ctx.calc_light_curve)
     ctx.set_data(t, flux, err)
