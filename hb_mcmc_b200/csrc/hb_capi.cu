@@ -197,17 +197,6 @@ int choose_parts(const hb_ctx* ctx, long n_chains, long N, bool hot)
     return (nseg + spp - 1) / spp;             // parts that get at least one segment (need not divide nseg)
 }
 
-// true when p points into page-locked host memory the device can DMA from / to directly
-bool is_pinned_host(const void* p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();  // pageable memory reports an error on old drivers: clear it
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
 // The device's address of page-locked host memory it can read and write in place (cudaHostAlloc / cudaHostRegister
 // under unified addressing: torch pin_memory, the shim's own buffers), or nullptr.
 void* mapped_host(const void* p)
