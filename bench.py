@@ -137,6 +137,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def wait_first(self, timeout: float = 8.0):
+        """nvidia-smi needs up to a few seconds for its first line on a fresh box: do not start the timed region
+        (which may last only a fraction of a second) before the sampler delivers."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
@@ -148,9 +155,10 @@ class ClockSampler:
     def summary(self, t0: float, t1: float) -> dict:
         sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ts, line in self.rows:
-            if not (t0 <= ts <= t1 + 0.05):
-                continue
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.05]
+        if not rows:  # a timed region shorter than the sampling period: the samples around it
+            rows = [r for r in self.rows if t0 - 0.5 <= r[0] <= t1 + 0.5]
+        for ts, line in rows:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -309,6 +317,7 @@ def gpu_arm(args, cfg, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
         time.sleep(0.15)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

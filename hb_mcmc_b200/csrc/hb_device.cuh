@@ -988,13 +988,13 @@ __device__ __forceinline__ void kepler_points(const double (&tsec)[V], const dou
         for (int j = 0; j < V; j++) {
             const double num = fma(-e, sE[j], E[j]) - M[j];
             const double dn = fma(-e, cE[j], 1.0);
-            const double En = E[j] - div_fast(num, dn, yr[j]);
-            dE[j] = E[j] - En;  // the step actually applied (exact difference of neighbours)
-            E[j] = En;
+            dE[j] = div_fast(num, dn, yr[j]);  // the step: the next iterate is E - dE
             tiny &= (__double2hiint(dE[j]) & 0x7fffffff) < 0x3e400000;  // |dE| < 2^-27
         }
         tiny = warp_all<kFullWarp>(tiny);
-        if (tiny) break;
+        if (tiny) break;  // (E itself is not needed any more: sin/cos E follow from the step, below)
+#pragma unroll
+        for (int j = 0; j < V; j++) E[j] -= dE[j];
     }
     if (tiny) {
         // sin/cos(E_prev - dE) to first order (the neglected dE^2/2 < 3e-17 is relative), and
