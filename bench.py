@@ -52,12 +52,12 @@ NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 x 1.965 GHz
 CHAIN_CONST_BYTES = 47 * 8  # sizeof(ChainConst): what k_chain_eval reads per chain
 # From the committed `ncu --set full` capture of one k_chain_eval launch on C2 (profiles/r2_chain_eval_ncu_summary.txt,
 # tools/ncu_mix.py); only meaningful for the default workload:
-NCU_TRAFFIC_C2_BYTES = 2.803712e6 + 17.815296e6  # dram__bytes_read.sum + dram__bytes_write.sum
+NCU_TRAFFIC_C2_BYTES = 2.806016e6 + 18.314496e6  # dram__bytes_read.sum + dram__bytes_write.sum
 NCU_EXECUTED = {
-    "fp64_instr_per_point": 80.7,   # DFMA 48.4 + DMUL 16.6 + DADD 10.0 + DSETP 5.8 (warp instructions / 32 samples)
+    "fp64_instr_per_point": 78.7,   # DFMA 48.4 + DMUL 16.6 + DADD 10.0 + DSETP 3.8 (warp instructions / 32 samples)
     "flop_per_point": 123.4,        # 2 x DFMA + DMUL + DADD
-    "all_instr_per_point": 187.0,
-    "fp64_pipe_active": 0.573,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+    "all_instr_per_point": 186.0,
+    "fp64_pipe_active": 0.562,      # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
     "issue_active": 0.664,          # smsp__issue_active.avg.pct_of_peak_sustained_active
     "source": "profiles/r2_chain_eval_ncu_summary.txt",
 }

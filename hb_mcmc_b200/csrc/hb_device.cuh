@@ -757,6 +757,9 @@ __device__ __forceinline__ double fmod_twopi(double M, int* hi_acc = nullptr)
     // Adding `magic - 0.5` in round-to-nearest does NOT work: that constant is not representable.
     double q = __fma_rd(am, kMisc[1], kMagic) - kMagic;
     double r = fma(-q, kMisc[0], am);
+    // (one integer test on the sample's path instead of two FP64 compares: the high word of r is at or above that of
+    // 2 pi for r < 0, NaN and the last 2e-6 below 2 pi -- the exact test follows only then)
+    if ((unsigned)__double2hiint(r) >= 0x401921fbu)
     if (!(r >= 0.0 && r < kMisc[0])) {
         // rare: quotient off by one (|M| within rounding of a multiple of 2 pi) -- repaired in line, so that the
         // sample loop does not marshal registers around a call at every sample -- or huge / inf / NaN input
